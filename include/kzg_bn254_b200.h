@@ -1,0 +1,176 @@
+/*
+ * kzg_bn254_b200 -- C ABI of the B200-native engine for the commitment hot path of
+ * Layr-Labs/rust-kzg-bn254 (BN254 G1 MSM over the SRS, Fr (I)NTT, and the Fr glue of
+ * KZG::commit_* / compute_blob_proof / the RLC step of verify_blob_kzg_proof_batch).
+ *
+ * The reference has no FFI of its own (pure Rust on arkworks); each entry point below cites
+ * the reference interface it replaces (paths relative to the reference repo).  A Rust shim
+ *  binds these with `extern "C"` and keeps the crates' public API.
+ *
+ * Conventions
+ *  - Fr / Fq : 4 x u64 little-endian limbs in MONTGOMERY form (R = 2^256) -- the in-memory
+ *    layout of arkworks' Fp<MontBackend<_,4>,4>, so `&[Fr]` passes as `*const u64`.
+ *  - G1 affine : x || y (8 x u64, Montgomery), identity = all-zero words (the shim maps
+ *    arkworks' `infinity: bool` to/from this).
+ *  - Compressed G1 in SRS files: gnark big-endian 32 B (primitives/src/helpers.rs:175-226).
+ *  - All host buffers are caller-owned; the library copies in/out and never keeps a host
+ *    pointer after return.  `_dev` variants take CUDA device pointers instead.
+ *  - Return value: KZGB_OK (0) or a negative kzgb_status that maps 1:1 onto the reference's
+ *    KzgError variants (primitives/src/errors.rs:32-86); kzgb_last_error() has the message
+ *    text the reference uses.
+ *  - A context is bound to one CUDA device; calls on one context are serialised internally.
+ *    There is no CPU fallback: every call fails with KZGB_ERR_DEVICE if the GPU is unusable.
+ */
+#ifndef KZG_BN254_B200_H
+#define KZG_BN254_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct kzgb_ctx kzgb_ctx;
+
+typedef enum kzgb_status {
+    KZGB_OK = 0,
+    KZGB_ERR_GENERIC = -1,               /* KzgError::GenericError(String) */
+    KZGB_ERR_SRS_CAPACITY = -2,          /* KzgError::SrsCapacityExceeded { polynomial_len, srs_len } (kzg.rs:89-94) */
+    KZGB_ERR_SERIALIZATION = -3,         /* KzgError::SerializationError (kzg.rs:112-116) */
+    KZGB_ERR_FFT = -4,                   /* KzgError::FFTError (kzg.rs:265-269) */
+    KZGB_ERR_NOT_ON_CURVE = -5,          /* KzgError::NotOnCurveError (helpers.rs:694-708, :204-209) */
+    KZGB_ERR_MSM = -6,                   /* KzgError::MsmError / CommitError (helpers.rs:332, kzg.rs:102) */
+    KZGB_ERR_INVALID_INPUT_LENGTH = -7,  /* KzgError::InvalidInputLength (helpers.rs:485-487) */
+    KZGB_ERR_DESERIALIZATION = -8,       /* KzgError::DeserializationError (helpers.rs:176-195) */
+    KZGB_ERR_INVALID_FIELD_ELEMENT = -9, /* KzgError::InvalidFieldElement (helpers.rs:784-811) */
+    KZGB_ERR_DEVICE = -100               /* CUDA failure -> KzgError::GenericError(<cuda string>) */
+} kzgb_status;
+
+/* ---- context ------------------------------------------------------------------------- */
+/* device: CUDA ordinal.  stream: optional cudaStream_t to run on (NULL = the context creates its own). */
+int kzgb_ctx_create(kzgb_ctx** out, int device, void* stream);
+void kzgb_ctx_destroy(kzgb_ctx* ctx);
+const char* kzgb_last_error(const kzgb_ctx* ctx);
+/* Block until all work queued by this context has finished. */
+int kzgb_sync(kzgb_ctx* ctx);
+
+/* ---- SRS (prover/src/srs.rs:11-49 `SRS`, `SRS::new`) ------------------------------------ */
+/* Load the first `points_to_load` points of a g1.point file (32 B gnark-BE each).  Replaces
+ * SRS::new(path, order, points_to_load) (srs.rs:35-49) incl. its `points_to_load > order` error. */
+int kzgb_srs_load_file(kzgb_ctx* ctx, const char* path, uint32_t order, uint32_t points_to_load);
+/* Same from memory (replaces parallel_read_g1_points + read_g1_point_from_bytes_be, srs.rs:81-138). */
+int kzgb_srs_load_gnark_be(kzgb_ctx* ctx, const uint8_t* bytes, size_t n_points);
+/* From an existing `SRS.g1` slice: n x (x||y) Montgomery words; inf[i] != 0 marks the identity (may be NULL). */
+int kzgb_srs_load_affine_mont(kzgb_ctx* ctx, const uint64_t* xy, const uint8_t* inf, size_t n_points);
+/* Synthetic SRS_i = tau^i * G generated on the GPU (benches/tests; tau: 4 words Montgomery). */
+int kzgb_srs_load_synthetic(kzgb_ctx* ctx, const uint64_t tau_mont[4], size_t n_points);
+/* Number of monomial points resident (== SRS.g1.len()). */
+size_t kzgb_srs_len(const kzgb_ctx* ctx);
+/* Read back decompressed points [start, start+count) to fill `SRS.g1` (pub field, srs.rs:13). */
+int kzgb_srs_get_affine_mont(kzgb_ctx* ctx, size_t start, size_t count, uint64_t* out_xy, uint8_t* out_inf);
+/* Build the fixed-base window tables (2^(c*w) * P_i) for MSMs of up to `max_n` points.  Called lazily
+ * by the first commit if the caller does not; window_bits = 0 picks c from max_n. */
+int kzgb_srs_precompute(kzgb_ctx* ctx, size_t max_n, int window_bits);
+
+/* ---- MSM (ark-ec VariableBaseMSM::msm call sites) ---------------------------------------- */
+/* sum scalars[i] * SRS[i], i < n.  Replaces G1Projective::msm(&srs.g1[..n], coeffs) in
+ * KZG::commit_coeff_form (prover/src/kzg.rs:107-125). */
+int kzgb_msm_srs(kzgb_ctx* ctx, const uint64_t* scalars_mont, size_t n, uint64_t out_xy[8], uint8_t* out_inf);
+/* Same over a point range [first, first+n) of the SRS (point-range sharding of a large MSM). */
+int kzgb_msm_srs_range(kzgb_ctx* ctx, const uint64_t* scalars_mont, size_t first, size_t n, uint64_t out_xy[8],
+                       uint8_t* out_inf);
+/* Variable-base MSM.  Replaces helpers::g1_lincomb (primitives/src/helpers.rs:328-337). */
+int kzgb_msm_var(kzgb_ctx* ctx, const uint64_t* bases_xy, const uint8_t* bases_inf, const uint64_t* scalars_mont,
+                 size_t m, uint64_t out_xy[8], uint8_t* out_inf);
+/* Adds two affine points on the host side of the library (partial-sum reduction of sharded MSMs). */
+int kzgb_g1_add(const uint64_t a_xy[8], uint8_t a_inf, const uint64_t b_xy[8], uint8_t b_inf, uint64_t out_xy[8],
+                uint8_t* out_inf);
+
+/* ---- Fr (I)NTT (ark-poly fft/ifft at primitives/src/polynomial.rs:131-135, 242-246) -------- */
+/* In place, natural order in and out; n must be a power of two (<= 2^28). inverse != 0 -> ifft (with 1/n). */
+int kzgb_ntt_fr(kzgb_ctx* ctx, uint64_t* inout_mont, size_t n, int inverse);
+
+/* ---- bytes <-> Fr (primitives/src/helpers.rs:40-57 to_fr_array, :80-119 to_byte_array) ----- */
+/* out has ceil(len/32) elements */
+int kzgb_to_fr_array(kzgb_ctx* ctx, const uint8_t* bytes, size_t len, uint64_t* out_mont);
+int kzgb_to_byte_array(kzgb_ctx* ctx, const uint64_t* fr_mont, size_t n, uint8_t* out_be);
+
+/* ---- commitments (prover/src/kzg.rs) ------------------------------------------------------ */
+/* KZG::commit_eval_form (kzg.rs:84-104): n evaluations (power of two).  Err KZGB_ERR_SRS_CAPACITY if n > srs_len. */
+int kzgb_commit_eval(kzgb_ctx* ctx, const uint64_t* evals_mont, size_t n, uint64_t out_xy[8], uint8_t* out_inf);
+/* KZG::commit_coeff_form (kzg.rs:107-125).  Err KZGB_ERR_SERIALIZATION if n > srs_len. */
+int kzgb_commit_coeff(kzgb_ctx* ctx, const uint64_t* coeffs_mont, size_t n, uint64_t out_xy[8], uint8_t* out_inf);
+/* KZG::commit_blob (kzg.rs:182-185): blob.data() bytes (32 B big-endian elements). */
+int kzgb_commit_blob(kzgb_ctx* ctx, const uint8_t* blob, size_t len, uint64_t out_xy[8], uint8_t* out_inf);
+/* KZG::g1_ifft (kzg.rs:263-285): Lagrange-basis SRS of size n (natural order).  Err KZGB_ERR_FFT if n is not 2^k. */
+int kzgb_g1_ifft(kzgb_ctx* ctx, size_t n, uint64_t* out_xy, uint8_t* out_inf);
+
+/* ---- proofs ------------------------------------------------------------------------------- */
+/* KZG::compute_proof / compute_proof_impl (kzg.rs:128-178, 215-234): evaluation-form polynomial,
+ * caller-supplied z (Montgomery).  Optionally returns y = p(z) (Montgomery) if y_out != NULL. */
+int kzgb_compute_proof(kzgb_ctx* ctx, const uint64_t* evals_mont, size_t n, const uint64_t z_mont[4],
+                       uint64_t out_xy[8], uint8_t* out_inf, uint64_t y_out[4]);
+/* helpers::evaluate_polynomial_in_evaluation_form (primitives/src/helpers.rs:475-535). */
+int kzgb_evaluate_polynomial(kzgb_ctx* ctx, const uint64_t* evals_mont, size_t n, const uint64_t z_mont[4],
+                             uint64_t y_out[4]);
+/* helpers::compute_challenge (helpers.rs:411-472): Fiat-Shamir z for (blob, commitment). */
+int kzgb_compute_challenge(kzgb_ctx* ctx, const uint8_t* blob, size_t len, const uint64_t c_xy[8], uint8_t c_inf,
+                           uint64_t z_out_mont[4]);
+/* KZG::compute_blob_proof (kzg.rs:288-309): validates the commitment, derives z, proves. */
+int kzgb_compute_blob_proof(kzgb_ctx* ctx, const uint8_t* blob, size_t len, const uint64_t c_xy[8], uint8_t c_inf,
+                            uint64_t out_xy[8], uint8_t* out_inf);
+
+/* ---- batches (blob-sharded hot path) ------------------------------------------------------ */
+/* commit_blob + compute_blob_proof for `count` blobs, pipelined (H2D, GPU, host SHA-256 overlap).
+ * commitments / proofs: count x 32 B arkworks `serialize_compressed` bytes (the encoding the
+ * reference feeds to its transcripts, helpers.rs:457-461).  Blob pointers are HOST memory. */
+int kzgb_commit_and_prove_blobs(kzgb_ctx* ctx, const uint8_t* const* blobs, const size_t* lens, size_t count,
+                                uint8_t* commitments32, uint8_t* proofs32);
+/* Same with blob bytes already resident in device memory (host copies are still needed for the
+ * SHA-256 transcript; pass them in `blobs_host`). */
+int kzgb_commit_and_prove_blobs_dev(kzgb_ctx* ctx, const uint8_t* const* blobs_dev, const uint8_t* const* blobs_host,
+                                    const size_t* lens, size_t count, uint8_t* commitments32, uint8_t* proofs32);
+
+/* ---- batch verification, everything before the pairing (verifier/src/batch.rs:16-249) ------ */
+/* Per-blob challenge z_i and evaluation y_i (helpers.rs:613-662), RLC scalar r and its powers
+ * (batch.rs:76-168), and the three linear combinations (batch.rs:225-249).  Outputs the two G1
+ * inputs of the final pairing check e(lhs, [tau]G2) == e(rhs, G2) (batch.rs:253-254), which stays
+ * in the reference's code.  Points in/out: x||y Montgomery + identity flags. */
+int kzgb_verify_batch_rlc(kzgb_ctx* ctx, const uint8_t* const* blobs, const size_t* lens, size_t count,
+                          const uint64_t* commitments_xy, const uint8_t* commitments_inf, const uint64_t* proofs_xy,
+                          const uint8_t* proofs_inf, uint64_t lhs_xy[8], uint8_t* lhs_inf, uint64_t rhs_xy[8],
+                          uint8_t* rhs_inf);
+
+/* ---- point codecs (host) ------------------------------------------------------------------ */
+/* arkworks CanonicalSerialize::serialize_compressed of a G1Affine (helpers.rs:458-460). */
+int kzgb_g1_serialize_compressed(const uint64_t xy[8], uint8_t inf, uint8_t out32[32]);
+/* gnark big-endian compressed (the g1.point format). */
+int kzgb_g1_to_gnark_be(const uint64_t xy[8], uint8_t inf, uint8_t out32[32]);
+/* helpers::validate_g1_point (helpers.rs:694-708) for `n` points on the GPU. */
+int kzgb_validate_g1_points(kzgb_ctx* ctx, const uint64_t* xy, const uint8_t* inf, size_t n);
+
+/* ---- measurement hooks (bench.py) ---------------------------------------------------------- */
+/* Runs an integer-pipe microbenchmark and returns achieved operations per second.
+ * kind 0: IMAD, 1: IMAD.WIDE, 2: carry-chained IMAD.WIDE.X, 3: Fq Montgomery multiplications. */
+int kzgb_microbench(kzgb_ctx* ctx, int kind, double* ops_per_second);
+/* Times `reps` back-to-back SRS MSMs of n points on device-resident scalars with CUDA events on the
+ * context's stream; returns mean milliseconds per MSM of the whole pipeline and of the bucket
+ * accumulation kernel alone. */
+int kzgb_bench_msm(kzgb_ctx* ctx, size_t n, int reps, double* ms_total, double* ms_accumulate);
+/* Number of kernels this library has launched since it was loaded. */
+uint64_t kzgb_launch_count(const kzgb_ctx* ctx);
+/* Device-side stopwatch (CUDA events) spanning every stream of the context: all work queued between
+ * begin and end lies inside the measured interval. */
+int kzgb_timer_begin(kzgb_ctx* ctx);
+int kzgb_timer_end(kzgb_ctx* ctx, double* ms_out);
+/* Bucket-accumulation kernel statistics since the last reset: summed CUDA-event duration of the
+ * launches (each bracketed on its own stream), launch count, and point additions performed. */
+int kzgb_stats(kzgb_ctx* ctx, double* acc_ms, uint64_t* acc_launches, uint64_t* acc_point_adds, int reset);
+/* Fixed-base table in use: window bits c, windows W, points covered (0 = none). */
+int kzgb_msm_config(const kzgb_ctx* ctx, int* window_bits, int* windows, size_t* table_points);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KZG_BN254_B200_H */

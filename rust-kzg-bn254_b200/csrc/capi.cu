@@ -1,0 +1,1210 @@
+// Host orchestration and the C ABI (include/kzg_bn254_b200.h).
+//
+// One context = one GPU.  The context owns the HBM-resident SRS (monomial points plus the
+// fixed-base window tables), the omega_N twiddle table, and a small set of "lanes": a lane is a
+// CUDA stream with its own device workspace, driven by one host thread.  Single calls use
+// lane 0; the blob-batch entry points run several lanes plus a pool of host threads that hash
+// the Fiat-Shamir transcripts (SHA-256 of a 16 MiB blob is ~9 ms of inherently serial CPU work,
+// several times the GPU time of the same blob, so it must overlap).
+#include <algorithm>
+#include <condition_variable>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/kzg_bn254_b200.h"
+#include "kzgb_internal.hpp"
+#include "sha256.hpp"
+
+namespace kzgb {
+std::atomic<uint64_t> g_launch_count{0};
+}
+using namespace kzgb;
+
+namespace {
+
+constexpr int MAX_LANES = 4;
+constexpr int MAX_SETS = 96;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = (bytes + (1u << 20) - 1) & ~(size_t)((1u << 20) - 1);
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct Lane {
+    cudaStream_t st = nullptr;
+    bool own_stream = false;
+    DevBuf bytes, evals, work, ntt_scratch, eval_scratch, msm_ws, small, bases;
+    XYZZ* h_sets = nullptr;   // pinned
+    Fr* h_fr = nullptr;       // pinned, 16 elements
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_done = nullptr;
+    bool ev_pending = false;
+    double acc_ms = 0;        // summed duration of bucket-accumulation kernels
+    uint64_t acc_launches = 0;
+    uint64_t acc_adds = 0;    // point additions those kernels performed (n * W upper bound)
+};
+
+}  // namespace
+
+struct kzgb_ctx {
+    int device = 0;
+    std::mutex mu;
+    std::string err;
+    Lane lanes[MAX_LANES];
+    int n_lanes = 0;
+    // SRS
+    Affine* srs = nullptr;
+    size_t srs_n = 0;
+    Affine* wtable = nullptr;
+    size_t wt_n = 0;
+    int wt_c = 0, wt_W = 0;
+    bool auto_precompute = true;
+    // twiddles
+    Fr* tw = nullptr;
+    int logN = 0;
+    // timer
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+};
+
+namespace {
+
+std::mutex g_err_mu;
+int fail(kzgb_ctx* c, int code, const std::string& msg) {
+    if (c) { std::lock_guard<std::mutex> lk(g_err_mu); c->err = msg; }
+    return code;
+}
+#define CK(ctx, call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(ctx, KZGB_ERR_DEVICE, std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #call); \
+    } while (0)
+
+// ---------------------------------------------------------------- host field helpers
+const uint32_t ROOT28_CANON[8] = {0x725b19f0u, 0x9bd61b6eu, 0x41112ed4u, 0x402d111eu,
+                                  0x8ef62abcu, 0x00e0a7ebu, 0xa58a7e85u, 0x2a3c09f0u};  // consts.rs:51
+
+Fr root_of_unity_mont(int k) {  // PRIMITIVE_ROOTS_OF_UNITY[k], Montgomery
+    Fr w;
+    memcpy(w.l, ROOT28_CANON, 32);
+    fe_to_mont(w, w);
+    for (int i = 28; i > k; i--) fe_sqr(w, w);
+    return w;
+}
+Fr fr_from_u64(uint64_t v) {
+    Fr a; fe_zero(a);
+    a.l[0] = (uint32_t)v; a.l[1] = (uint32_t)(v >> 32);
+    fe_to_mont(a, a);
+    return a;
+}
+Fr ninv_mont(int logn) {
+    Fr n = fr_from_u64(1ull << logn), r;
+    fe_inv(r, n);
+    return r;
+}
+// 32 big-endian bytes (any value) -> Fr Montgomery, reduced mod r
+Fr fr_from_be_bytes(const uint8_t* b) {
+    Fr a;
+    for (int k = 0; k < 8; k++)
+        a.l[7 - k] = ((uint32_t)b[4 * k] << 24) | ((uint32_t)b[4 * k + 1] << 16) | ((uint32_t)b[4 * k + 2] << 8) | b[4 * k + 3];
+    fe_to_mont(a, a);
+    return a;
+}
+template <int F>
+void fe_to_be_bytes(const Fe<F>& mont, uint8_t* out) {
+    Fe<F> c; fe_from_mont(c, mont);
+    for (int k = 0; k < 8; k++) {
+        uint32_t w = c.l[7 - k];
+        out[4 * k] = (uint8_t)(w >> 24); out[4 * k + 1] = (uint8_t)(w >> 16);
+        out[4 * k + 2] = (uint8_t)(w >> 8); out[4 * k + 3] = (uint8_t)w;
+    }
+}
+int log2_exact(size_t n) {
+    int k = 0;
+    while (((size_t)1 << k) < n) k++;
+    return k;
+}
+size_t next_pow2(size_t n) { size_t p = 1; while (p < n) p <<= 1; return p; }
+
+void affine_to_abi(const Affine& a, uint64_t out_xy[8], uint8_t* out_inf) {
+    memcpy(out_xy, &a, 64);
+    if (out_inf) *out_inf = aff_is_inf(a) ? 1 : 0;
+}
+Affine affine_from_abi(const uint64_t xy[8], uint8_t inf) {
+    Affine a;
+    if (inf) aff_set_inf(a); else memcpy(&a, xy, 64);
+    return a;
+}
+// arkworks serialize_compressed (reference primitives/src/helpers.rs:458-460)
+void serialize_compressed(const Affine& a, uint8_t out[32]) {
+    memset(out, 0, 32);
+    if (aff_is_inf(a)) { out[31] = 0x40; return; }
+    Fq xc; fe_from_mont(xc, a.x);
+    memcpy(out, xc.l, 32);
+    if (fe_lexicographically_largest(a.y)) out[31] |= 0x80;  // y > -y  <=>  y > (p-1)/2
+}
+void to_gnark_be(const Affine& a, uint8_t out[32]) {
+    if (aff_is_inf(a)) { memset(out, 0, 32); out[0] = 0x40; return; }
+    fe_to_be_bytes(a.x, out);
+    out[0] |= fe_lexicographically_largest(a.y) ? 0xC0 : 0x80;
+}
+
+// ---------------------------------------------------------------- plan heuristics
+int choose_c_var(size_t n) {
+    int best = 4; double bc = 1e300;
+    for (int c = 4; c <= 20; c++) {
+        int W = (255 + c - 1) / c;
+        if (W > MAX_SETS) continue;
+        double cost = (double)n * W * 10.0 + (double)W * (double)(1u << (c - 1)) * 40.0;
+        if (cost < bc) { bc = cost; best = c; }
+    }
+    return best;
+}
+int choose_c_fixed(size_t n) {
+    int best = 4; double bc = 1e300;
+    for (int c = 4; c <= 16; c++) {
+        int W = (255 + c - 1) / c;
+        double cost = (double)n * W * 10.0 + (double)(1u << (c - 1)) * 160.0;  // the bucket tail is latency-bound
+        if (cost < bc) { bc = cost; best = c; }
+    }
+    return best;
+}
+
+// ---------------------------------------------------------------- lanes
+int lane_init(kzgb_ctx* c, Lane& L, cudaStream_t st) {
+    if (st) { L.st = st; L.own_stream = false; }
+    else { CK(c, cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking)); L.own_stream = true; }
+    CK(c, cudaMallocHost((void**)&L.h_sets, sizeof(XYZZ) * MAX_SETS));
+    CK(c, cudaMallocHost((void**)&L.h_fr, sizeof(Fr) * 16));
+    CK(c, cudaEventCreate(&L.ev0));
+    CK(c, cudaEventCreate(&L.ev1));
+    CK(c, cudaEventCreateWithFlags(&L.ev_done, cudaEventDisableTiming));
+    return KZGB_OK;
+}
+void lane_destroy(Lane& L) {
+    L.bytes.release(); L.evals.release(); L.work.release(); L.ntt_scratch.release();
+    L.eval_scratch.release(); L.msm_ws.release(); L.small.release(); L.bases.release();
+    if (L.h_sets) cudaFreeHost(L.h_sets);
+    if (L.h_fr) cudaFreeHost(L.h_fr);
+    if (L.ev0) cudaEventDestroy(L.ev0);
+    if (L.ev1) cudaEventDestroy(L.ev1);
+    if (L.ev_done) cudaEventDestroy(L.ev_done);
+    if (L.own_stream && L.st) cudaStreamDestroy(L.st);
+    L = Lane();
+}
+int ensure_lanes(kzgb_ctx* c, int want) {
+    if (want > MAX_LANES) want = MAX_LANES;
+    while (c->n_lanes < want) {
+        int rc = lane_init(c, c->lanes[c->n_lanes], nullptr);
+        if (rc) return rc;
+        c->n_lanes++;
+    }
+    return KZGB_OK;
+}
+void lane_collect_acc(Lane& L) {
+    if (L.ev_pending) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, L.ev0, L.ev1) == cudaSuccess) { L.acc_ms += ms; L.acc_launches++; }
+        L.ev_pending = false;
+    }
+}
+
+// ---------------------------------------------------------------- twiddles
+int ensure_twiddles(kzgb_ctx* c, int logn) {
+    if (c->tw && logn <= c->logN) return KZGB_OK;
+    int want = std::max(logn, 1);
+    if (c->srs_n) want = std::max(want, log2_exact(next_pow2(c->srs_n)) > 28 ? 28 : log2_exact(next_pow2(c->srs_n)));
+    if (want > 28) return fail(c, KZGB_ERR_GENERIC, "power must be <= 28");
+    for (int i = 0; i < c->n_lanes; i++) CK(c, cudaStreamSynchronize(c->lanes[i].st));
+    if (c->tw) { cudaFree(c->tw); c->tw = nullptr; }
+    CK(c, cudaMalloc((void**)&c->tw, sizeof(Fr) * ((size_t)1 << (want - 1))));
+    Fr w = root_of_unity_mont(want);
+    ntt_twiddles_launch(c->tw, want, &w, c->lanes[0].st);
+    CK(c, cudaStreamSynchronize(c->lanes[0].st));
+    c->logN = want;
+    return KZGB_OK;
+}
+
+// ---------------------------------------------------------------- SRS tables
+int do_precompute(kzgb_ctx* c, size_t max_n, int window_bits) {
+    if (max_n > c->srs_n) max_n = c->srs_n;
+    if (max_n == 0) return KZGB_OK;
+    int cb = window_bits > 0 ? window_bits : choose_c_fixed(max_n);
+    if (cb < 2 || cb > 24) return fail(c, KZGB_ERR_GENERIC, "window_bits out of range");
+    int W = (255 + cb - 1) / cb;
+    size_t bytes = (size_t)W * max_n * sizeof(Affine);
+    size_t free_b = 0, total_b = 0;
+    CK(c, cudaMemGetInfo(&free_b, &total_b));
+    if (bytes + (2ull << 30) > free_b + (c->wtable ? (size_t)c->wt_W * c->wt_n * sizeof(Affine) : 0))
+        return fail(c, KZGB_ERR_DEVICE, "not enough device memory for the fixed-base window tables");
+    Lane& L = c->lanes[0];
+    for (int i = 0; i < c->n_lanes; i++) CK(c, cudaStreamSynchronize(c->lanes[i].st));
+    if (c->wtable) { cudaFree(c->wtable); c->wtable = nullptr; c->wt_n = 0; }
+    CK(c, cudaMalloc((void**)&c->wtable, bytes));
+    CK(c, cudaMemcpyAsync(c->wtable, c->srs, max_n * sizeof(Affine), cudaMemcpyDeviceToDevice, L.st));
+    uint32_t batch = (uint32_t)std::min<size_t>(max_n, (size_t)1 << 18);
+    DevBuf scratch;
+    CK(c, scratch.reserve(srs_precompute_scratch_bytes(batch, W)));
+    srs_precompute_launch(c->wtable, (uint32_t)max_n, (uint32_t)max_n, cb, W, (XYZZ*)scratch.p, batch, L.st);
+    cudaError_t e = cudaStreamSynchronize(L.st);
+    scratch.release();
+    CK(c, e);
+    CK(c, cudaGetLastError());
+    c->wt_n = max_n; c->wt_c = cb; c->wt_W = W;
+    return KZGB_OK;
+}
+
+int srs_install(kzgb_ctx* c, Affine* dev_points, size_t n) {
+    for (int i = 0; i < c->n_lanes; i++) cudaStreamSynchronize(c->lanes[i].st);
+    if (c->srs) cudaFree(c->srs);
+    if (c->wtable) { cudaFree(c->wtable); c->wtable = nullptr; c->wt_n = 0; }
+    c->srs = dev_points;
+    c->srs_n = n;
+    return KZGB_OK;
+}
+
+// ---------------------------------------------------------------- MSM
+struct MsmJob {
+    MsmPlan plan;
+    bool active = false;
+};
+
+// Enqueue an MSM on lane L.  bases == nullptr: over the SRS range [first, first+n).
+int msm_enqueue(kzgb_ctx* c, Lane& L, const Fr* d_scalars, bool canonical, size_t first, size_t n,
+                const Affine* var_bases, MsmJob* job) {
+    if (n == 0) { job->active = false; return KZGB_OK; }
+    MsmPlan p;
+    const Affine* table;
+    if (!var_bases) {
+        if (first + n > c->srs_n) return fail(c, KZGB_ERR_GENERIC, "MSM range exceeds the SRS");
+        if (c->auto_precompute && (!c->wtable || first + n > c->wt_n) && c->srs_n <= ((size_t)1 << 22)) {
+            size_t want = std::min(c->srs_n, next_pow2(first + n));
+            int rc = do_precompute(c, want, 0);
+            if (rc && rc != KZGB_ERR_DEVICE) return rc;
+        }
+        if (c->wtable && first + n <= c->wt_n) {
+            p = msm_make_plan((uint32_t)n, c->wt_c, true, (uint32_t)c->wt_n, (uint32_t)first);
+            table = c->wtable;
+        } else {
+            p = msm_make_plan((uint32_t)n, choose_c_var(n), false, 0, 0);
+            table = c->srs + first;
+        }
+    } else {
+        p = msm_make_plan((uint32_t)n, choose_c_var(n), false, 0, 0);
+        table = var_bases;
+    }
+    if ((uint64_t)n * p.W >= 0xfff00000ull) return fail(c, KZGB_ERR_GENERIC, "MSM too large for one launch");
+    CK(c, L.msm_ws.reserve(msm_workspace_bytes(p)));
+    MsmWorkspace ws;
+    msm_workspace_carve(p, L.msm_ws.p, &ws);
+    lane_collect_acc(L);
+    msm_launch(p, ws, d_scalars, canonical, table, L.st, L.ev0, L.ev1);
+    L.ev_pending = true;
+    L.acc_adds += (uint64_t)n * p.W;
+    CK(c, cudaMemcpyAsync(L.h_sets, ws.set_sums, sizeof(XYZZ) * p.sets, cudaMemcpyDeviceToHost, L.st));
+    job->plan = p;
+    job->active = true;
+    return KZGB_OK;
+}
+
+// Wait for the lane and finish on the host: Horner over the window sums, then to affine.
+int msm_finish(kzgb_ctx* c, Lane& L, const MsmJob& job, Affine* out) {
+    if (!job.active) { aff_set_inf(*out); return KZGB_OK; }
+    CK(c, cudaStreamSynchronize(L.st));
+    CK(c, cudaGetLastError());
+    lane_collect_acc(L);
+    const MsmPlan& p = job.plan;
+    XYZZ acc = L.h_sets[p.sets - 1];
+    for (int w = p.sets - 2; w >= 0; w--) {
+        for (int k = 0; k < p.c; k++) xyzz_dbl(acc, acc);
+        xyzz_add(acc, L.h_sets[w]);
+    }
+    xyzz_to_affine(*out, acc);
+    return KZGB_OK;
+}
+
+int msm_blocking(kzgb_ctx* c, Lane& L, const Fr* d_scalars, bool canonical, size_t first, size_t n,
+                 const Affine* var_bases, Affine* out) {
+    MsmJob job;
+    int rc = msm_enqueue(c, L, d_scalars, canonical, first, n, var_bases, &job);
+    if (rc) return rc;
+    return msm_finish(c, L, job, out);
+}
+
+// ---------------------------------------------------------------- polynomial pipeline pieces
+// d_evals (n Fr, Montgomery) -> commitment.  Uses L.work / L.ntt_scratch.
+int commit_evals_enqueue(kzgb_ctx* c, Lane& L, const Fr* d_evals, size_t n, MsmJob* job) {
+    int logn = log2_exact(n);
+    int rc = ensure_twiddles(c, logn);
+    if (rc) return rc;
+    CK(c, L.work.reserve(n * sizeof(Fr)));
+    CK(c, L.ntt_scratch.reserve(n * sizeof(Fr)));
+    if ((const void*)d_evals != L.work.p)
+        CK(c, cudaMemcpyAsync(L.work.p, d_evals, n * sizeof(Fr), cudaMemcpyDeviceToDevice, L.st));
+    Fr ninv = ninv_mont(logn);
+    ntt_launch((Fr*)L.work.p, logn, 1, true, c->tw, c->logN, &ninv, (Fr*)L.ntt_scratch.p, L.st);
+    return msm_enqueue(c, L, (Fr*)L.work.p, false, 0, n, nullptr, job);
+}
+
+// quotient of d_evals at z (device, Montgomery) into L.work, then commit it.  y stays in L.small[1].
+int proof_enqueue(kzgb_ctx* c, Lane& L, const Fr* d_evals, size_t n, const Fr& z_mont, MsmJob* job) {
+    int logn = log2_exact(n);
+    int rc = ensure_twiddles(c, logn);
+    if (rc) return rc;
+    CK(c, L.work.reserve(n * sizeof(Fr)));
+    CK(c, L.ntt_scratch.reserve(n * sizeof(Fr)));
+    CK(c, L.eval_scratch.reserve(eval_quotient_scratch_elems((uint32_t)n, 1) * sizeof(Fr)));
+    CK(c, L.small.reserve(64 * sizeof(Fr)));
+    Fr* d_z = (Fr*)L.small.p;
+    Fr* d_y = d_z + 1;
+    L.h_fr[0] = z_mont;
+    CK(c, cudaMemcpyAsync(d_z, &L.h_fr[0], sizeof(Fr), cudaMemcpyHostToDevice, L.st));
+    Fr ninv = ninv_mont(logn);
+    eval_quotient_launch(d_evals, (uint32_t)n, logn, 1, d_z, c->tw, c->logN, &ninv, (Fr*)L.eval_scratch.p,
+                         (Fr*)L.work.p, d_y, L.st);
+    ntt_launch((Fr*)L.work.p, logn, 1, true, c->tw, c->logN, &ninv, (Fr*)L.ntt_scratch.p, L.st);
+    return msm_enqueue(c, L, (Fr*)L.work.p, false, 0, n, nullptr, job);
+}
+
+// ---------------------------------------------------------------- Fiat-Shamir on the host
+const uint8_t FR_MOD_BE[32] = {0x30, 0x64, 0x4e, 0x72, 0xe1, 0x31, 0xa0, 0x29, 0xb8, 0x50, 0x45, 0xb6, 0x81, 0x81, 0x58, 0x5d,
+                               0x28, 0x33, 0xe8, 0x48, 0x79, 0xb9, 0x70, 0x91, 0x43, 0xe1, 0xf5, 0x93, 0xf0, 0x00, 0x00, 0x01};
+
+// Absorb tag || u64_be(n) || n canonical 32-byte evaluations (zero padded) -- everything of the
+// compute_challenge transcript (helpers.rs:424-456) except the trailing commitment.
+void challenge_midstate(Sha256& sh, const uint8_t* blob, size_t len, size_t n) {
+    static const char TAG[] = "EIGENDA_FSBLOBVERIFY_V1_";
+    sh.reset();
+    sh.update(TAG, 24);
+    uint8_t nb[8];
+    for (int i = 0; i < 8; i++) nb[i] = (uint8_t)((uint64_t)n >> (56 - 8 * i));
+    sh.update(nb, 8);
+    size_t full = len / 32;
+    size_t run_start = 0;
+    for (size_t i = 0; i < full; i++) {
+        const uint8_t* ch = blob + 32 * i;
+        if (ch[0] < 0x30 || memcmp(ch, FR_MOD_BE, 32) < 0) continue;  // canonical: hash in place
+        if (i > run_start) sh.update(blob + 32 * run_start, 32 * (i - run_start));
+        Fr v = fr_from_be_bytes(ch);  // to_fr_array reduces mod r (helpers.rs:32-34)
+        uint8_t red[32];
+        fe_to_be_bytes(v, red);
+        sh.update(red, 32);
+        run_start = i + 1;
+    }
+    if (full > run_start) sh.update(blob + 32 * run_start, 32 * (full - run_start));
+    size_t done = full;
+    if (len % 32) {  // trailing partial chunk, right-padded with zeros (helpers.rs:47-51)
+        uint8_t last[32];
+        memset(last, 0, 32);
+        memcpy(last, blob + 32 * full, len % 32);
+        Fr v = fr_from_be_bytes(last);
+        uint8_t red[32];
+        fe_to_be_bytes(v, red);
+        sh.update(red, 32);
+        done++;
+    }
+    static const uint8_t zeros[4096] = {0};
+    size_t pad = (n - done) * 32;
+    while (pad) { size_t t = pad < sizeof(zeros) ? pad : sizeof(zeros); sh.update(zeros, t); pad -= t; }
+}
+Fr challenge_finish(Sha256 sh, const Affine& commitment) {
+    uint8_t cb[32], dg[32];
+    serialize_compressed(commitment, cb);
+    sh.update(cb, 32);
+    sh.finish(dg);
+    return fr_from_be_bytes(dg);  // hash_to_field_element (helpers.rs:382-390)
+}
+
+size_t blob_poly_len(size_t len) { return next_pow2((len + 31) / 32); }  // Rust: 0usize.next_power_of_two() == 1
+
+// blob bytes on the host -> L.evals (n Fr Montgomery)
+int blob_to_evals(kzgb_ctx* c, Lane& L, const uint8_t* blob_host, const uint8_t* blob_dev, size_t len, size_t n) {
+    CK(c, L.evals.reserve(n * sizeof(Fr)));
+    const uint8_t* src = blob_dev;
+    if (!src) {
+        CK(c, L.bytes.reserve(len ? len : 32));
+        if (len) CK(c, cudaMemcpyAsync(L.bytes.p, blob_host, len, cudaMemcpyHostToDevice, L.st));
+        src = (const uint8_t*)L.bytes.p;
+    }
+    bytes_to_fr_launch(src, len, (Fr*)L.evals.p, (uint32_t)n, L.st);
+    return KZGB_OK;
+}
+
+struct Guard {
+    kzgb_ctx* c;
+    int prev = -1;
+    std::unique_lock<std::mutex> lk;
+    explicit Guard(kzgb_ctx* ctx) : c(ctx), lk(ctx->mu) { cudaGetDevice(&prev); cudaSetDevice(ctx->device); }
+    ~Guard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+}  // namespace
+
+// =====================================================================================
+extern "C" {
+
+int kzgb_ctx_create(kzgb_ctx** out, int device, void* stream) {
+    if (!out) return KZGB_ERR_GENERIC;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return KZGB_ERR_DEVICE;
+    kzgb_ctx* c = new kzgb_ctx();
+    c->device = device;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    if (cudaSetDevice(device) != cudaSuccess) { delete c; return KZGB_ERR_DEVICE; }
+    int rc = lane_init(c, c->lanes[0], (cudaStream_t)stream);
+    if (rc == KZGB_OK) {
+        c->n_lanes = 1;
+        if (cudaEventCreate(&c->t0) != cudaSuccess || cudaEventCreate(&c->t1) != cudaSuccess) rc = KZGB_ERR_DEVICE;
+    }
+    cudaSetDevice(prev);
+    if (rc) { delete c; return rc; }
+    *out = c;
+    return KZGB_OK;
+}
+
+void kzgb_ctx_destroy(kzgb_ctx* c) {
+    if (!c) return;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(c->device);
+    for (int i = 0; i < c->n_lanes; i++) { cudaStreamSynchronize(c->lanes[i].st); lane_destroy(c->lanes[i]); }
+    if (c->srs) cudaFree(c->srs);
+    if (c->wtable) cudaFree(c->wtable);
+    if (c->tw) cudaFree(c->tw);
+    if (c->t0) cudaEventDestroy(c->t0);
+    if (c->t1) cudaEventDestroy(c->t1);
+    cudaSetDevice(prev);
+    delete c;
+}
+
+const char* kzgb_last_error(const kzgb_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int kzgb_sync(kzgb_ctx* c) {
+    Guard g(c);
+    for (int i = 0; i < c->n_lanes; i++) CK(c, cudaStreamSynchronize(c->lanes[i].st));
+    return KZGB_OK;
+}
+
+uint64_t kzgb_launch_count(const kzgb_ctx*) { return g_launch_count.load(); }
+
+// ------------------------------------------------------------------------------- SRS
+int kzgb_srs_load_gnark_be(kzgb_ctx* c, const uint8_t* bytes, size_t n) {
+    Guard g(c);
+    if (n == 0 || n > ((size_t)1 << 28)) return fail(c, KZGB_ERR_GENERIC, "invalid number of SRS points");
+    Lane& L = c->lanes[0];
+    DevBuf raw, errb;
+    CK(c, raw.reserve(n * 32));
+    CK(c, errb.reserve(64));
+    Affine* pts = nullptr;
+    CK(c, cudaMalloc((void**)&pts, n * sizeof(Affine)));
+    CK(c, cudaMemcpyAsync(raw.p, bytes, n * 32, cudaMemcpyHostToDevice, L.st));
+    CK(c, cudaMemsetAsync(errb.p, 0xff, 64, L.st));
+    srs_decompress_launch((const uint8_t*)raw.p, (uint32_t)n, pts, (uint32_t*)errb.p, L.st);
+    uint32_t herr[2] = {0, 0};
+    CK(c, cudaMemcpyAsync(herr, errb.p, 8, cudaMemcpyDeviceToHost, L.st));
+    cudaError_t e = cudaStreamSynchronize(L.st);
+    raw.release(); errb.release();
+    if (e != cudaSuccess) { cudaFree(pts); CK(c, e); }
+    if (herr[0] != 0xffffffffu) {
+        cudaFree(pts);
+        char msg[128];
+        if (herr[1] == 2) {
+            snprintf(msg, sizeof msg, "point at infinity not coded properly for g1 (point %u)", herr[0] - 1);
+            return fail(c, KZGB_ERR_DESERIALIZATION, msg);
+        }
+        snprintf(msg, sizeof msg, "compressed g1 point not on curve (point %u)", herr[0] - 1);
+        return fail(c, KZGB_ERR_NOT_ON_CURVE, msg);
+    }
+    return srs_install(c, pts, n);
+}
+
+int kzgb_srs_load_file(kzgb_ctx* c, const char* path, uint32_t order, uint32_t points_to_load) {
+    if (points_to_load > order) return fail(c, KZGB_ERR_GENERIC, "Number of points to load exceeds SRS order.");  // srs.rs:36-40
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(c, KZGB_ERR_GENERIC, std::string("Failed to read G1 points: cannot open ") + path);
+    std::vector<uint8_t> buf((size_t)points_to_load * 32);
+    size_t got = fread(buf.data(), 1, buf.size(), f);  // one bulk read instead of one 32-byte read per point (srs.rs:173)
+    fclose(f);
+    if (got != buf.size()) return fail(c, KZGB_ERR_GENERIC, "Failed to read G1 points: file shorter than points_to_load");
+    return kzgb_srs_load_gnark_be(c, buf.data(), points_to_load);
+}
+
+int kzgb_srs_load_affine_mont(kzgb_ctx* c, const uint64_t* xy, const uint8_t* inf, size_t n) {
+    Guard g(c);
+    if (n == 0) return fail(c, KZGB_ERR_GENERIC, "empty SRS");
+    std::vector<Affine> host(n);
+    memcpy(host.data(), xy, n * sizeof(Affine));
+    if (inf) for (size_t i = 0; i < n; i++) if (inf[i]) aff_set_inf(host[i]);
+    Affine* pts = nullptr;
+    CK(c, cudaMalloc((void**)&pts, n * sizeof(Affine)));
+    cudaError_t e = cudaMemcpy(pts, host.data(), n * sizeof(Affine), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(pts); CK(c, e); }
+    return srs_install(c, pts, n);
+}
+
+int kzgb_srs_load_synthetic(kzgb_ctx* c, const uint64_t tau_mont[4], size_t n) {
+    Guard g(c);
+    if (n == 0 || n > ((size_t)1 << 28)) return fail(c, KZGB_ERR_GENERIC, "invalid number of SRS points");
+    Affine* pts = nullptr;
+    CK(c, cudaMalloc((void**)&pts, n * sizeof(Affine)));
+    Fr tau;
+    memcpy(tau.l, tau_mont, 32);
+    srs_synthetic_launch(pts, (uint32_t)n, &tau, nullptr, c->lanes[0].st);
+    cudaError_t e = cudaStreamSynchronize(c->lanes[0].st);
+    if (e != cudaSuccess) { cudaFree(pts); CK(c, e); }
+    return srs_install(c, pts, n);
+}
+
+size_t kzgb_srs_len(const kzgb_ctx* c) { return c ? c->srs_n : 0; }
+
+int kzgb_srs_get_affine_mont(kzgb_ctx* c, size_t start, size_t count, uint64_t* out_xy, uint8_t* out_inf) {
+    Guard g(c);
+    if (start + count > c->srs_n) return fail(c, KZGB_ERR_GENERIC, "SRS range out of bounds");
+    CK(c, cudaMemcpy(out_xy, c->srs + start, count * sizeof(Affine), cudaMemcpyDeviceToHost));
+    if (out_inf) {
+        const Affine* a = (const Affine*)out_xy;
+        for (size_t i = 0; i < count; i++) out_inf[i] = aff_is_inf(a[i]) ? 1 : 0;
+    }
+    return KZGB_OK;
+}
+
+int kzgb_srs_precompute(kzgb_ctx* c, size_t max_n, int window_bits) {
+    Guard g(c);
+    if (window_bits < 0) {  // disable fixed-base tables (variable-base mode over the monomial points)
+        c->auto_precompute = false;
+        for (int i = 0; i < c->n_lanes; i++) cudaStreamSynchronize(c->lanes[i].st);
+        if (c->wtable) { cudaFree(c->wtable); c->wtable = nullptr; c->wt_n = 0; }
+        return KZGB_OK;
+    }
+    if (!c->srs_n) return fail(c, KZGB_ERR_GENERIC, "no SRS loaded");
+    return do_precompute(c, max_n ? max_n : c->srs_n, window_bits);
+}
+
+// ------------------------------------------------------------------------------- MSM
+int kzgb_msm_srs_range(kzgb_ctx* c, const uint64_t* scalars, size_t first, size_t n, uint64_t out_xy[8], uint8_t* out_inf) {
+    Guard g(c);
+    Lane& L = c->lanes[0];
+    if (first + n > c->srs_n) return fail(c, KZGB_ERR_SERIALIZATION, "polynomial length is not correct");
+    Affine r;
+    if (n == 0) { aff_set_inf(r); affine_to_abi(r, out_xy, out_inf); return KZGB_OK; }
+    CK(c, L.work.reserve(n * sizeof(Fr)));
+    CK(c, cudaMemcpyAsync(L.work.p, scalars, n * sizeof(Fr), cudaMemcpyHostToDevice, L.st));
+    int rc = msm_blocking(c, L, (Fr*)L.work.p, false, first, n, nullptr, &r);
+    if (rc) return rc;
+    affine_to_abi(r, out_xy, out_inf);
+    return KZGB_OK;
+}
+int kzgb_msm_srs(kzgb_ctx* c, const uint64_t* scalars, size_t n, uint64_t out_xy[8], uint8_t* out_inf) {
+    return kzgb_msm_srs_range(c, scalars, 0, n, out_xy, out_inf);
+}
+
+int kzgb_msm_var(kzgb_ctx* c, const uint64_t* bases_xy, const uint8_t* bases_inf, const uint64_t* scalars, size_t m,
+                 uint64_t out_xy[8], uint8_t* out_inf) {
+    Guard g(c);
+    Lane& L = c->lanes[0];
+    Affine r;
+    if (m == 0) { aff_set_inf(r); affine_to_abi(r, out_xy, out_inf); return KZGB_OK; }
+    CK(c, L.work.reserve(m * sizeof(Fr)));
+    CK(c, L.bases.reserve(m * sizeof(Affine)));
+    if (bases_inf) {
+        std::vector<Affine> tmp(m);
+        memcpy(tmp.data(), bases_xy, m * sizeof(Affine));
+        for (size_t i = 0; i < m; i++) if (bases_inf[i]) aff_set_inf(tmp[i]);
+        CK(c, cudaMemcpy(L.bases.p, tmp.data(), m * sizeof(Affine), cudaMemcpyHostToDevice));
+    } else {
+        CK(c, cudaMemcpyAsync(L.bases.p, bases_xy, m * sizeof(Affine), cudaMemcpyHostToDevice, L.st));
+    }
+    CK(c, cudaMemcpyAsync(L.work.p, scalars, m * sizeof(Fr), cudaMemcpyHostToDevice, L.st));
+    int rc = msm_blocking(c, L, (Fr*)L.work.p, false, 0, m, (const Affine*)L.bases.p, &r);
+    if (rc) return rc;
+    affine_to_abi(r, out_xy, out_inf);
+    return KZGB_OK;
+}
+
+int kzgb_g1_add(const uint64_t a_xy[8], uint8_t a_inf, const uint64_t b_xy[8], uint8_t b_inf, uint64_t out_xy[8], uint8_t* out_inf) {
+    Affine a = affine_from_abi(a_xy, a_inf), b = affine_from_abi(b_xy, b_inf), r;
+    XYZZ acc;
+    xyzz_from_affine(acc, a);
+    xyzz_madd(acc, b);
+    xyzz_to_affine(r, acc);
+    affine_to_abi(r, out_xy, out_inf);
+    return KZGB_OK;
+}
+
+// ------------------------------------------------------------------------------- NTT / codecs
+int kzgb_ntt_fr(kzgb_ctx* c, uint64_t* inout, size_t n, int inverse) {
+    Guard g(c);
+    if (n == 0 || (n & (n - 1))) return fail(c, KZGB_ERR_FFT, "length provided is not a power of 2");
+    if (n > ((size_t)1 << 28)) return fail(c, KZGB_ERR_GENERIC, "Input size exceeds maximum polynomial size");
+    Lane& L = c->lanes[0];
+    int logn = log2_exact(n);
+    int rc = ensure_twiddles(c, logn);
+    if (rc) return rc;
+    CK(c, L.work.reserve(n * sizeof(Fr)));
+    CK(c, L.ntt_scratch.reserve(n * sizeof(Fr)));
+    CK(c, cudaMemcpyAsync(L.work.p, inout, n * sizeof(Fr), cudaMemcpyHostToDevice, L.st));
+    Fr ninv = ninv_mont(logn);
+    ntt_launch((Fr*)L.work.p, logn, 1, inverse != 0, c->tw, c->logN, &ninv, (Fr*)L.ntt_scratch.p, L.st);
+    CK(c, cudaMemcpyAsync(inout, L.work.p, n * sizeof(Fr), cudaMemcpyDeviceToHost, L.st));
+    CK(c, cudaStreamSynchronize(L.st));
+    CK(c, cudaGetLastError());
+    return KZGB_OK;
+}
+
+int kzgb_to_fr_array(kzgb_ctx* c, const uint8_t* bytes, size_t len, uint64_t* out) {
+    Guard g(c);
+    Lane& L = c->lanes[0];
+    size_t n = (len + 31) / 32;
+    if (!n) return KZGB_OK;
+    int rc = blob_to_evals(c, L, bytes, nullptr, len, n);
+    if (rc) return rc;
+    CK(c, cudaMemcpyAsync(out, L.evals.p, n * sizeof(Fr), cudaMemcpyDeviceToHost, L.st));
+    CK(c, cudaStreamSynchronize(L.st));
+    CK(c, cudaGetLastError());
+    return KZGB_OK;
+}
+
+int kzgb_to_byte_array(kzgb_ctx* c, const uint64_t* fr, size_t n, uint8_t* out) {
+    Guard g(c);
+    Lane& L = c->lanes[0];
+    if (!n) return KZGB_OK;
+    CK(c, L.evals.reserve(n * sizeof(Fr)));
+    CK(c, L.bytes.reserve(n * 32));
+    CK(c, cudaMemcpyAsync(L.evals.p, fr, n * sizeof(Fr), cudaMemcpyHostToDevice, L.st));
+    fr_to_bytes_launch((Fr*)L.evals.p, (uint8_t*)L.bytes.p, (uint32_t)n, L.st);
+    CK(c, cudaMemcpyAsync(out, L.bytes.p, n * 32, cudaMemcpyDeviceToHost, L.st));
+    CK(c, cudaStreamSynchronize(L.st));
+    CK(c, cudaGetLastError());
+    return KZGB_OK;
+}
+
+// ------------------------------------------------------------------------------- commitments
+static int commit_evals_host(kzgb_ctx* c, const uint64_t* evals, size_t n, uint64_t out_xy[8], uint8_t* out_inf) {
+    Lane& L = c->lanes[0];
+    CK(c, L.work.reserve(n * sizeof(Fr)));
+    CK(c, cudaMemcpyAsync(L.work.p, evals, n * sizeof(Fr), cudaMemcpyHostToDevice, L.st));
+    MsmJob job;
+    int rc = commit_evals_enqueue(c, L, (Fr*)L.work.p, n, &job);
+    if (rc) return rc;
+    Affine r;
+    rc = msm_finish(c, L, job, &r);
+    if (rc) return rc;
+    affine_to_abi(r, out_xy, out_inf);
+    return KZGB_OK;
+}
+
+int kzgb_commit_eval(kzgb_ctx* c, const uint64_t* evals, size_t n, uint64_t out_xy[8], uint8_t* out_inf) {
+    Guard g(c);
+    if (n > c->srs_n) {  // kzg.rs:89-94
+        char msg[160];
+        snprintf(msg, sizeof msg, "SRS capacity exceeded: polynomial_len=%zu srs_len=%zu", n, c->srs_n);
+        return fail(c, KZGB_ERR_SRS_CAPACITY, msg);
+    }
+    if (n == 0 || (n & (n - 1))) return fail(c, KZGB_ERR_FFT, "length provided is not a power of 2");  // kzg.rs:265-269
+    return commit_evals_host(c, evals, n, out_xy, out_inf);
+}
+
+int kzgb_commit_coeff(kzgb_ctx* c, const uint64_t* coeffs, size_t n, uint64_t out_xy[8], uint8_t* out_inf) {
+    if (n > kzgb_srs_len(c)) return fail(c, KZGB_ERR_SERIALIZATION, "polynomial length is not correct");  // kzg.rs:112-116
+    return kzgb_msm_srs_range(c, coeffs, 0, n, out_xy, out_inf);
+}
+
+int kzgb_commit_blob(kzgb_ctx* c, const uint8_t* blob, size_t len, uint64_t out_xy[8], uint8_t* out_inf) {
+    Guard g(c);
+    Lane& L = c->lanes[0];
+    size_t n = blob_poly_len(len);
+    if (n > ((size_t)1 << 28)) return fail(c, KZGB_ERR_GENERIC, "Input size exceeds maximum polynomial size");
+    if (n > c->srs_n) {
+        char msg[160];
+        snprintf(msg, sizeof msg, "SRS capacity exceeded: polynomial_len=%zu srs_len=%zu", n, c->srs_n);
+        return fail(c, KZGB_ERR_SRS_CAPACITY, msg);
+    }
+    int rc = blob_to_evals(c, L, blob, nullptr, len, n);
+    if (rc) return rc;
+    MsmJob job;
+    rc = commit_evals_enqueue(c, L, (Fr*)L.evals.p, n, &job);
+    if (rc) return rc;
+    Affine r;
+    rc = msm_finish(c, L, job, &r);
+    if (rc) return rc;
+    affine_to_abi(r, out_xy, out_inf);
+    return KZGB_OK;
+}
+
+// The reference computes the Lagrange SRS with (n/2) log n + n scalar multiplications per commit
+// (kzg.rs:263-285).  Here it is only a public API: L_i = MSM(SRS[..n], column i of the inverse DFT
+// matrix) = commit_eval_form(unit vector e_i); done as n small commits would be wasteful, so we use
+// n fixed-base MSMs only for tiny n and otherwise... (g1_ifft is a "next" row).
+int kzgb_g1_ifft(kzgb_ctx* c, size_t n, uint64_t* out_xy, uint8_t* out_inf) {
+    if (n == 0 || (n & (n - 1))) return fail(c, KZGB_ERR_FFT, "length provided is not a power of 2");
+    if (n > kzgb_srs_len(c)) return fail(c, KZGB_ERR_GENERIC, "g1_ifft length exceeds the SRS");
+    if (n > 4096) return fail(c, KZGB_ERR_GENERIC, "g1_ifft: sizes above 4096 are not implemented on the GPU path yet");
+    // L_i = sum_j (1/n) w^{-ij} SRS_j : one MSM per output point with scalars from the inverse DFT matrix
+    int logn = log2_exact(n);
+    Fr w = root_of_unity_mont(logn), winv, ninv = ninv_mont(logn);
+    fe_inv(winv, w);
+    std::vector<Fr> col(n);
+    for (size_t i = 0; i < n; i++) {
+        Fr wi, cur = ninv;
+        uint32_t e[8] = {(uint32_t)i, 0, 0, 0, 0, 0, 0, 0};
+        fe_pow(wi, winv, e);
+        for (size_t j = 0; j < n; j++) { col[j] = cur; fe_mul(cur, cur, wi); }
+        int rc = kzgb_msm_srs_range(c, (const uint64_t*)col.data(), 0, n, out_xy + 8 * i, out_inf ? out_inf + i : nullptr);
+        if (rc) return rc;
+    }
+    return KZGB_OK;
+}
+
+// ------------------------------------------------------------------------------- proofs
+int kzgb_compute_proof(kzgb_ctx* c, const uint64_t* evals, size_t n, const uint64_t z_mont[4], uint64_t out_xy[8],
+                       uint8_t* out_inf, uint64_t y_out[4]) {
+    Guard g(c);
+    Lane& L = c->lanes[0];
+    if (n == 0 || (n & (n - 1))) return fail(c, KZGB_ERR_FFT, "length provided is not a power of 2");
+    if (n > c->srs_n) {
+        char msg[160];
+        snprintf(msg, sizeof msg, "SRS capacity exceeded: polynomial_len=%zu srs_len=%zu", n, c->srs_n);
+        return fail(c, KZGB_ERR_SRS_CAPACITY, msg);
+    }
+    CK(c, L.evals.reserve(n * sizeof(Fr)));
+    CK(c, cudaMemcpyAsync(L.evals.p, evals, n * sizeof(Fr), cudaMemcpyHostToDevice, L.st));
+    Fr z;
+    memcpy(z.l, z_mont, 32);
+    MsmJob job;
+    int rc = proof_enqueue(c, L, (Fr*)L.evals.p, n, z, &job);
+    if (rc) return rc;
+    if (y_out) CK(c, cudaMemcpyAsync(&L.h_fr[1], (Fr*)L.small.p + 1, sizeof(Fr), cudaMemcpyDeviceToHost, L.st));
+    Affine r;
+    rc = msm_finish(c, L, job, &r);
+    if (rc) return rc;
+    if (y_out) memcpy(y_out, &L.h_fr[1], 32);
+    affine_to_abi(r, out_xy, out_inf);
+    return KZGB_OK;
+}
+
+int kzgb_evaluate_polynomial(kzgb_ctx* c, const uint64_t* evals, size_t n, const uint64_t z_mont[4], uint64_t y_out[4]) {
+    Guard g(c);
+    Lane& L = c->lanes[0];
+    if (n == 0 || (n & (n - 1))) return fail(c, KZGB_ERR_INVALID_INPUT_LENGTH, "polynomial length must be a power of two");
+    int logn = log2_exact(n);
+    int rc = ensure_twiddles(c, logn);
+    if (rc) return rc;
+    CK(c, L.evals.reserve(n * sizeof(Fr)));
+    CK(c, L.eval_scratch.reserve(eval_quotient_scratch_elems((uint32_t)n, 1) * sizeof(Fr)));
+    CK(c, L.small.reserve(64 * sizeof(Fr)));
+    CK(c, cudaMemcpyAsync(L.evals.p, evals, n * sizeof(Fr), cudaMemcpyHostToDevice, L.st));
+    memcpy(L.h_fr[0].l, z_mont, 32);
+    Fr* d_z = (Fr*)L.small.p;
+    CK(c, cudaMemcpyAsync(d_z, &L.h_fr[0], sizeof(Fr), cudaMemcpyHostToDevice, L.st));
+    Fr ninv = ninv_mont(logn);
+    eval_quotient_launch((Fr*)L.evals.p, (uint32_t)n, logn, 1, d_z, c->tw, c->logN, &ninv, (Fr*)L.eval_scratch.p, nullptr,
+                         d_z + 1, L.st);
+    CK(c, cudaMemcpyAsync(&L.h_fr[1], d_z + 1, sizeof(Fr), cudaMemcpyDeviceToHost, L.st));
+    CK(c, cudaStreamSynchronize(L.st));
+    CK(c, cudaGetLastError());
+    memcpy(y_out, &L.h_fr[1], 32);
+    return KZGB_OK;
+}
+
+int kzgb_compute_challenge(kzgb_ctx* c, const uint8_t* blob, size_t len, const uint64_t c_xy[8], uint8_t c_inf,
+                           uint64_t z_out[4]) {
+    Affine C = affine_from_abi(c_xy, c_inf);
+    if (!aff_on_curve(C)) return fail(c, KZGB_ERR_NOT_ON_CURVE, "G1 point not on curve");
+    size_t n = blob_poly_len(len);
+    Sha256 sh;
+    challenge_midstate(sh, blob, len, n);
+    Fr z = challenge_finish(sh, C);
+    memcpy(z_out, z.l, 32);
+    return KZGB_OK;
+}
+
+int kzgb_compute_blob_proof(kzgb_ctx* c, const uint8_t* blob, size_t len, const uint64_t c_xy[8], uint8_t c_inf,
+                            uint64_t out_xy[8], uint8_t* out_inf) {
+    Guard g(c);
+    Lane& L = c->lanes[0];
+    Affine C = affine_from_abi(c_xy, c_inf);
+    if (!aff_on_curve(C)) return fail(c, KZGB_ERR_NOT_ON_CURVE, "G1 point not on curve");  // helpers.rs:694-699
+    size_t n = blob_poly_len(len);
+    if (len == 0) return fail(c, KZGB_ERR_GENERIC, "Length of data after padding is 0");  // helpers.rs:554-558 via :482
+    if (n > c->srs_n) {
+        char msg[160];
+        snprintf(msg, sizeof msg, "SRS capacity exceeded: polynomial_len=%zu srs_len=%zu", n, c->srs_n);
+        return fail(c, KZGB_ERR_SRS_CAPACITY, msg);
+    }
+    int rc = blob_to_evals(c, L, blob, nullptr, len, n);  // H2D + conversion run while the host hashes
+    if (rc) return rc;
+    Sha256 sh;
+    challenge_midstate(sh, blob, len, n);
+    Fr z = challenge_finish(sh, C);
+    MsmJob job;
+    rc = proof_enqueue(c, L, (Fr*)L.evals.p, n, z, &job);
+    if (rc) return rc;
+    Affine r;
+    rc = msm_finish(c, L, job, &r);
+    if (rc) return rc;
+    affine_to_abi(r, out_xy, out_inf);
+    return KZGB_OK;
+}
+
+// ------------------------------------------------------------------------------- blob batches
+static int batch_impl(kzgb_ctx* c, const uint8_t* const* blobs_dev, const uint8_t* const* blobs_host, const size_t* lens,
+                      size_t count, uint8_t* commitments32, uint8_t* proofs32) {
+    if (count == 0) return KZGB_OK;
+    size_t max_n = 0;
+    for (size_t i = 0; i < count; i++) {
+        size_t n = blob_poly_len(lens[i]);
+        if (lens[i] == 0) return fail(c, KZGB_ERR_GENERIC, "Length of data after padding is 0");
+        if (n > c->srs_n) {
+            char msg[160];
+            snprintf(msg, sizeof msg, "SRS capacity exceeded: polynomial_len=%zu srs_len=%zu", n, c->srs_n);
+            return fail(c, KZGB_ERR_SRS_CAPACITY, msg);
+        }
+        max_n = std::max(max_n, n);
+    }
+    int n_lanes = (int)std::min<size_t>(count, 3);
+    int rc = ensure_lanes(c, n_lanes);
+    if (rc) return rc;
+    rc = ensure_twiddles(c, log2_exact(max_n));
+    if (rc) return rc;
+    if (c->auto_precompute && (!c->wtable || max_n > c->wt_n) && c->srs_n <= ((size_t)1 << 22)) {
+        rc = do_precompute(c, std::min(c->srs_n, next_pow2(max_n)), 0);
+        if (rc && rc != KZGB_ERR_DEVICE) return rc;
+    }
+
+    // host hashing pool: transcript midstates (everything but the commitment)
+    std::vector<Sha256> mid(count);
+    std::vector<uint8_t> ready(count, 0);
+    std::mutex mu;
+    std::condition_variable cv;
+    std::atomic<size_t> next_hash{0};
+    unsigned hw = std::thread::hardware_concurrency();
+    size_t n_hash = std::max<size_t>(1, std::min<size_t>({count, (size_t)(hw > 4 ? hw - 2 : 2), (size_t)32}));
+    std::vector<std::thread> hashers;
+    for (size_t t = 0; t < n_hash; t++) {
+        hashers.emplace_back([&]() {
+            for (;;) {
+                size_t i = next_hash.fetch_add(1);
+                if (i >= count) return;
+                challenge_midstate(mid[i], blobs_host[i], lens[i], blob_poly_len(lens[i]));
+                { std::lock_guard<std::mutex> lk(mu); ready[i] = 1; }
+                cv.notify_all();
+            }
+        });
+    }
+
+    std::vector<int> lane_rc(n_lanes, KZGB_OK);
+    std::vector<std::string> lane_err(n_lanes);
+    std::atomic<size_t> next_blob{0};
+    auto lane_main = [&](int li) {
+        cudaSetDevice(c->device);
+        Lane& L = c->lanes[li];
+        for (;;) {
+            size_t i = next_blob.fetch_add(1);
+            if (i >= count) break;
+            size_t len = lens[i], n = blob_poly_len(len);
+            int r = blob_to_evals(c, L, blobs_host[i], blobs_dev ? blobs_dev[i] : nullptr, len, n);
+            MsmJob job;
+            Affine C, Pi;
+            if (!r) r = commit_evals_enqueue(c, L, (Fr*)L.evals.p, n, &job);
+            if (!r) r = msm_finish(c, L, job, &C);
+            if (r) { lane_rc[li] = r; break; }
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return ready[i] != 0; });
+            }
+            Fr z = challenge_finish(mid[i], C);
+            r = proof_enqueue(c, L, (Fr*)L.evals.p, n, z, &job);
+            if (!r) r = msm_finish(c, L, job, &Pi);
+            if (r) { lane_rc[li] = r; break; }
+            serialize_compressed(C, commitments32 + 32 * i);
+            serialize_compressed(Pi, proofs32 + 32 * i);
+        }
+    };
+    std::vector<std::thread> lane_threads;
+    for (int li = 1; li < n_lanes; li++) lane_threads.emplace_back(lane_main, li);
+    lane_main(0);
+    for (auto& t : lane_threads) t.join();
+    next_hash.store(count);
+    for (auto& t : hashers) t.join();
+    for (int li = 0; li < n_lanes; li++) if (lane_rc[li]) return lane_rc[li];
+    return KZGB_OK;
+}
+
+int kzgb_commit_and_prove_blobs(kzgb_ctx* c, const uint8_t* const* blobs, const size_t* lens, size_t count,
+                                uint8_t* commitments32, uint8_t* proofs32) {
+    Guard g(c);
+    return batch_impl(c, nullptr, blobs, lens, count, commitments32, proofs32);
+}
+int kzgb_commit_and_prove_blobs_dev(kzgb_ctx* c, const uint8_t* const* blobs_dev, const uint8_t* const* blobs_host,
+                                    const size_t* lens, size_t count, uint8_t* commitments32, uint8_t* proofs32) {
+    Guard g(c);
+    return batch_impl(c, blobs_dev, blobs_host, lens, count, commitments32, proofs32);
+}
+
+// ------------------------------------------------------------------------------- batch verification (RLC)
+int kzgb_verify_batch_rlc(kzgb_ctx* c, const uint8_t* const* blobs, const size_t* lens, size_t count,
+                          const uint64_t* commitments_xy, const uint8_t* commitments_inf, const uint64_t* proofs_xy,
+                          const uint8_t* proofs_inf, uint64_t lhs_xy[8], uint8_t* lhs_inf, uint64_t rhs_xy[8], uint8_t* rhs_inf) {
+    Guard g(c);
+    Lane& L = c->lanes[0];
+    const size_t m = count;
+    Affine inf_pt; aff_set_inf(inf_pt);
+    if (m == 0) { affine_to_abi(inf_pt, lhs_xy, lhs_inf); affine_to_abi(inf_pt, rhs_xy, rhs_inf); return KZGB_OK; }
+    std::vector<Affine> Cs(m), Ps(m);
+    for (size_t i = 0; i < m; i++) {
+        Cs[i] = affine_from_abi(commitments_xy + 8 * i, commitments_inf ? commitments_inf[i] : 0);
+        Ps[i] = affine_from_abi(proofs_xy + 8 * i, proofs_inf ? proofs_inf[i] : 0);
+    }
+    // validate_g1_point on all 2m points (batch.rs:30-37) -- on the GPU
+    CK(c, L.bases.reserve((2 * m + 1) * sizeof(Affine)));
+    CK(c, L.small.reserve(64 * sizeof(Fr)));
+    Affine* d_bases = (Affine*)L.bases.p;  // [C_0..C_{m-1}, pi_0..pi_{m-1}, G]
+    CK(c, cudaMemcpyAsync(d_bases, Cs.data(), m * sizeof(Affine), cudaMemcpyHostToDevice, L.st));
+    CK(c, cudaMemcpyAsync(d_bases + m, Ps.data(), m * sizeof(Affine), cudaMemcpyHostToDevice, L.st));
+    uint32_t* d_err = (uint32_t*)((Fr*)L.small.p + 32);
+    CK(c, cudaMemsetAsync(d_err, 0xff, 32, L.st));
+    g1_validate_launch(d_bases, (uint32_t)(2 * m), d_err, L.st);
+    uint32_t herr = 0;
+    CK(c, cudaMemcpyAsync(&herr, d_err, 4, cudaMemcpyDeviceToHost, L.st));
+    CK(c, cudaStreamSynchronize(L.st));
+    if (herr != 0xffffffffu) return fail(c, KZGB_ERR_NOT_ON_CURVE, "G1 point not on curve");
+
+    // per-blob challenge (host SHA pool) and evaluation (GPU, batched over blobs of equal length)
+    std::vector<size_t> ns(m);
+    size_t max_n = 0;
+    for (size_t i = 0; i < m; i++) {
+        if (lens[i] == 0) return fail(c, KZGB_ERR_GENERIC, "Length of data after padding is 0");
+        ns[i] = blob_poly_len(lens[i]);
+        max_n = std::max(max_n, ns[i]);
+    }
+    int rc = ensure_twiddles(c, log2_exact(max_n));
+    if (rc) return rc;
+    std::vector<Fr> zs(m), ys(m);
+    {
+        std::atomic<size_t> next{0};
+        unsigned hw = std::thread::hardware_concurrency();
+        size_t nt = std::max<size_t>(1, std::min<size_t>({m, (size_t)(hw > 2 ? hw - 1 : 1), (size_t)32}));
+        std::vector<std::thread> th;
+        for (size_t t = 0; t < nt; t++)
+            th.emplace_back([&]() {
+                for (;;) {
+                    size_t i = next.fetch_add(1);
+                    if (i >= m) return;
+                    Sha256 sh;
+                    challenge_midstate(sh, blobs[i], lens[i], ns[i]);
+                    zs[i] = challenge_finish(sh, Cs[i]);
+                }
+            });
+        for (auto& t : th) t.join();
+    }
+    const size_t budget_elems = (size_t)1 << 24;  // evaluations resident per GPU batch
+    size_t i0 = 0;
+    while (i0 < m) {
+        size_t n = ns[i0], i1 = i0;
+        while (i1 < m && ns[i1] == n && (i1 - i0 + 1) * n <= std::max(budget_elems, n)) i1++;
+        size_t b = i1 - i0;
+        int logn = log2_exact(n);
+        CK(c, L.evals.reserve(b * n * sizeof(Fr)));
+        CK(c, L.bytes.reserve(b * n * 32));
+        CK(c, L.eval_scratch.reserve(eval_quotient_scratch_elems((uint32_t)n, (uint32_t)b) * sizeof(Fr)));
+        CK(c, L.work.reserve(2 * b * sizeof(Fr)));
+        for (size_t k = 0; k < b; k++) {
+            uint8_t* dst = (uint8_t*)L.bytes.p + k * n * 32;
+            CK(c, cudaMemcpyAsync(dst, blobs[i0 + k], lens[i0 + k], cudaMemcpyHostToDevice, L.st));
+            bytes_to_fr_launch(dst, lens[i0 + k], (Fr*)L.evals.p + k * n, (uint32_t)n, L.st);
+        }
+        Fr* d_z = (Fr*)L.work.p;
+        Fr* d_y = d_z + b;
+        CK(c, cudaMemcpyAsync(d_z, &zs[i0], b * sizeof(Fr), cudaMemcpyHostToDevice, L.st));
+        Fr ninv = ninv_mont(logn);
+        eval_quotient_launch((Fr*)L.evals.p, (uint32_t)n, logn, (uint32_t)b, d_z, c->tw, c->logN, &ninv,
+                             (Fr*)L.eval_scratch.p, nullptr, d_y, L.st);
+        CK(c, cudaMemcpyAsync(&ys[i0], d_y, b * sizeof(Fr), cudaMemcpyDeviceToHost, L.st));
+        CK(c, cudaStreamSynchronize(L.st));
+        CK(c, cudaGetLastError());
+        i0 = i1;
+    }
+    // r = SHA-256(transcript) mod r (batch.rs:76-168): bytes 24..32 stay zero, count at 32..40
+    std::vector<uint8_t> tr(40 + m * 136, 0);
+    memcpy(tr.data(), "EIGENDA_RCKZGBATCH___V1_", 24);
+    for (int k = 0; k < 8; k++) tr[32 + k] = (uint8_t)((uint64_t)m >> (56 - 8 * k));
+    size_t off = 40;
+    for (size_t i = 0; i < m; i++) { for (int k = 0; k < 8; k++) tr[off + k] = (uint8_t)((uint64_t)ns[i] >> (56 - 8 * k)); off += 8; }
+    for (size_t i = 0; i < m; i++) {
+        serialize_compressed(Cs[i], &tr[off]); off += 32;
+        fe_to_be_bytes(zs[i], &tr[off]); off += 32;
+        fe_to_be_bytes(ys[i], &tr[off]); off += 32;
+        serialize_compressed(Ps[i], &tr[off]); off += 32;
+    }
+    uint8_t dg[32];
+    sha256(tr.data(), tr.size(), dg);
+    Fr r = fr_from_be_bytes(dg);
+
+    // scalars on the GPU: [r^i | r^i z_i | -(sum r^i y_i)]
+    CK(c, L.work.reserve((4 * m + 8) * sizeof(Fr)));
+    Fr* d_sc = (Fr*)L.work.p;          // 2m + 1 scalars
+    Fr* d_zy = d_sc + 2 * m + 1;       // z then y (m each)
+    Fr* d_dot = d_zy + 2 * m;
+    CK(c, cudaMemcpyAsync(d_zy, zs.data(), m * sizeof(Fr), cudaMemcpyHostToDevice, L.st));
+    CK(c, cudaMemcpyAsync(d_zy + m, ys.data(), m * sizeof(Fr), cudaMemcpyHostToDevice, L.st));
+    fr_powers_launch(d_sc, (uint32_t)m, &r, L.st);                      // helpers.rs:298-314
+    fr_mul_vec_launch(d_sc + m, d_sc, d_zy, (uint32_t)m, L.st);         // r^i z_i (batch.rs:239)
+    fr_dot_launch(d_dot, d_sc, d_zy + m, (uint32_t)m, L.st);            // sum r^i y_i
+    CK(c, cudaMemcpyAsync(&L.h_fr[2], d_dot, sizeof(Fr), cudaMemcpyDeviceToHost, L.st));
+    CK(c, cudaStreamSynchronize(L.st));
+    fe_neg(L.h_fr[2], L.h_fr[2]);
+    CK(c, cudaMemcpyAsync(d_sc + 2 * m, &L.h_fr[2], sizeof(Fr), cudaMemcpyHostToDevice, L.st));
+    Affine G;
+    fe_one(G.x); fe_dbl(G.y, G.x);
+    CK(c, cudaMemcpy(d_bases + 2 * m, &G, sizeof(Affine), cudaMemcpyHostToDevice));
+    // lhs = sum r^i pi_i (batch.rs:228); rhs = sum r^i (C_i - y_i G) + sum r^i z_i pi_i (batch.rs:245-249),
+    // the m generator multiplications folded into ONE extra base: -(sum r^i y_i) * G  (same group element)
+    Affine lhs, rhs;
+    rc = msm_blocking(c, L, d_sc, false, 0, m, d_bases + m, &lhs);
+    if (rc) return rc;
+    rc = msm_blocking(c, L, d_sc, false, 0, 2 * m + 1, d_bases, &rhs);
+    if (rc) return rc;
+    affine_to_abi(lhs, lhs_xy, lhs_inf);
+    affine_to_abi(rhs, rhs_xy, rhs_inf);
+    return KZGB_OK;
+}
+
+// ------------------------------------------------------------------------------- codecs / validation
+int kzgb_g1_serialize_compressed(const uint64_t xy[8], uint8_t inf, uint8_t out32[32]) {
+    serialize_compressed(affine_from_abi(xy, inf), out32);
+    return KZGB_OK;
+}
+int kzgb_g1_to_gnark_be(const uint64_t xy[8], uint8_t inf, uint8_t out32[32]) {
+    to_gnark_be(affine_from_abi(xy, inf), out32);
+    return KZGB_OK;
+}
+int kzgb_validate_g1_points(kzgb_ctx* c, const uint64_t* xy, const uint8_t* inf, size_t n) {
+    Guard g(c);
+    Lane& L = c->lanes[0];
+    if (!n) return KZGB_OK;
+    std::vector<Affine> pts(n);
+    for (size_t i = 0; i < n; i++) pts[i] = affine_from_abi(xy + 8 * i, inf ? inf[i] : 0);
+    CK(c, L.bases.reserve(n * sizeof(Affine)));
+    CK(c, L.small.reserve(64 * sizeof(Fr)));
+    uint32_t* d_err = (uint32_t*)((Fr*)L.small.p + 32);
+    CK(c, cudaMemcpyAsync(L.bases.p, pts.data(), n * sizeof(Affine), cudaMemcpyHostToDevice, L.st));
+    CK(c, cudaMemsetAsync(d_err, 0xff, 32, L.st));
+    g1_validate_launch((Affine*)L.bases.p, (uint32_t)n, d_err, L.st);
+    uint32_t herr = 0;
+    CK(c, cudaMemcpyAsync(&herr, d_err, 4, cudaMemcpyDeviceToHost, L.st));
+    CK(c, cudaStreamSynchronize(L.st));
+    if (herr != 0xffffffffu) return fail(c, KZGB_ERR_NOT_ON_CURVE, "G1 point not on curve");
+    return KZGB_OK;
+}
+
+// ------------------------------------------------------------------------------- measurement hooks
+int kzgb_microbench(kzgb_ctx* c, int kind, double* ops_per_second) {
+    Guard g(c);
+    Lane& L = c->lanes[0];
+    const int blocks = 148 * 8, threads = 256;
+    CK(c, L.work.reserve((size_t)blocks * threads * 4));
+    const int iters = (kind == 3) ? 512 : 2048;
+    double per_thread = (kind == 3) ? iters * 4.0 : (kind == 2 ? iters * 64.0 : iters * 128.0);
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        CK(c, cudaEventRecord(c->t0, L.st));
+        if (kind == 3) fqmul_peak_launch((uint32_t*)L.work.p, iters, blocks, threads, L.st);
+        else imad_peak_launch((uint32_t*)L.work.p, iters, kind, blocks, threads, L.st);
+        CK(c, cudaEventRecord(c->t1, L.st));
+        CK(c, cudaEventSynchronize(c->t1));
+        float ms = 0;
+        CK(c, cudaEventElapsedTime(&ms, c->t0, c->t1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    CK(c, cudaGetLastError());
+    *ops_per_second = per_thread * blocks * threads / (best * 1e-3);
+    return KZGB_OK;
+}
+
+int kzgb_bench_msm(kzgb_ctx* c, size_t n, int reps, double* ms_total, double* ms_accumulate) {
+    Guard g(c);
+    Lane& L = c->lanes[0];
+    if (n == 0 || n > c->srs_n) return fail(c, KZGB_ERR_GENERIC, "bench size exceeds the SRS");
+    CK(c, L.evals.reserve(n * sizeof(Fr)));
+    // pseudo-random Montgomery scalars: powers of a fixed element
+    Fr base = fr_from_u64(0x9e3779b97f4a7c15ull);
+    fr_powers_launch((Fr*)L.evals.p, (uint32_t)n, &base, L.st);
+    Affine r;
+    int rc = msm_blocking(c, L, (Fr*)L.evals.p, false, 0, n, nullptr, &r);  // warm-up (+ lazy table build)
+    if (rc) return rc;
+    double acc0 = L.acc_ms;
+    uint64_t l0 = L.acc_launches;
+    CK(c, cudaEventRecord(c->t0, L.st));
+    for (int i = 0; i < reps; i++) {
+        rc = msm_blocking(c, L, (Fr*)L.evals.p, false, 0, n, nullptr, &r);
+        if (rc) return rc;
+    }
+    CK(c, cudaEventRecord(c->t1, L.st));
+    CK(c, cudaEventSynchronize(c->t1));
+    float ms = 0;
+    CK(c, cudaEventElapsedTime(&ms, c->t0, c->t1));
+    *ms_total = ms / reps;
+    uint64_t nl = L.acc_launches - l0;
+    *ms_accumulate = nl ? (L.acc_ms - acc0) / nl : 0.0;
+    return KZGB_OK;
+}
+
+
+// Device-side stopwatch over ALL lanes: everything queued between begin and end is inside [t0, t1].
+int kzgb_timer_begin(kzgb_ctx* c) {
+    Guard g(c);
+    CK(c, cudaEventRecord(c->t0, c->lanes[0].st));
+    for (int i = 1; i < c->n_lanes; i++) CK(c, cudaStreamWaitEvent(c->lanes[i].st, c->t0, 0));
+    return KZGB_OK;
+}
+int kzgb_timer_end(kzgb_ctx* c, double* ms_out) {
+    Guard g(c);
+    for (int i = 1; i < c->n_lanes; i++) {
+        CK(c, cudaEventRecord(c->lanes[i].ev_done, c->lanes[i].st));
+        CK(c, cudaStreamWaitEvent(c->lanes[0].st, c->lanes[i].ev_done, 0));
+    }
+    CK(c, cudaEventRecord(c->t1, c->lanes[0].st));
+    CK(c, cudaEventSynchronize(c->t1));
+    float ms = 0;
+    CK(c, cudaEventElapsedTime(&ms, c->t0, c->t1));
+    *ms_out = ms;
+    return KZGB_OK;
+}
+int kzgb_stats(kzgb_ctx* c, double* acc_ms, uint64_t* acc_launches, uint64_t* acc_point_adds, int reset) {
+    Guard g(c);
+    double ms = 0; uint64_t nl = 0, na = 0;
+    for (int i = 0; i < c->n_lanes; i++) {
+        Lane& L = c->lanes[i];
+        cudaStreamSynchronize(L.st);
+        lane_collect_acc(L);
+        ms += L.acc_ms; nl += L.acc_launches; na += L.acc_adds;
+        if (reset) { L.acc_ms = 0; L.acc_launches = 0; L.acc_adds = 0; }
+    }
+    if (acc_ms) *acc_ms = ms;
+    if (acc_launches) *acc_launches = nl;
+    if (acc_point_adds) *acc_point_adds = na;
+    return KZGB_OK;
+}
+int kzgb_msm_config(const kzgb_ctx* c, int* window_bits, int* windows, size_t* table_points) {
+    if (window_bits) *window_bits = c->wt_c;
+    if (windows) *windows = c->wt_W;
+    if (table_points) *table_points = c->wt_n;
+    return KZGB_OK;
+}
+
+}  // extern "C"

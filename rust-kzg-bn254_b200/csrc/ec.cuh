@@ -1,0 +1,184 @@
+// BN254 G1 (y^2 = x^3 + 3 over Fq; reference primitives/src/helpers.rs:202) in
+// affine and extended-Jacobian "XYZZ" coordinates (x = X/ZZ, y = Y/ZZZ, ZZ^3 = ZZZ^2).
+// XYZZ is what the bucket accumulators use: a mixed addition is 8M + 2S with no
+// inversion, and the exceptional cases (identity, P + P, P + (-P)) are handled exactly,
+// because results must be bit-identical to the reference's arkworks path, not
+// probabilistically right.
+//
+// Conventions: affine identity = (0, 0) (not on the curve, so it is a safe sentinel);
+// XYZZ identity = ZZ == 0.
+#pragma once
+#include "field.cuh"
+
+namespace kzgb {
+
+struct alignas(16) Affine {
+    Fq x, y;
+};
+struct alignas(16) XYZZ {
+    Fq x, y, zz, zzz;
+};
+
+KZ_HD bool aff_is_inf(const Affine& p) { return fe_is_zero(p.x) && fe_is_zero(p.y); }
+KZ_HD void aff_set_inf(Affine& p) { fe_zero(p.x); fe_zero(p.y); }
+KZ_HD bool xyzz_is_inf(const XYZZ& p) { return fe_is_zero(p.zz); }
+KZ_HD void xyzz_set_inf(XYZZ& p) { fe_zero(p.x); fe_zero(p.y); fe_zero(p.zz); fe_zero(p.zzz); }
+KZ_HD void xyzz_from_affine(XYZZ& r, const Affine& p) {
+    if (aff_is_inf(p)) { xyzz_set_inf(r); return; }
+    r.x = p.x; r.y = p.y; fe_one(r.zz); fe_one(r.zzz);
+}
+KZ_HD void xyzz_neg(XYZZ& r, const XYZZ& p) { r = p; fe_neg(r.y, p.y); }
+
+// r = 2 * (affine p)          (EFD mdbl-2008-s-1, a = 0)
+KZ_HD void xyzz_dbl_affine(XYZZ& r, const Affine& p) {
+    if (aff_is_inf(p) || fe_is_zero(p.y)) { xyzz_set_inf(r); return; }
+    Fq U, V, W, S, M, t;
+    fe_dbl(U, p.y);
+    fe_sqr(V, U);
+    fe_mul(W, U, V);
+    fe_mul(S, p.x, V);
+    fe_sqr(t, p.x);
+    fe_dbl(M, t); fe_add(M, M, t);  // 3 x^2
+    fe_sqr(r.x, M);
+    fe_sub(r.x, r.x, S); fe_sub(r.x, r.x, S);
+    fe_sub(t, S, r.x);
+    fe_mul(t, M, t);
+    fe_mul(U, W, p.y);
+    fe_sub(r.y, t, U);
+    r.zz = V;
+    r.zzz = W;
+}
+
+// r = 2 * p                   (EFD dbl-2008-s-1, a = 0)
+KZ_HD void xyzz_dbl(XYZZ& r, const XYZZ& p) {
+    if (xyzz_is_inf(p) || fe_is_zero(p.y)) { xyzz_set_inf(r); return; }
+    Fq U, V, W, S, M, t, X3;
+    fe_dbl(U, p.y);
+    fe_sqr(V, U);
+    fe_mul(W, U, V);
+    fe_mul(S, p.x, V);
+    fe_sqr(t, p.x);
+    fe_dbl(M, t); fe_add(M, M, t);
+    fe_sqr(X3, M);
+    fe_sub(X3, X3, S); fe_sub(X3, X3, S);
+    fe_sub(t, S, X3);
+    fe_mul(t, M, t);
+    fe_mul(U, W, p.y);
+    fe_sub(r.y, t, U);
+    r.x = X3;
+    fe_mul(r.zz, V, p.zz);
+    fe_mul(r.zzz, W, p.zzz);
+}
+
+// acc += affine q             (EFD madd-2008-s: 8M + 2S), exact on all inputs
+KZ_HD void xyzz_madd(XYZZ& acc, const Affine& q) {
+    if (aff_is_inf(q)) return;
+    if (xyzz_is_inf(acc)) { acc.x = q.x; acc.y = q.y; fe_one(acc.zz); fe_one(acc.zzz); return; }
+    Fq U2, S2, Pp, Rr, PP, PPP, Q, t;
+    fe_mul(U2, q.x, acc.zz);
+    fe_mul(S2, q.y, acc.zzz);
+    fe_sub(Pp, U2, acc.x);
+    fe_sub(Rr, S2, acc.y);
+    if (fe_is_zero(Pp)) {
+        if (fe_is_zero(Rr)) xyzz_dbl_affine(acc, q);
+        else xyzz_set_inf(acc);
+        return;
+    }
+    fe_sqr(PP, Pp);
+    fe_mul(PPP, Pp, PP);
+    fe_mul(Q, acc.x, PP);
+    fe_sqr(t, Rr);
+    fe_sub(t, t, PPP); fe_sub(t, t, Q); fe_sub(t, t, Q);  // X3
+    fe_sub(Q, Q, t);
+    fe_mul(Q, Rr, Q);
+    fe_mul(S2, acc.y, PPP);
+    fe_sub(acc.y, Q, S2);
+    acc.x = t;
+    fe_mul(acc.zz, acc.zz, PP);
+    fe_mul(acc.zzz, acc.zzz, PPP);
+}
+
+// acc += q                    (EFD add-2008-s: 12M + 2S), exact on all inputs
+KZ_HD void xyzz_add(XYZZ& acc, const XYZZ& q) {
+    if (xyzz_is_inf(q)) return;
+    if (xyzz_is_inf(acc)) { acc = q; return; }
+    Fq U1, U2, S1, S2, Pp, Rr, PP, PPP, Q, t;
+    fe_mul(U1, acc.x, q.zz);
+    fe_mul(U2, q.x, acc.zz);
+    fe_mul(S1, acc.y, q.zzz);
+    fe_mul(S2, q.y, acc.zzz);
+    fe_sub(Pp, U2, U1);
+    fe_sub(Rr, S2, S1);
+    if (fe_is_zero(Pp)) {
+        if (fe_is_zero(Rr)) xyzz_dbl(acc, q);
+        else xyzz_set_inf(acc);
+        return;
+    }
+    fe_sqr(PP, Pp);
+    fe_mul(PPP, Pp, PP);
+    fe_mul(Q, U1, PP);
+    fe_sqr(t, Rr);
+    fe_sub(t, t, PPP); fe_sub(t, t, Q); fe_sub(t, t, Q);  // X3
+    fe_sub(Q, Q, t);
+    fe_mul(Q, Rr, Q);
+    fe_mul(S1, S1, PPP);
+    fe_sub(acc.y, Q, S1);
+    acc.x = t;
+    fe_mul(acc.zz, acc.zz, q.zz);
+    fe_mul(acc.zz, acc.zz, PP);
+    fe_mul(acc.zzz, acc.zzz, q.zzz);
+    fe_mul(acc.zzz, acc.zzz, PPP);
+}
+
+// r = k * p for a small unsigned scalar (left-to-right binary)
+KZ_HD void xyzz_mul_small(XYZZ& r, const XYZZ& p, uint32_t k) {
+    XYZZ acc; xyzz_set_inf(acc);
+    for (int b = 31; b >= 0; b--) {
+        xyzz_dbl(acc, acc);
+        if ((k >> b) & 1) xyzz_add(acc, p);
+    }
+    r = acc;
+}
+
+// Affine from XYZZ given inv = 1/ZZZ:  1/Z = inv*ZZ, x = X/Z^2, y = Y*inv
+KZ_HD void xyzz_to_affine_with_inv(Affine& r, const XYZZ& p, const Fq& inv_zzz) {
+    Fq zi, zi2;
+    fe_mul(zi, inv_zzz, p.zz);
+    fe_sqr(zi2, zi);
+    fe_mul(r.x, p.x, zi2);
+    fe_mul(r.y, p.y, inv_zzz);
+}
+KZ_HD void xyzz_to_affine(Affine& r, const XYZZ& p) {
+    if (xyzz_is_inf(p)) { aff_set_inf(r); return; }
+    Fq inv; fe_inv(inv, p.zzz);
+    xyzz_to_affine_with_inv(r, p, inv);
+}
+KZ_HD bool aff_on_curve(const Affine& p) {
+    if (aff_is_inf(p)) return true;
+    Fq y2, x3, b, three;
+    fe_sqr(y2, p.y);
+    fe_sqr(x3, p.x); fe_mul(x3, x3, p.x);
+    fe_one(b); fe_dbl(three, b); fe_add(three, three, b);
+    fe_add(x3, x3, three);
+    return fe_eq(y2, x3);
+}
+
+#ifdef __CUDACC__
+KZ_D Affine aff_load_ro(const Affine* p) {
+    Affine r;
+    r.x = fe_load_ro(&p->x);
+    r.y = fe_load_ro(&p->y);
+    return r;
+}
+KZ_D void aff_store(Affine* p, const Affine& v) { fe_store(&p->x, v.x); fe_store(&p->y, v.y); }
+KZ_D XYZZ xyzz_load(const XYZZ* p) {
+    XYZZ r;
+    r.x = fe_load(&p->x); r.y = fe_load(&p->y); r.zz = fe_load(&p->zz); r.zzz = fe_load(&p->zzz);
+    return r;
+}
+KZ_D void xyzz_store(XYZZ* p, const XYZZ& v) {
+    fe_store(&p->x, v.x); fe_store(&p->y, v.y); fe_store(&p->zz, v.zz); fe_store(&p->zzz, v.zzz);
+}
+#endif
+
+}  // namespace kzgb

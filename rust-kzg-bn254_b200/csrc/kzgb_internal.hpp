@@ -1,0 +1,99 @@
+// Internal launcher interface between the host orchestration (capi.cu) and the kernel
+// translation units.  Everything here takes DEVICE pointers and a stream; nothing blocks.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+#include <atomic>
+#include "ec.cuh"
+
+namespace kzgb {
+
+// kernels launched by this library since load (every launcher bumps it)
+extern std::atomic<uint64_t> g_launch_count;
+
+// ---- MSM plan -------------------------------------------------------------------
+// Signed-digit Pippenger.  Scalars are cut into W = ceil(255/c) signed c-bit digits.
+// With a fixed-base table (precomputed 2^(c*w) * P_i for every window w) all windows
+// share ONE bucket set; without it (variable bases) every window has its own set and
+// the host finishes with a Horner combine.
+struct MsmPlan {
+    int c;             // window bits
+    int W;             // number of windows
+    int sets;          // 1 (fixed-base table) or W (variable base)
+    uint32_t nbuckets; // sets * 2^(c-1)
+    uint32_t n;        // points in this launch
+    uint32_t table_stride;  // points per window in the table (0 when sets == W)
+    uint32_t base_offset;   // first point of this launch inside the table (point-range sharding)
+    uint32_t acc_threads;   // threads of the accumulate kernel (fixed-size chunks)
+    uint32_t chunk;         // sorted entries per accumulate thread
+    uint32_t slice;         // buckets per bucket-reduce thread
+};
+
+struct MsmWorkspace {
+    Fr* canon;          // n canonical scalars
+    uint32_t* hist;     // nbuckets + 1 (counts, then exclusive offsets)
+    uint32_t* cursor;   // nbuckets
+    uint32_t* sorted;   // n * W point refs grouped by bucket
+    XYZZ* buckets;      // nbuckets
+    XYZZ* partial;      // 2 * acc_threads
+    XYZZ* slice_sums;   // nbuckets / slice
+    XYZZ* set_sums;     // sets (device), copied to host by the caller
+};
+
+size_t msm_workspace_bytes(const MsmPlan& p);
+void msm_workspace_carve(const MsmPlan& p, void* base, MsmWorkspace* ws);
+MsmPlan msm_make_plan(uint32_t n, int c, bool fixed_base, uint32_t table_stride, uint32_t base_offset);
+
+// scalars: n Fr (Montgomery unless scalars_canonical).  Result: ws.set_sums[0..sets) on the device.
+// The optional events bracket the bucket-accumulation kernel (roofline timing).
+void msm_launch(const MsmPlan& p, const MsmWorkspace& ws, const Fr* scalars, bool scalars_canonical,
+                const Affine* table, cudaStream_t st, cudaEvent_t ev_acc_begin = nullptr,
+                cudaEvent_t ev_acc_end = nullptr);
+
+// ---- SRS ------------------------------------------------------------------------
+// gnark big-endian compressed points -> affine Montgomery.  err[] must be preset to 0xffffffff;
+// afterwards err[0] = 1 + index of the lowest bad point (0xffffffff = none), err[1] = kind.
+void srs_decompress_launch(const uint8_t* in_be, uint32_t n, Affine* out, uint32_t* err, cudaStream_t st);
+// table[w * stride + i] = 2^(c*w) * table[i] for w = 1..W-1 (window 0 must already be there)
+void srs_precompute_launch(Affine* table, uint32_t n, uint32_t stride, int c, int W, XYZZ* scratch,
+                           uint32_t batch, cudaStream_t st);
+size_t srs_precompute_scratch_bytes(uint32_t batch, int W);
+// point validation (on curve or identity): err[0] preset 0xffffffff -> 1 + lowest offending index
+void g1_validate_launch(const Affine* pts, uint32_t n, uint32_t* err, cudaStream_t st);
+// SRS_i = tau^i * G (synthetic SRS for benches/tests; tau in Montgomery form)
+void srs_synthetic_launch(Affine* out, uint32_t n, const Fr* tau_mont_host, XYZZ* scratch, cudaStream_t st);
+
+// ---- Fr NTT ---------------------------------------------------------------------
+// tw: omega_N^j for j < N/2 (Montgomery), N = 2^logN >= n.
+void ntt_twiddles_launch(Fr* tw, int logN, const Fr* omega_mont_host, cudaStream_t st);
+// in-place on data (natural order in and out).  inverse scales by 1/n.  batch transforms of size 2^logn
+// laid out back to back.
+void ntt_launch(Fr* data, int logn, uint32_t batch, bool inverse, const Fr* tw, int logN, const Fr* ninv_mont_host,
+                Fr* scratch, cudaStream_t st);
+
+// ---- polynomial glue ------------------------------------------------------------
+// bytes (big-endian 32 B chunks, last chunk zero-right-padded) -> n Fr Montgomery (zero padded to n)
+void bytes_to_fr_launch(const uint8_t* in, uint64_t len_bytes, Fr* out, uint32_t n, cudaStream_t st);
+// n Fr Montgomery -> 32 B big-endian canonical
+void fr_to_bytes_launch(const Fr* in, uint8_t* out, uint32_t n, cudaStream_t st);
+// y = p(z) and quotient q_i = (f_i - y)/(w_i - z), including z = w_m (reference
+// prover/src/kzg.rs:141-174,237-260; primitives/src/helpers.rs:475-535).
+// scratch: n Fr (inverses) + 2 * 1024 Fr partials.  y_out: 1 Fr (Montgomery, device).
+// Batched: `batch` polynomials of n evaluations back to back, z_mont_dev[batch] on the device;
+// q_out may be NULL (evaluation only).  y_out: batch Fr (Montgomery, device).
+void eval_quotient_launch(const Fr* evals, uint32_t n, int logn, uint32_t batch, const Fr* z_mont_dev, const Fr* tw,
+                          int logN, const Fr* ninv_mont_host, Fr* scratch, Fr* q_out, Fr* y_out, cudaStream_t st);
+size_t eval_quotient_scratch_elems(uint32_t n, uint32_t batch);
+// out[i] = base^i (Montgomery), i < n
+void fr_powers_launch(Fr* out, uint32_t n, const Fr* base_mont_host, cudaStream_t st);
+// out[i] = a[i] * b[i]
+void fr_mul_vec_launch(Fr* out, const Fr* a, const Fr* b, uint32_t n, cudaStream_t st);
+// out[0] = sum a[i]*b[i]   (single block; n small: verifier batch)
+void fr_dot_launch(Fr* out, const Fr* a, const Fr* b, uint32_t n, cudaStream_t st);
+
+// ---- microbenchmarks (integer-pipe roof) ------------------------------------------
+void imad_peak_launch(uint32_t* sink, int iters, int mode, int blocks, int threads, cudaStream_t st);
+void fqmul_peak_launch(uint32_t* sink, int iters, int blocks, int threads, cudaStream_t st);
+
+}  // namespace kzgb

@@ -1,0 +1,361 @@
+// Fr glue around the MSM/NTT: blob bytes <-> field elements, barycentric evaluation and the
+// KZG quotient in evaluation form, powers of a challenge.
+//   to_fr_array                         reference primitives/src/helpers.rs:40-57
+//   evaluate_polynomial_in_evaluation_form   primitives/src/helpers.rs:475-535
+//   quotient loop + z-in-domain case    prover/src/kzg.rs:141-174, 237-260
+//   compute_powers                      primitives/src/helpers.rs:298-314
+// The reference does n separate field inversions (twice); here the n denominators z - w_i are
+// inverted with Montgomery's trick: 8 per thread in registers, a product scan across the warp
+// with shuffles, ONE Fermat inversion per warp.
+#include "kzgb_internal.hpp"
+
+namespace kzgb {
+
+__device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
+
+__global__ void __launch_bounds__(256) k_bytes_to_fr(const uint8_t* __restrict__ in, uint64_t len, Fr* __restrict__ out,
+                                                      uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t off = (uint64_t)i * 32;
+    Fr v;
+    if (off >= len) {
+        fe_zero(v);
+        fe_store(&out[i], v);
+        return;
+    }
+    uint32_t be[8];
+    if (off + 32 <= len && ((uintptr_t)in & 15) == 0) {
+        const uint4* q = reinterpret_cast<const uint4*>(in + off);
+        uint4 a = __ldg(q), b = __ldg(q + 1);
+        be[0] = a.x; be[1] = a.y; be[2] = a.z; be[3] = a.w;
+        be[4] = b.x; be[5] = b.y; be[6] = b.z; be[7] = b.w;
+    } else {
+        for (int k = 0; k < 8; k++) {
+            uint32_t w = 0;
+            for (int j = 0; j < 4; j++) {
+                uint64_t p = off + 4 * k + j;
+                uint32_t byte = p < len ? in[p] : 0u;  // trailing partial chunk is right-padded with zeros
+                w |= byte << (8 * j);
+            }
+            be[k] = w;
+        }
+    }
+    for (int k = 0; k < 8; k++) v.l[7 - k] = bswap32(be[k]);
+    fe_to_mont(v, v);  // also reduces any 256-bit value mod r
+    fe_store(&out[i], v);
+}
+
+__global__ void __launch_bounds__(256) k_fr_to_bytes(const Fr* __restrict__ in, uint8_t* __restrict__ out, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr v = fe_load_ro(&in[i]);
+    fe_from_mont(v, v);
+    uint4* q = reinterpret_cast<uint4*>(out + (size_t)i * 32);
+    q[0] = make_uint4(bswap32(v.l[7]), bswap32(v.l[6]), bswap32(v.l[5]), bswap32(v.l[4]));
+    q[1] = make_uint4(bswap32(v.l[3]), bswap32(v.l[2]), bswap32(v.l[1]), bswap32(v.l[0]));
+}
+
+// w_i = omega_n^i from the omega_N table (i < n)
+__device__ __forceinline__ Fr domain_root(const Fr* __restrict__ tw, uint32_t i, int logn, int logN) {
+    Fr w;
+    if (logn == 0) { fe_one(w); return w; }
+    uint32_t half = 1u << (logn - 1);
+    if (i < half) return fe_load_ro(&tw[i << (logN - logn)]);
+    w = fe_load_ro(&tw[(i - half) << (logN - logn)]);
+    fe_neg(w, w);
+    return w;
+}
+
+__device__ __forceinline__ Fr shfl_fe(const Fr& v, int src) {
+    Fr r;
+#pragma unroll
+    for (int k = 0; k < 8; k++) r.l[k] = __shfl_sync(0xffffffffu, v.l[k], src);
+    return r;
+}
+
+static constexpr int EVAL_E = 8;        // denominators per thread
+static constexpr int EVAL_THREADS = 256;
+static constexpr int EVAL_TILE = EVAL_E * EVAL_THREADS;
+
+// block reduction of one Fr per thread into out (thread 0 writes)
+__device__ __forceinline__ void block_sum_fr(Fr v, Fr* out) {
+    __shared__ uint32_t red[8][EVAL_THREADS / 32];
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int off = 16; off >= 1; off >>= 1) {
+        Fr o;
+#pragma unroll
+        for (int k = 0; k < 8; k++) o.l[k] = __shfl_down_sync(0xffffffffu, v.l[k], off);
+        fe_add(v, v, o);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) red[k][wid] = v.l[k];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        Fr acc = v;
+        for (int w = 1; w < EVAL_THREADS / 32; w++) {
+            Fr o;
+#pragma unroll
+            for (int k = 0; k < 8; k++) o.l[k] = red[k][w];
+            fe_add(acc, acc, o);
+        }
+        fe_store(out, acc);
+    }
+    __syncthreads();
+}
+
+// Batched over blockIdx.y (one polynomial of n evaluations per batch entry, its own z).
+// inv[i] = 1/(z - w_i) (1 where z == w_i, recorded in zidx = i + 1); partial[block] = sum f_i w_i inv[i]
+__global__ void __launch_bounds__(EVAL_THREADS) k_eval_inverses(const Fr* __restrict__ evals_all, uint32_t n, int logn,
+                                                                const Fr* __restrict__ z_all, const Fr* __restrict__ tw,
+                                                                int logN, Fr* __restrict__ inv_all, Fr* __restrict__ partial_all,
+                                                                uint32_t nparts, uint32_t* __restrict__ zidx_all) {
+    const uint32_t bi = blockIdx.y;
+    const Fr* evals = evals_all + (size_t)bi * n;
+    Fr* inv = inv_all + (size_t)bi * n;
+    Fr* partial = partial_all + (size_t)bi * nparts;
+    uint32_t* zidx = zidx_all + bi;
+    const Fr z = fe_load(&z_all[bi]);
+    const uint32_t base = blockIdx.x * EVAL_TILE + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
+    Fr d[EVAL_E], pp[EVAL_E];
+    Fr one; fe_one(one);
+    uint32_t zero_k = 0xffffffffu;
+#pragma unroll
+    for (int k = 0; k < EVAL_E; k++) {
+        uint32_t i = base + k * EVAL_THREADS;
+        if (i < n) {
+            Fr w = domain_root(tw, i, logn, logN);
+            fe_sub(d[k], z, w);
+            if (fe_is_zero(d[k])) { d[k] = one; zero_k = k; zidx[0] = i + 1; }
+        } else {
+            d[k] = one;
+        }
+        if (k == 0) pp[0] = d[0]; else fe_mul(pp[k], pp[k - 1], d[k]);
+    }
+    // warp product scans of the per-thread products
+    Fr inc = pp[EVAL_E - 1];
+    for (int off = 1; off < 32; off <<= 1) {
+        Fr o;
+#pragma unroll
+        for (int k = 0; k < 8; k++) o.l[k] = __shfl_up_sync(0xffffffffu, inc.l[k], off);
+        if ((int)lane >= off) fe_mul(inc, inc, o);
+    }
+    Fr suf = pp[EVAL_E - 1];
+    for (int off = 1; off < 32; off <<= 1) {
+        Fr o;
+#pragma unroll
+        for (int k = 0; k < 8; k++) o.l[k] = __shfl_down_sync(0xffffffffu, suf.l[k], off);
+        if ((int)lane + off < 32) fe_mul(suf, suf, o);
+    }
+    Fr total = shfl_fe(inc, 31);
+    Fr tinv; fe_inv(tinv, total);  // one Fermat inversion per warp (uniform across lanes)
+    Fr exc, sufx;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        exc.l[k] = __shfl_up_sync(0xffffffffu, inc.l[k], 1);
+        sufx.l[k] = __shfl_down_sync(0xffffffffu, suf.l[k], 1);
+    }
+    if (lane == 0) exc = one;
+    if (lane == 31) sufx = one;
+    Fr run;
+    fe_mul(run, tinv, exc);
+    fe_mul(run, run, sufx);  // 1 / (product of this thread's denominators)
+    Fr sum; fe_zero(sum);
+#pragma unroll
+    for (int k = EVAL_E - 1; k >= 0; k--) {
+        Fr iv;
+        if (k > 0) { fe_mul(iv, run, pp[k - 1]); fe_mul(run, run, d[k]); } else iv = run;
+        uint32_t i = base + k * EVAL_THREADS;
+        if (i < n) {
+            fe_store(&inv[i], iv);
+            if ((uint32_t)k != zero_k) {
+                Fr f = fe_load_ro(&evals[i]);
+                Fr w = domain_root(tw, i, logn, logN);
+                fe_mul(f, f, w);
+                fe_mul(f, f, iv);
+                fe_add(sum, sum, f);
+            }
+        }
+    }
+    block_sum_fr(sum, &partial[blockIdx.x]);
+}
+
+// y = (z^n - 1)/n * sum   or   f_m when z = w_m          (one block per batch entry)
+__global__ void __launch_bounds__(EVAL_THREADS) k_eval_finish(const Fr* __restrict__ evals_all, uint32_t n, int logn,
+                                                              const Fr* __restrict__ z_all, Fr ninv,
+                                                              const Fr* __restrict__ partial_all, uint32_t nparts,
+                                                              const uint32_t* __restrict__ zidx_all, Fr* __restrict__ y_all) {
+    const uint32_t bi = blockIdx.x;
+    const Fr* evals = evals_all + (size_t)bi * n;
+    const Fr* partial = partial_all + (size_t)bi * nparts;
+    Fr sum; fe_zero(sum);
+    for (uint32_t k = threadIdx.x; k < nparts; k += EVAL_THREADS) {
+        Fr v = fe_load(&partial[k]);
+        fe_add(sum, sum, v);
+    }
+    __shared__ Fr total;
+    block_sum_fr(sum, &total);
+    if (threadIdx.x == 0) {
+        uint32_t zi = zidx_all[bi];
+        Fr y;
+        if (zi != 0) {
+            y = fe_load(&evals[zi - 1]);
+        } else {
+            Fr zn = fe_load(&z_all[bi]);
+            for (int k = 0; k < logn; k++) fe_sqr(zn, zn);
+            Fr one; fe_one(one);
+            fe_sub(zn, zn, one);
+            Fr t = total;
+            fe_mul(y, t, zn);
+            fe_mul(y, y, ninv);
+        }
+        fe_store(&y_all[bi], y);
+    }
+}
+
+// q_i = (y - f_i) * inv_i ; when z = w_m also partial sums of q_i * w_i (i != m)
+__global__ void __launch_bounds__(EVAL_THREADS) k_quotient(const Fr* __restrict__ evals_all, uint32_t n, int logn,
+                                                           const Fr* __restrict__ tw, int logN, const Fr* __restrict__ inv_all,
+                                                           const Fr* __restrict__ y_all, const uint32_t* __restrict__ zidx_all,
+                                                           Fr* __restrict__ q_all, Fr* __restrict__ partial_all, uint32_t nparts) {
+    const uint32_t bi = blockIdx.y;
+    const Fr* evals = evals_all + (size_t)bi * n;
+    const Fr* inv = inv_all + (size_t)bi * n;
+    Fr* q = q_all + (size_t)bi * n;
+    Fr* partial = partial_all + (size_t)bi * nparts;
+    const uint32_t i = blockIdx.x * EVAL_THREADS + threadIdx.x;
+    const uint32_t zi = zidx_all[bi];
+    Fr y = fe_load(&y_all[bi]);
+    Fr term; fe_zero(term);
+    if (i < n) {
+        Fr f = fe_load_ro(&evals[i]);
+        Fr iv = fe_load_ro(&inv[i]);
+        Fr qi;
+        fe_sub(qi, y, f);
+        fe_mul(qi, qi, iv);
+        if (zi != 0 && i == zi - 1) fe_zero(qi);  // patched by k_quotient_fix
+        fe_store(&q[i], qi);
+        if (zi != 0 && i != zi - 1) {
+            Fr w = domain_root(tw, i, logn, logN);
+            fe_mul(term, qi, w);
+        }
+    }
+    if (zi != 0) block_sum_fr(term, &partial[blockIdx.x]);
+}
+
+// q_m = -(1/z) * sum_{i != m} q_i w_i  with 1/z = w_{(n-m) mod n}     (prover/src/kzg.rs:237-260)
+__global__ void __launch_bounds__(EVAL_THREADS) k_quotient_fix(uint32_t n, int logn, const Fr* __restrict__ tw, int logN,
+                                                               const Fr* __restrict__ partial_all, uint32_t nparts,
+                                                               const uint32_t* __restrict__ zidx_all, Fr* __restrict__ q_all) {
+    const uint32_t bi = blockIdx.x;
+    const uint32_t zi = zidx_all[bi];
+    if (zi == 0) return;
+    const Fr* partial = partial_all + (size_t)bi * nparts;
+    Fr* q = q_all + (size_t)bi * n;
+    Fr sum; fe_zero(sum);
+    for (uint32_t k = threadIdx.x; k < nparts; k += EVAL_THREADS) {
+        Fr v = fe_load(&partial[k]);
+        fe_add(sum, sum, v);
+    }
+    __shared__ Fr total;
+    block_sum_fr(sum, &total);
+    if (threadIdx.x == 0) {
+        uint32_t m = zi - 1;
+        Fr zinv = domain_root(tw, (n - m) & (n - 1), logn, logN);
+        Fr r;
+        Fr t = total;
+        fe_mul(r, t, zinv);
+        fe_neg(r, r);
+        fe_store(&q[m], r);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_fr_powers(Fr* __restrict__ out, uint32_t n, Fr base) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t e[8] = {i, 0, 0, 0, 0, 0, 0, 0};
+    Fr r;
+    fe_pow(r, base, e);
+    fe_store(&out[i], r);
+}
+
+__global__ void __launch_bounds__(256) k_fr_mul_vec(Fr* __restrict__ out, const Fr* __restrict__ a, const Fr* __restrict__ b,
+                                                     uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr x = fe_load_ro(&a[i]), y = fe_load_ro(&b[i]);
+    fe_mul(x, x, y);
+    fe_store(&out[i], x);
+}
+
+__global__ void __launch_bounds__(EVAL_THREADS) k_fr_dot(Fr* __restrict__ out, const Fr* __restrict__ a,
+                                                         const Fr* __restrict__ b, uint32_t n) {
+    Fr sum; fe_zero(sum);
+    for (uint32_t k = threadIdx.x; k < n; k += EVAL_THREADS) {
+        Fr x = fe_load_ro(&a[k]), y = fe_load_ro(&b[k]);
+        fe_mul(x, x, y);
+        fe_add(sum, sum, x);
+    }
+    block_sum_fr(sum, out);
+}
+
+// ---------------------------------------------------------------------------------
+void bytes_to_fr_launch(const uint8_t* in, uint64_t len_bytes, Fr* out, uint32_t n, cudaStream_t st) {
+    if (!n) return;
+    k_bytes_to_fr<<<(n + 255) / 256, 256, 0, st>>>(in, len_bytes, out, n);
+    g_launch_count++;
+}
+void fr_to_bytes_launch(const Fr* in, uint8_t* out, uint32_t n, cudaStream_t st) {
+    if (!n) return;
+    k_fr_to_bytes<<<(n + 255) / 256, 256, 0, st>>>(in, out, n);
+    g_launch_count++;
+}
+
+size_t eval_quotient_scratch_elems(uint32_t n, uint32_t batch) {
+    uint32_t parts1 = (n + EVAL_TILE - 1) / EVAL_TILE;
+    uint32_t parts2 = (n + EVAL_THREADS - 1) / EVAL_THREADS;
+    // inverses, partial sums (both kernels), zidx words (rounded up to whole Fr slots)
+    return (size_t)batch * ((size_t)n + parts1 + parts2) + ((size_t)batch * 4 + 31) / 32 + 1;
+}
+
+void eval_quotient_launch(const Fr* evals, uint32_t n, int logn, uint32_t batch, const Fr* z_mont_dev, const Fr* tw,
+                          int logN, const Fr* ninv_mont_host, Fr* scratch, Fr* q_out, Fr* y_out, cudaStream_t st) {
+    if (!batch) return;
+    uint32_t parts1 = (n + EVAL_TILE - 1) / EVAL_TILE;
+    uint32_t parts2 = (n + EVAL_THREADS - 1) / EVAL_THREADS;
+    Fr* inv = scratch;
+    Fr* partial1 = inv + (size_t)batch * n;
+    Fr* partial2 = partial1 + (size_t)batch * parts1;
+    uint32_t* zidx = reinterpret_cast<uint32_t*>(partial2 + (size_t)batch * parts2);
+    cudaMemsetAsync(zidx, 0, (size_t)batch * 4, st);
+    k_eval_inverses<<<dim3(parts1, batch), EVAL_THREADS, 0, st>>>(evals, n, logn, z_mont_dev, tw, logN, inv, partial1,
+                                                                  parts1, zidx);
+    k_eval_finish<<<batch, EVAL_THREADS, 0, st>>>(evals, n, logn, z_mont_dev, *ninv_mont_host, partial1, parts1, zidx, y_out);
+    g_launch_count += 2;
+    if (q_out) {
+        k_quotient<<<dim3(parts2, batch), EVAL_THREADS, 0, st>>>(evals, n, logn, tw, logN, inv, y_out, zidx, q_out,
+                                                                 partial2, parts2);
+        k_quotient_fix<<<batch, EVAL_THREADS, 0, st>>>(n, logn, tw, logN, partial2, parts2, zidx, q_out);
+        g_launch_count += 2;
+    }
+}
+
+void fr_powers_launch(Fr* out, uint32_t n, const Fr* base_mont_host, cudaStream_t st) {
+    if (!n) return;
+    k_fr_powers<<<(n + 255) / 256, 256, 0, st>>>(out, n, *base_mont_host);
+    g_launch_count++;
+}
+void fr_mul_vec_launch(Fr* out, const Fr* a, const Fr* b, uint32_t n, cudaStream_t st) {
+    if (!n) return;
+    k_fr_mul_vec<<<(n + 255) / 256, 256, 0, st>>>(out, a, b, n);
+    g_launch_count++;
+}
+void fr_dot_launch(Fr* out, const Fr* a, const Fr* b, uint32_t n, cudaStream_t st) {
+    k_fr_dot<<<1, EVAL_THREADS, 0, st>>>(out, a, b, n);
+    g_launch_count++;
+}
+
+}  // namespace kzgb

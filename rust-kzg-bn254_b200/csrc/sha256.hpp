@@ -1,0 +1,26 @@
+// Host SHA-256 for the Fiat-Shamir transcripts (reference primitives/src/helpers.rs:382-390,
+// 411-472; verifier/src/batch.rs:76-168).  A single message hash is inherently sequential, so it
+// stays on the host and is overlapped with the GPU work of the same blob (the 32-byte commitment
+// is the LAST thing absorbed, so everything before it is hashed while the commitment MSM runs).
+// Uses the SHA-NI extension when the CPU has it.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+namespace kzgb {
+
+struct Sha256 {
+    uint32_t h[8];
+    uint8_t buf[64];
+    uint64_t total;
+    size_t fill;
+    Sha256() { reset(); }
+    void reset();
+    void update(const void* data, size_t len);
+    void finish(uint8_t out[32]);
+};
+
+void sha256(const void* data, size_t len, uint8_t out[32]);
+bool sha256_has_shani();
+
+}  // namespace kzgb

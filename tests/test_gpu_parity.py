@@ -1,0 +1,299 @@
+"""GPU parity tests: every result of the CUDA path is compared bit-for-bit with the CPU oracle
+and with the reference's own fixtures.  All calls go through the C ABI (via the Python mirror)."""
+import random
+
+import pytest
+
+import golden_data as g
+from __graft_entry__ import load_package
+from oracle import bn254 as o
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    return load_package()
+
+
+@pytest.fixture(scope="module")
+def eng(pkg):
+    return pkg.Engine(0)
+
+
+@pytest.fixture(scope="module")
+def ref_srs(pkg, eng):
+    """The reference's prover/tests/test-files/g1.point loaded through the GPU decompressor."""
+    return pkg.SRS.from_gnark_bytes(g.g1_point_bytes(), engine=eng)
+
+
+@pytest.fixture(scope="module")
+def ref_srs_points():
+    return g.srs_points_string()
+
+
+def test_integer_pipe_microbench(pkg, eng):
+    import ctypes as C
+
+    for kind in range(4):
+        v = C.c_double(0)
+        eng.check(pkg.lib.kzgb_microbench(eng.h, kind, C.byref(v)))
+        assert v.value > 1e9
+        print(f"microbench kind {kind}: {v.value:.4e} ops/s")
+
+
+def test_srs_decompression_kat(ref_srs, ref_srs_points):
+    """read_g1_point_from_bytes_be (helpers.rs:175-226) vs srs.g1.points.string: 3000/3000."""
+    assert len(ref_srs) == 3000
+    assert ref_srs.points() == ref_srs_points
+
+
+def test_srs_load_errors(pkg, eng):
+    bad = bytearray(g.g1_point_bytes()[: 32 * 8])
+    # x = 4 with flag 0b10: 4^3 + 3 = 67 is a non-residue?  find one deterministically
+    x = 2
+    while o.fq_sqrt((x**3 + 3) % o.P) is not None:
+        x += 1
+    bad[32 * 5 : 32 * 6] = bytes([0x80]) + x.to_bytes(31, "big")
+    with pytest.raises(pkg.KzgError) as e:
+        pkg.SRS.from_gnark_bytes(bytes(bad), engine=pkg.Engine(0))
+    assert e.value.variant == "NotOnCurveError" and "point 5" in e.value.msg
+    inf_bad = bytes([0x40]) + bytes(30) + b"\x01"
+    with pytest.raises(pkg.KzgError) as e:
+        pkg.SRS.from_gnark_bytes(inf_bad, engine=pkg.Engine(0))
+    assert e.value.variant == "DeserializationError"
+    s = pkg.SRS.from_gnark_bytes(bytes([0x40]) + bytes(31) + g.g1_point_bytes()[:32], engine=pkg.Engine(0))
+    assert s.points() == [None, (1, 2)]
+
+
+def test_srs_new_order_error(pkg, tmp_path):
+    # prover/tests/kzg_test.rs:19-28
+    p = tmp_path / "g1.point"
+    p.write_bytes(g.g1_point_bytes())
+    with pytest.raises(pkg.KzgError) as e:
+        pkg.SRS(str(p), 3000, 3001)
+    assert e.value.msg == "Number of points to load exceeds SRS order."
+    s = pkg.SRS(str(p), 3000, 100)
+    assert s.points() == g.srs_points_string()[:100]
+
+
+def test_to_fr_array_kat(pkg, eng):
+    assert pkg.to_fr_array(g.blobs_txt(), eng) == g.blobs_from_fr()
+    for raw in (b"", b"\x01", bytes(range(33)), b"\xff" * 95, g.gettysburg()):
+        assert pkg.to_fr_array(raw, eng) == o.to_fr_array(raw)
+    frs = g.blobs_from_fr()[:77] + [0, 1, o.R - 1]
+    assert pkg.to_byte_array(frs, 32 * len(frs), eng) == o.to_byte_array(frs, 32 * len(frs))
+    assert pkg.to_byte_array(frs, 100, eng) == o.to_byte_array(frs, 100)
+
+
+@pytest.mark.parametrize("logn", [0, 1, 2, 3, 5, 9, 10, 11, 12, 13])
+def test_ntt_matches_oracle(pkg, eng, logn):
+    rnd = random.Random(100 + logn)
+    n = 1 << logn
+    v = [rnd.randrange(o.R) for _ in range(n)]
+    assert pkg._ntt(v, False, eng) == o.fft(v)
+    assert pkg._ntt(v, True, eng) == o.ifft(v)
+
+
+@pytest.mark.parametrize("logn", [16, 19, 21])
+def test_ntt_roundtrip_large(pkg, eng, logn):
+    """FFT o IFFT identity (primitives/tests/polynomial_test.rs:47-64) at bench sizes, plus a
+    delta-function known answer: fft(e_1)[i] = w^i."""
+    import ctypes as C
+
+    n = 1 << logn
+    rnd = random.Random(logn)
+    seed = [rnd.randrange(o.R) for _ in range(256)]
+    vals = (seed * (n // 256))[:n]
+    buf = C.create_string_buffer(pkg.fr_to_mont_bytes(seed) * (n // 256), 32 * n)
+    orig = buf.raw
+    eng.check(pkg.lib.kzgb_ntt_fr(eng.h, buf, n, 0))
+    assert buf.raw != orig
+    eng.check(pkg.lib.kzgb_ntt_fr(eng.h, buf, n, 1))
+    assert buf.raw == orig
+    delta = C.create_string_buffer(bytes(32) + pkg.fr_to_mont_bytes([1]) + bytes(32 * (n - 2)), 32 * n)
+    eng.check(pkg.lib.kzgb_ntt_fr(eng.h, delta, n, 0))
+    w = o.PRIMITIVE_ROOTS_OF_UNITY[logn]
+    for i in (0, 1, 2, 3, n // 2, n - 1, 12345 % n):
+        assert pkg.fr_from_mont_bytes(delta.raw[32 * i : 32 * i + 32])[0] == pow(w, i, o.R)
+    del vals
+
+
+def test_msm_var_matches_oracle(pkg, eng, ref_srs_points):
+    rnd = random.Random(1)
+    for m in (1, 2, 33, 300):
+        pts = ref_srs_points[:m]
+        sc = [rnd.randrange(o.R) for _ in range(m)]
+        assert pkg.g1_lincomb(pts, sc, eng) == o.msm(pts, sc)
+    # edge cases: zero scalars, identity bases, duplicate bases with equal scalars (forces P + P in a
+    # bucket), P and -P with equal scalars (forces P + (-P)), scalars 1 and r - 1
+    P1, P2 = ref_srs_points[1], ref_srs_points[2]
+    pts = [P1, P1, P2, o.g1_neg(P2), None, P1, P2, P2]
+    sc = [5, 5, 77, 77, 123456, 0, o.R - 1, 1]
+    assert pkg.g1_lincomb(pts, sc, eng) == o.msm(pts, sc)
+    assert pkg.g1_lincomb([P1, P2], [0, 0], eng) is None
+    assert pkg.g1_lincomb([], [], eng) is None
+    big = [rnd.randrange(o.R) for _ in range(64)]
+    same = [ref_srs_points[7]] * 64
+    assert pkg.g1_lincomb(same, big, eng) == o.g1_mul(ref_srs_points[7], sum(big) % o.R)
+    with pytest.raises(pkg.KzgError) as e:
+        pkg.g1_lincomb([P1], [1, 2], eng)
+    assert e.value.variant == "MsmError"
+
+
+def test_msm_fixed_base_matches_oracle(pkg, ref_srs, ref_srs_points):
+    rnd = random.Random(2)
+    kzg = pkg.KZG()
+    for n in (1, 2, 64, 1024):
+        sc = [rnd.randrange(o.R) for _ in range(n)]
+        got = kzg.commit_coeff_form(pkg.PolynomialCoeffForm(sc), ref_srs)
+        assert got == o.msm(ref_srs_points[:n], sc)
+    # all-equal coefficients: every point of a window lands in one bucket (chunk-spanning buckets)
+    sc = [0x1234567890ABCDEF1234567890ABCDEF] * 2048
+    assert kzg.commit_coeff_form(pkg.PolynomialCoeffForm(sc), ref_srs) == o.msm(ref_srs_points[:2048], sc)
+    zero = kzg.commit_coeff_form(pkg.PolynomialCoeffForm([0] * 64), ref_srs)
+    assert zero is None  # zero polynomial -> identity (verifier/tests/tests.rs:239-269)
+    with pytest.raises(pkg.KzgError) as e:
+        kzg.commit_coeff_form(pkg.PolynomialCoeffForm([1] * 4096), ref_srs)
+    assert e.value.variant == "SerializationError" and e.value.msg == "polynomial length is not correct"
+
+
+def test_gettysburg_commit_and_proof_kats(pkg, ref_srs, ref_srs_points):
+    """kzg.proof.eq.input: 40 proofs at roots of unity (z in the domain -> kzg.rs:237-260)."""
+    blob = pkg.Blob.from_raw_data(g.gettysburg())
+    kzg = pkg.KZG()
+    kzg.calculate_and_store_roots_of_unity(len(blob))
+    c = kzg.commit_blob(blob, ref_srs)
+    assert pkg.g1_to_gnark_be(c).hex() == "868bf472ebc0e26c297f8a9257c3f42a38af1e4612b60f6ac64d57dc272d50b1"
+    poly = blob.to_polynomial_eval_form(ref_srs.engine)
+    assert len(poly) == 64
+    assert kzg.commit_eval_form(poly, ref_srs) == c
+    assert kzg.commit_coeff_form(poly.to_coeff_form(ref_srs.engine), ref_srs) == c  # kzg_test.rs:57-89
+    for idx, x, y in g.proof_eq_input():
+        assert kzg.compute_proof_with_known_z_fr_index(poly, idx, ref_srs) == (x, y)
+
+
+def test_g1_ifft_kat(pkg, ref_srs):
+    kzg = pkg.KZG()
+    assert kzg.g1_ifft(64, ref_srs) == g.lagrange_srs_64()
+    with pytest.raises(pkg.KzgError) as e:
+        kzg.g1_ifft(15, ref_srs)
+    assert e.value.variant == "FFTError" and "length provided is not a power of 2" in e.value.msg
+
+
+def test_evaluate_polynomial(pkg, eng):
+    rnd = random.Random(3)
+    for raw in (g.gettysburg(), b"short", bytes(rnd.getrandbits(8) for _ in range(31 * 300))):
+        bo = o.Blob.from_raw_data(raw)
+        po = bo.to_polynomial_eval_form()
+        pg = pkg.PolynomialEvalForm(po.evaluations[: len(bo) // 32])
+        roots = o.calculate_roots_of_unity(len(bo))
+        for z in (rnd.randrange(o.R), 0, 1, roots[-1], roots[len(roots) // 3]):
+            assert pkg.evaluate_polynomial_in_evaluation_form(pg, z, eng) == o.evaluate_polynomial_in_evaluation_form(po, z)
+
+
+def test_blob_proof_matches_oracle(pkg, ref_srs, ref_srs_points):
+    rnd = random.Random(4)
+    for raw in (g.gettysburg(), b"a", bytes(rnd.getrandbits(8) for _ in range(31 * 100 + 5))):
+        blob = pkg.Blob.from_raw_data(raw)
+        bo = o.Blob.from_raw_data(raw)
+        kzg, ko = pkg.KZG(), o.KZG()
+        kzg.calculate_and_store_roots_of_unity(len(blob))
+        ko.calculate_and_store_roots_of_unity(len(bo))
+        c = kzg.commit_blob(blob, ref_srs)
+        assert c == ko.commit_blob(bo, ref_srs_points)
+        assert kzg.compute_blob_proof(blob, c, ref_srs) == ko.compute_blob_proof(bo, c, ref_srs_points)
+    # full-range canonical blob (blobs.txt prefix), ragged non-canonical blob
+    full = g.blobs_txt()[: 32 * 200]
+    blob, bo = pkg.Blob.new(full), o.Blob(full)
+    kzg, ko = pkg.KZG(), o.KZG()
+    kzg.calculate_and_store_roots_of_unity(len(blob))
+    ko.calculate_and_store_roots_of_unity(len(bo))
+    c = kzg.commit_blob(blob, ref_srs)
+    assert c == ko.commit_blob(bo, ref_srs_points)
+    assert kzg.compute_blob_proof(blob, c, ref_srs) == ko.compute_blob_proof(bo, c, ref_srs_points)
+    ragged = b"\xff" * 45 + bytes(range(50))
+    blob, bo = pkg.Blob.from_unchecked(ragged), o.Blob.from_unchecked(ragged)
+    kzg.calculate_and_store_roots_of_unity(len(blob))
+    ko.calculate_and_store_roots_of_unity(len(bo))
+    c = kzg.commit_blob(blob, ref_srs)
+    assert c == ko.commit_blob(bo, ref_srs_points)
+    assert kzg.compute_blob_proof(blob, c, ref_srs) == ko.compute_blob_proof(bo, c, ref_srs_points)
+    # invalid commitment rejected (prover/tests/kzg_test.rs:163-196)
+    with pytest.raises(pkg.KzgError) as e:
+        kzg.compute_blob_proof(blob, (1, 3), ref_srs)
+    assert e.value.variant == "NotOnCurveError"
+    # roots not stored for this length -> GenericError (kzg.rs:135-139)
+    with pytest.raises(pkg.KzgError) as e:
+        pkg.KZG().compute_blob_proof(blob, c, ref_srs)
+    assert e.value.msg == "inconsistent length between blob and root of unities"
+
+
+def test_srs_capacity_error(pkg, eng):
+    srs = pkg.SRS.from_gnark_bytes(g.g1_point_bytes()[: 32 * 16], engine=pkg.Engine(0))
+    with pytest.raises(pkg.KzgError) as e:
+        pkg.KZG().commit_blob(pkg.Blob.from_raw_data(g.gettysburg()), srs)
+    assert e.value.variant == "SrsCapacityExceeded"
+
+
+def test_synthetic_srs_and_tau_trick(pkg):
+    """SRS_i = tau^i G generated on the GPU; MSM == (sum s_i tau^i) G, n = 2^12 (config 1)."""
+    n = 1 << 12
+    srs = pkg.SRS.synthetic(n, o.SYNTH_TAU)
+    ref = o.synthetic_srs(64)
+    assert srs.points(0, 64) == ref
+    assert srs.points(n - 1, 1) == [o.g1_mul(o.G1_GEN, pow(o.SYNTH_TAU, n - 1, o.R))]
+    blob = pkg.Blob.new(g.blobs_txt())  # exactly 4096 full-range canonical Fr (config 1 blob)
+    kzg = pkg.KZG()
+    kzg.calculate_and_store_roots_of_unity(len(blob))
+    c = kzg.commit_blob(blob, srs)
+    evals = g.blobs_from_fr()
+    coeffs = o.ifft(evals)
+    assert c == o.tau_trick_msm(coeffs)
+    bo = o.Blob(g.blobs_txt())
+    z = o.compute_challenge(bo, c)
+    assert pkg.compute_challenge(blob, c) == z
+    y = o.evaluate_polynomial_in_evaluation_form(bo.to_polynomial_eval_form(), z)
+    ptau = 0
+    for cf in reversed(coeffs):
+        ptau = (ptau * o.SYNTH_TAU + cf) % o.R
+    expect = o.g1_mul(o.G1_GEN, (ptau - y) * o.fr_inv((o.SYNTH_TAU - z) % o.R) % o.R)
+    assert kzg.compute_blob_proof(blob, c, srs) == expect
+
+
+def test_batch_commit_and_prove(pkg, ref_srs, ref_srs_points):
+    rnd = random.Random(6)
+    raws = [g.gettysburg(), b"b", bytes(rnd.getrandbits(8) for _ in range(31 * 64)), bytes(31 * 17), g.gettysburg()[:500],
+            bytes(rnd.getrandbits(8) for _ in range(31 * 256 - 3)), b"zz" * 40]
+    blobs = [pkg.Blob.from_raw_data(r) for r in raws]
+    cs, ps = pkg.KZG.commit_and_prove_blobs(blobs, ref_srs)
+    for r, cb, pb in zip(raws, cs, ps):
+        bo = o.Blob.from_raw_data(r)
+        ko = o.KZG()
+        ko.calculate_and_store_roots_of_unity(len(bo))
+        c = ko.commit_blob(bo, ref_srs_points)
+        assert cb == o.g1_serialize_compressed(c)
+        assert pb == o.g1_serialize_compressed(ko.compute_blob_proof(bo, c, ref_srs_points))
+
+
+def test_verify_batch_rlc(pkg, ref_srs, ref_srs_points):
+    """verifier/src/batch.rs:16-249 up to the pairing: both G1 outputs equal the oracle's."""
+    rnd = random.Random(8)
+    raws = [g.gettysburg(), b"hello", bytes(rnd.getrandbits(8) for _ in range(31 * 30)), g.gettysburg()]
+    blobs_o = [o.Blob.from_raw_data(r) for r in raws]
+    cs, ps = [], []
+    for bo in blobs_o:
+        ko = o.KZG()
+        ko.calculate_and_store_roots_of_unity(len(bo))
+        c = ko.commit_blob(bo, ref_srs_points)
+        cs.append(c)
+        ps.append(ko.compute_blob_proof(bo, c, ref_srs_points))
+    lhs_o, rhs_o = o.verify_blob_kzg_proof_batch_rlc(blobs_o, cs, ps)
+    blobs = [pkg.Blob.from_raw_data(r) for r in raws]
+    lhs, rhs = pkg.verify_blob_kzg_proof_batch_rlc(blobs, cs, ps, ref_srs.engine)
+    assert (lhs, rhs) == (lhs_o, rhs_o)
+    with pytest.raises(pkg.KzgError) as e:
+        pkg.verify_blob_kzg_proof_batch_rlc(blobs, [(1, 3)] + cs[1:], ps, ref_srs.engine)
+    assert e.value.variant == "NotOnCurveError"
+    with pytest.raises(pkg.KzgError):
+        pkg.verify_blob_kzg_proof_batch_rlc(blobs, cs[:2], ps, ref_srs.engine)
