@@ -1,0 +1,322 @@
+#!/usr/bin/env python3
+"""Headline benchmark: blob commits+proofs/s on 2^19-Fr (16 MiB) blobs (BASELINE.json configs[1]).
+
+One step = commit_blob + compute_blob_proof for a batch of B distinct 16 MiB blobs on each GPU
+(eval-form IFFT + 2^19-point G1 MSM for the commitment, Fiat-Shamir challenge, barycentric
+evaluation + quotient, IFFT + MSM for the proof).  N > 1 shards by blob: every rank runs its own
+batch, no collective on the data path ("weak" scaling).
+
+  value : blobs/s with the blob bytes already resident in HBM (kzgb_commit_and_prove_blobs_dev)
+  e2e   : the same through the host-buffer C-ABI call (kzgb_commit_and_prove_blobs): pinned host
+          blobs, H2D copies and the D2H of every commitment/proof inside the timed region
+  roofline : the bucket-accumulation kernel (k_accumulate), achieved Fq multiplications/s against
+          the integer-pipe roof measured live (IMAD/s / 136 IMAD per Montgomery multiplication)
+  cpu_baseline : the CPU oracle (C++ restatement of the arkworks algorithm) on the box's cores
+
+`--impl reference` times only the CPU oracle (the reference is Rust + arkworks and cannot be
+built in this image -- see DESIGN.md) on the same metric/config.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LOG_N = 19
+TAU = 2480609854371098259468018140899271569021640719453669963486734696239309822386  # SHA-256("kzg-bn254-b200/tau/v1") mod r
+R_MOD = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+FQMUL_PER_MADD = 10  # XYZZ += affine: 8M + 2S
+IMAD_PER_FQMUL = 136
+
+
+def make_blob(n_elems: int, seed: int):
+    """D1 'payload' distribution: byte 0 of every 32 B element is 0 (what Blob::from_raw_data yields)."""
+    import numpy as np
+
+    rng = np.random.default_rng(seed)
+    a = rng.integers(0, 256, size=(n_elems, 32), dtype=np.uint8)
+    a[:, 0] = 0
+    return a.reshape(-1)
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = [int(r[0]) for r in self.rows if r[0].isdigit()]
+        mx = [int(r[1]) for r in self.rows if r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) >= 6 and r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def load_oracle_lib():
+    path = os.path.join(ROOT, "oracle", "liboracle_cpu.so")
+    if not os.path.exists(path):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")])
+    lib = C.CDLL(path)
+    lib.ref_hw_threads.restype = C.c_int
+    return lib
+
+
+def cpu_commit_and_prove(olib, blob_bytes: bytes, srs_xy: bytes, threads: int) -> float:
+    """One blob through the CPU oracle: commit_blob + compute_blob_proof, Fr-IFFT + MSM form."""
+    cm = C.create_string_buffer(64)
+    pf = C.create_string_buffer(64)
+    t0 = time.perf_counter()
+    olib.ref_commit_blob(blob_bytes, C.c_size_t(len(blob_bytes)), srs_xy, threads, 0, cm)
+    olib.ref_blob_proof(blob_bytes, C.c_size_t(len(blob_bytes)), cm, srs_xy, threads, 0, pf)
+    return time.perf_counter() - t0
+
+
+def cpu_srs(olib, n: int, threads: int) -> bytes:
+    """tau^i * G on the CPU for the reference arm (no GPU involved)."""
+    # cheap route: SRS_i = SRS_{i-1} * tau is a scalar mul each; instead build via the oracle MSM-free path:
+    from oracle import bn254 as o
+
+    # 2^19 scalar multiplications in pure Python would take minutes; use the C oracle's g1 ops through
+    # ref_msm with single-point MSMs batched by thread is also slow.  The reference arm therefore reads
+    # a bounded SRS: it benchmarks at the same n but with bases = tau^i G for i < 4096 tiled to n
+    # (MSM cost does not depend on the base values).
+    small = o.synthetic_srs(4096)
+    mont = 1 << 256
+    one = b"".join((p[0] * mont % o.P).to_bytes(32, "little") + (p[1] * mont % o.P).to_bytes(32, "little") for p in small)
+    return one * (n // 4096)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    olib = load_oracle_lib()
+    threads = olib.ref_hw_threads()
+    n = 1 << LOG_N
+    srs_xy = cpu_srs(olib, n, threads)
+    blob = make_blob(n, 1234).tobytes()
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        cpu_commit_and_prove(olib, blob, srs_xy, threads)
+    times = [cpu_commit_and_prove(olib, blob, srs_xy, threads) for _ in range(args.steps)]
+    total = sum(times)
+    value = args.steps / total
+    line = {
+        "impl": "reference", "metric": "blob commits+proofs/s (2^19 Fr, 16 MiB)", "value": value, "unit": "blobs/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 (4x64-bit Montgomery, BN254 Fq/Fr)",
+        "data": "synthetic",
+        "config": {"workload": "single 16 MiB blob (2^19 Fr): commit_blob + compute_blob_proof", "blobs_per_step": 1,
+                   "log_n": LOG_N, "algorithm": "Fr-IFFT + MSM (the cheaper form; the reference's literal G1-IFFT-per-commit path is ~180x slower, see BASELINE.md)"},
+        "cpu_baseline": {"value": value, "unit": "blobs/s", "cores": threads, "kind": "port",
+                         "sample": "1 blob (2^19 Fr) commit+proof per step; C++ restatement of the arkworks algorithm (oracle/cpu_ref.cpp), "
+                                   "MSM threaded over windows as arkworks does, evaluation/quotient with n separate inversions as the reference does"},
+        "e2e": {"value": value, "unit": "blobs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--blobs-per-step", type=int, default=16)
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from __graft_entry__ import load_package
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+
+    pkg = load_package()
+    lib = pkg.lib
+    eng = pkg.Engine(local_rank)
+    n = 1 << LOG_N
+    B = args.blobs_per_step
+
+    # synthetic SRS tau^i G generated on the GPU + fixed-base window tables (one-time setup)
+    t_setup = time.perf_counter()
+    srs = pkg.SRS.synthetic(n, TAU, engine=eng)
+    srs.precompute(n, 0)
+    setup_s = time.perf_counter() - t_setup
+    cbits, cwin, ctab = C.c_int(0), C.c_int(0), C.c_size_t(0)
+    lib.kzgb_msm_config(eng.h, C.byref(cbits), C.byref(cwin), C.byref(ctab))
+
+    # blobs: pinned host copies (SHA-256 transcript + e2e H2D source) and HBM-resident copies
+    host_blobs, dev_blobs = [], []
+    for i in range(B):
+        hb = torch.from_numpy(make_blob(n, 1000 * rank + i)).pin_memory()
+        host_blobs.append(hb)
+        dev_blobs.append(hb.to("cuda", non_blocking=False))
+    lens = (C.c_size_t * B)(*[n * 32] * B)
+    hptr = (C.c_void_p * B)(*[t.data_ptr() for t in host_blobs])
+    dptr = (C.c_void_p * B)(*[t.data_ptr() for t in dev_blobs])
+    cm = C.create_string_buffer(32 * B)
+    pf = C.create_string_buffer(32 * B)
+
+    def step_dev():
+        eng.check(lib.kzgb_commit_and_prove_blobs_dev(eng.h, dptr, hptr, lens, B, cm, pf))
+
+    def step_e2e():
+        eng.check(lib.kzgb_commit_and_prove_blobs(eng.h, hptr, lens, B, cm, pf))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        ms = C.c_double(0)
+        barrier()
+        w0 = time.perf_counter()
+        eng.check(lib.kzgb_timer_begin(eng.h))
+        for _ in range(steps):
+            fn()
+        eng.check(lib.kzgb_timer_end(eng.h, C.byref(ms)))
+        wall = (time.perf_counter() - w0) * 1e3
+        barrier()
+        t = torch.tensor([ms.value, wall], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1])
+
+    for _ in range(args.warmup):
+        step_dev()
+    lib.kzgb_stats(eng.h, None, None, None, 1)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = eng.launch_count()
+    dev_ms, dev_wall = timed(step_dev, args.steps)
+    launches = eng.launch_count() - l0
+    acc_ms, acc_n, acc_adds = C.c_double(0), C.c_uint64(0), C.c_uint64(0)
+    lib.kzgb_stats(eng.h, C.byref(acc_ms), C.byref(acc_n), C.byref(acc_adds), 1)
+    out_dev = (cm.raw, pf.raw)
+
+    for _ in range(min(args.warmup, 2)):
+        step_e2e()
+    e2e_ms, e2e_wall = timed(step_e2e, args.steps)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    assert (cm.raw, pf.raw) == out_dev, "device-resident and host-buffer paths disagree"
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    value = world * B * args.steps / (dev_ms * 1e-3)
+    e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
+
+    # integer-pipe roof measured live (dependency-free IMAD chains) and the kernel's achieved rate
+    imad = C.c_double(0)
+    eng.check(lib.kzgb_microbench(eng.h, 0, C.byref(imad)))
+    imadx = C.c_double(0)
+    eng.check(lib.kzgb_microbench(eng.h, 2, C.byref(imadx)))
+    fqpeak = C.c_double(0)
+    eng.check(lib.kzgb_microbench(eng.h, 3, C.byref(fqpeak)))
+    peak = imad.value / IMAD_PER_FQMUL / 1e9
+    adds_per_launch = acc_adds.value / max(1, acc_n.value)
+    avg_acc_ms = acc_ms.value / max(1, acc_n.value)
+    achieved = FQMUL_PER_MADD * adds_per_launch / (avg_acc_ms * 1e-3) / 1e9 if avg_acc_ms else 0.0
+    # isolated (single stream, nothing else on the GPU) timing of the same kernel
+    iso_total, iso_acc = C.c_double(0), C.c_double(0)
+    eng.check(lib.kzgb_bench_msm(eng.h, n, 5, C.byref(iso_total), C.byref(iso_acc)))
+    achieved_iso = FQMUL_PER_MADD * adds_per_launch / (iso_acc.value * 1e-3) / 1e9 if iso_acc.value else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("k_accumulate_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {
+        "kernel": "k_accumulate (MSM bucket accumulation, XYZZ += affine)", "bound": "integer-pipe (IMAD)",
+        "achieved": achieved_iso, "peak": peak, "unit": "GFqmul/s", "frac": achieved_iso / peak if peak else None,
+        "traffic": traffic,
+        "achieved_in_pipeline": achieved, "frac_in_pipeline": achieved / peak if peak else None,
+        "launch_ms_isolated": iso_acc.value, "launch_ms_in_pipeline": avg_acc_ms, "msm_total_ms_isolated": iso_total.value,
+        "algorithmic_fqmul_per_launch": FQMUL_PER_MADD * adds_per_launch, "point_adds_per_launch": adds_per_launch,
+        "peak_source": "measured live: dependency-free IMAD chains / 136 IMAD per 8x32-bit Montgomery multiplication",
+        "imad_per_s": imad.value, "carry_chain_imad_wide_per_s": imadx.value, "fqmul_microbench_per_s": fqpeak.value,
+        "hbm_gather_GBps_isolated": adds_per_launch * 64 / (iso_acc.value * 1e-3) / 1e9 if iso_acc.value else None,
+    }
+
+    cpu_baseline = None
+    if world == 1 and not args.skip_cpu_baseline:
+        olib = load_oracle_lib()
+        threads = olib.ref_hw_threads()
+        xy = C.create_string_buffer(64 * n)
+        eng.check(lib.kzgb_srs_get_affine_mont(eng.h, 0, n, xy, None))
+        blob0 = host_blobs[0].numpy().tobytes()
+        dt = cpu_commit_and_prove(olib, blob0, xy.raw, threads)
+        # parity of the timed configuration: CPU oracle vs GPU on the same blob and SRS
+        ocm = C.create_string_buffer(64)
+        olib.ref_commit_blob(blob0, C.c_size_t(len(blob0)), xy.raw, threads, 0, ocm)
+        oc32 = C.create_string_buffer(32)
+        lib.kzgb_g1_serialize_compressed(ocm, 0, oc32)
+        cpu_baseline = {"value": 1.0 / dt, "unit": "blobs/s", "cores": threads, "kind": "port",
+                        "sample": "1 blob (2^19 Fr) commit+proof; C++ restatement of the arkworks algorithm (Fr-IFFT + MSM form)",
+                        "commitment_matches_gpu": oc32.raw == out_dev[0][:32]}
+
+    line = {
+        "metric": "blob commits+proofs/s (2^19 Fr, 16 MiB)", "value": value, "unit": "blobs/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32 (8x32-bit Montgomery limbs, BN254 Fq/Fr)", "data": "synthetic",
+        "config": {"workload": "single 16 MiB blob (2^19 Fr): eval-form IFFT + 2^19-point G1 MSM commitment and blob proof",
+                   "blobs_per_step_per_gpu": B, "log_n": LOG_N, "srs": "tau^i*G, 2^19 points, generated on GPU",
+                   "blob_distribution": "D1 payload (byte 0 of each element = 0)", "sharding": "by blob, no collective",
+                   "msm_window_bits": cbits.value, "msm_windows": cwin.value,
+                   "l2": f"inputs larger than L2: {B * n * 32 >> 20} MiB of blobs + {cwin.value * n * 64 >> 20} MiB window table per step"},
+        "e2e": {"value": e2e_value, "unit": "blobs/s", "h2d_bytes_per_step": B * n * 32, "d2h_bytes_per_step": B * 2 * 128,
+                "ms_per_step": e2e_ms / args.steps, "wall_ms_per_step": e2e_wall / args.steps},
+        "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "wall_ms_per_step": dev_wall / args.steps, "setup_s": setup_s,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
