@@ -115,6 +115,16 @@ Fr ninv_mont(int logn) {
     fe_inv(r, n);
     return r;
 }
+// 1 / prod_i (z - w_i) with the zero factor (z = w_m) replaced by 1: prod = z^n - 1, or n / z in the domain
+Fr eval_tinv(const Fr& z, int logn) {
+    Fr zn = z, one, r;
+    for (int k = 0; k < logn; k++) fe_sqr(zn, zn);
+    fe_one(one);
+    if (fe_eq(zn, one)) { Fr ni = ninv_mont(logn); fe_mul(r, z, ni); return r; }
+    fe_sub(zn, zn, one);
+    fe_inv(r, zn);
+    return r;
+}
 // 32 big-endian bytes (any value) -> Fr Montgomery, reduced mod r
 Fr fr_from_be_bytes(const uint8_t* b) {
     Fr a;
@@ -359,7 +369,7 @@ int commit_evals_enqueue(kzgb_ctx* c, Lane& L, const Fr* d_evals, size_t n, MsmJ
     return msm_enqueue(c, L, (Fr*)L.work.p, false, 0, n, nullptr, job);
 }
 
-// quotient of d_evals at z (device, Montgomery) into L.work, then commit it.  y stays in L.small[1].
+// quotient of d_evals at z (device, Montgomery) into L.work, then commit it.  y stays in L.small[2].
 int proof_enqueue(kzgb_ctx* c, Lane& L, const Fr* d_evals, size_t n, const Fr& z_mont, MsmJob* job) {
     int logn = log2_exact(n);
     int rc = ensure_twiddles(c, logn);
@@ -368,12 +378,13 @@ int proof_enqueue(kzgb_ctx* c, Lane& L, const Fr* d_evals, size_t n, const Fr& z
     CK(c, L.ntt_scratch.reserve(n * sizeof(Fr)));
     CK(c, L.eval_scratch.reserve(eval_quotient_scratch_elems((uint32_t)n, 1) * sizeof(Fr)));
     CK(c, L.small.reserve(64 * sizeof(Fr)));
-    Fr* d_z = (Fr*)L.small.p;
-    Fr* d_y = d_z + 1;
+    Fr* d_z = (Fr*)L.small.p;  // [z, tinv, y]
+    Fr* d_y = d_z + 2;
     L.h_fr[0] = z_mont;
-    CK(c, cudaMemcpyAsync(d_z, &L.h_fr[0], sizeof(Fr), cudaMemcpyHostToDevice, L.st));
+    L.h_fr[1] = eval_tinv(z_mont, logn);
+    CK(c, cudaMemcpyAsync(d_z, &L.h_fr[0], 2 * sizeof(Fr), cudaMemcpyHostToDevice, L.st));
     Fr ninv = ninv_mont(logn);
-    eval_quotient_launch(d_evals, (uint32_t)n, logn, 1, d_z, c->tw, c->logN, &ninv, (Fr*)L.eval_scratch.p,
+    eval_quotient_launch(d_evals, (uint32_t)n, logn, 1, d_z, d_z + 1, c->tw, c->logN, &ninv, (Fr*)L.eval_scratch.p,
                          (Fr*)L.work.p, d_y, L.st);
     ntt_launch((Fr*)L.work.p, logn, 1, true, c->tw, c->logN, &ninv, (Fr*)L.ntt_scratch.p, L.st);
     return msm_enqueue(c, L, (Fr*)L.work.p, false, 0, n, nullptr, job);
@@ -467,6 +478,7 @@ int kzgb_ctx_create(kzgb_ctx** out, int device, void* stream) {
     cudaGetDevice(&prev);
     if (cudaSetDevice(device) != cudaSuccess) { delete c; return KZGB_ERR_DEVICE; }
     int rc = lane_init(c, c->lanes[0], (cudaStream_t)stream);
+    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 64);  // the MSM gathers 64-byte points at random
     if (rc == KZGB_OK) {
         c->n_lanes = 1;
         if (cudaEventCreate(&c->t0) != cudaSuccess || cudaEventCreate(&c->t1) != cudaSuccess) rc = KZGB_ERR_DEVICE;
@@ -788,11 +800,11 @@ int kzgb_compute_proof(kzgb_ctx* c, const uint64_t* evals, size_t n, const uint6
     MsmJob job;
     int rc = proof_enqueue(c, L, (Fr*)L.evals.p, n, z, &job);
     if (rc) return rc;
-    if (y_out) CK(c, cudaMemcpyAsync(&L.h_fr[1], (Fr*)L.small.p + 1, sizeof(Fr), cudaMemcpyDeviceToHost, L.st));
+    if (y_out) CK(c, cudaMemcpyAsync(&L.h_fr[3], (Fr*)L.small.p + 2, sizeof(Fr), cudaMemcpyDeviceToHost, L.st));
     Affine r;
     rc = msm_finish(c, L, job, &r);
     if (rc) return rc;
-    if (y_out) memcpy(y_out, &L.h_fr[1], 32);
+    if (y_out) memcpy(y_out, &L.h_fr[3], 32);
     affine_to_abi(r, out_xy, out_inf);
     return KZGB_OK;
 }
@@ -809,15 +821,16 @@ int kzgb_evaluate_polynomial(kzgb_ctx* c, const uint64_t* evals, size_t n, const
     CK(c, L.small.reserve(64 * sizeof(Fr)));
     CK(c, cudaMemcpyAsync(L.evals.p, evals, n * sizeof(Fr), cudaMemcpyHostToDevice, L.st));
     memcpy(L.h_fr[0].l, z_mont, 32);
+    L.h_fr[1] = eval_tinv(L.h_fr[0], logn);
     Fr* d_z = (Fr*)L.small.p;
-    CK(c, cudaMemcpyAsync(d_z, &L.h_fr[0], sizeof(Fr), cudaMemcpyHostToDevice, L.st));
+    CK(c, cudaMemcpyAsync(d_z, &L.h_fr[0], 2 * sizeof(Fr), cudaMemcpyHostToDevice, L.st));
     Fr ninv = ninv_mont(logn);
-    eval_quotient_launch((Fr*)L.evals.p, (uint32_t)n, logn, 1, d_z, c->tw, c->logN, &ninv, (Fr*)L.eval_scratch.p, nullptr,
-                         d_z + 1, L.st);
-    CK(c, cudaMemcpyAsync(&L.h_fr[1], d_z + 1, sizeof(Fr), cudaMemcpyDeviceToHost, L.st));
+    eval_quotient_launch((Fr*)L.evals.p, (uint32_t)n, logn, 1, d_z, d_z + 1, c->tw, c->logN, &ninv,
+                         (Fr*)L.eval_scratch.p, nullptr, d_z + 2, L.st);
+    CK(c, cudaMemcpyAsync(&L.h_fr[3], d_z + 2, sizeof(Fr), cudaMemcpyDeviceToHost, L.st));
     CK(c, cudaStreamSynchronize(L.st));
     CK(c, cudaGetLastError());
-    memcpy(y_out, &L.h_fr[1], 32);
+    memcpy(y_out, &L.h_fr[3], 32);
     return KZGB_OK;
 }
 
@@ -1022,17 +1035,21 @@ int kzgb_verify_batch_rlc(kzgb_ctx* c, const uint8_t* const* blobs, const size_t
         CK(c, L.evals.reserve(b * n * sizeof(Fr)));
         CK(c, L.bytes.reserve(b * n * 32));
         CK(c, L.eval_scratch.reserve(eval_quotient_scratch_elems((uint32_t)n, (uint32_t)b) * sizeof(Fr)));
-        CK(c, L.work.reserve(2 * b * sizeof(Fr)));
+        CK(c, L.work.reserve(3 * b * sizeof(Fr)));
         for (size_t k = 0; k < b; k++) {
             uint8_t* dst = (uint8_t*)L.bytes.p + k * n * 32;
             CK(c, cudaMemcpyAsync(dst, blobs[i0 + k], lens[i0 + k], cudaMemcpyHostToDevice, L.st));
             bytes_to_fr_launch(dst, lens[i0 + k], (Fr*)L.evals.p + k * n, (uint32_t)n, L.st);
         }
         Fr* d_z = (Fr*)L.work.p;
-        Fr* d_y = d_z + b;
+        Fr* d_t = d_z + b;
+        Fr* d_y = d_t + b;
+        std::vector<Fr> tinvs(b);
+        for (size_t k = 0; k < b; k++) tinvs[k] = eval_tinv(zs[i0 + k], logn);
         CK(c, cudaMemcpyAsync(d_z, &zs[i0], b * sizeof(Fr), cudaMemcpyHostToDevice, L.st));
+        CK(c, cudaMemcpyAsync(d_t, tinvs.data(), b * sizeof(Fr), cudaMemcpyHostToDevice, L.st));
         Fr ninv = ninv_mont(logn);
-        eval_quotient_launch((Fr*)L.evals.p, (uint32_t)n, logn, (uint32_t)b, d_z, c->tw, c->logN, &ninv,
+        eval_quotient_launch((Fr*)L.evals.p, (uint32_t)n, logn, (uint32_t)b, d_z, d_t, c->tw, c->logN, &ninv,
                              (Fr*)L.eval_scratch.p, nullptr, d_y, L.st);
         CK(c, cudaMemcpyAsync(&ys[i0], d_y, b * sizeof(Fr), cudaMemcpyDeviceToHost, L.st));
         CK(c, cudaStreamSynchronize(L.st));

@@ -39,6 +39,7 @@ struct MsmWorkspace {
     XYZZ* partial;      // 2 * acc_threads
     XYZZ* slice_sums;   // nbuckets / slice
     XYZZ* set_sums;     // sets (device), copied to host by the caller
+    uint32_t* tile_tot; // scan tile totals (<= 1024)
 };
 
 size_t msm_workspace_bytes(const MsmPlan& p);
@@ -82,8 +83,10 @@ void fr_to_bytes_launch(const Fr* in, uint8_t* out, uint32_t n, cudaStream_t st)
 // scratch: n Fr (inverses) + 2 * 1024 Fr partials.  y_out: 1 Fr (Montgomery, device).
 // Batched: `batch` polynomials of n evaluations back to back, z_mont_dev[batch] on the device;
 // q_out may be NULL (evaluation only).  y_out: batch Fr (Montgomery, device).
-void eval_quotient_launch(const Fr* evals, uint32_t n, int logn, uint32_t batch, const Fr* z_mont_dev, const Fr* tw,
-                          int logN, const Fr* ninv_mont_host, Fr* scratch, Fr* q_out, Fr* y_out, cudaStream_t st);
+// tinv_mont_dev[batch]: 1/(z^n - 1), or z/n when z^n == 1 (one host inversion per polynomial).
+void eval_quotient_launch(const Fr* evals, uint32_t n, int logn, uint32_t batch, const Fr* z_mont_dev,
+                          const Fr* tinv_mont_dev, const Fr* tw, int logN, const Fr* ninv_mont_host, Fr* scratch,
+                          Fr* q_out, Fr* y_out, cudaStream_t st);
 size_t eval_quotient_scratch_elems(uint32_t n, uint32_t batch);
 // out[i] = base^i (Montgomery), i < n
 void fr_powers_launch(Fr* out, uint32_t n, const Fr* base_mont_host, cudaStream_t st);

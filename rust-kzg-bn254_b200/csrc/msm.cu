@@ -55,31 +55,91 @@ __global__ void __launch_bounds__(256) k_digits_hist(const Fr* __restrict__ scal
     }
 }
 
-// in-place exclusive scan of hist[0..nb) ; hist[nb] = total ; cursor = copy of offsets
-__global__ void __launch_bounds__(1024) k_scan(uint32_t* __restrict__ hist, uint32_t* __restrict__ cursor, uint32_t nb) {
-    __shared__ uint32_t sums[1024];
-    uint32_t tid = threadIdx.x;
-    uint32_t per = (nb + 1023u) / 1024u;
-    uint32_t lo = tid * per, hi = min(lo + per, nb);
-    uint32_t s = 0;
-    for (uint32_t k = lo; k < hi; k++) s += hist[k];
-    sums[tid] = s;
+// Exclusive scan of the bucket histogram, 32 counters per thread held in registers (8 x 128-bit
+// loads in flight), warp-shuffle scan of the thread totals, one smem hop across warps.
+// block b scans items [b*SCAN_TILE, (b+1)*SCAN_TILE); block_tot[b] = its total.
+static constexpr uint32_t SCAN_PER_THREAD = 32;
+static constexpr uint32_t SCAN_THREADS = 1024;
+static constexpr uint32_t SCAN_TILE = SCAN_PER_THREAD * SCAN_THREADS;
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(uint32_t* __restrict__ hist, uint32_t* __restrict__ cursor,
+                                                             uint32_t nb, uint32_t* __restrict__ block_tot, bool single) {
+    __shared__ uint32_t warp_tot[32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t base = blockIdx.x * SCAN_TILE + tid * SCAN_PER_THREAD;
+    uint32_t v[SCAN_PER_THREAD];
+    if (base + SCAN_PER_THREAD <= nb) {
+        const uint4* q = reinterpret_cast<const uint4*>(hist + base);
+#pragma unroll
+        for (int k = 0; k < 8; k++) { uint4 t = q[k]; v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w; }
+    } else {
+#pragma unroll
+        for (int k = 0; k < (int)SCAN_PER_THREAD; k++) v[k] = (base + k < nb) ? hist[base + k] : 0u;
+    }
+    uint32_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < (int)SCAN_PER_THREAD; k++) { uint32_t t = v[k]; v[k] = sum; sum += t; }
+    uint32_t inc = sum;
+    for (int off = 1; off < 32; off <<= 1) {
+        uint32_t o = __shfl_up_sync(0xffffffffu, inc, off);
+        if ((int)lane >= off) inc += o;
+    }
+    if (lane == 31) warp_tot[wid] = inc;
     __syncthreads();
-    // Hillis-Steele inclusive scan over 1024 partials
-    for (uint32_t off = 1; off < 1024; off <<= 1) {
-        uint32_t v = (tid >= off) ? sums[tid - off] : 0u;
+    if (wid == 0) {
+        uint32_t w = warp_tot[lane], wi = w;
+        for (int off = 1; off < 32; off <<= 1) {
+            uint32_t o = __shfl_up_sync(0xffffffffu, wi, off);
+            if ((int)lane >= off) wi += o;
+        }
+        warp_tot[lane] = wi - w;  // exclusive
+        if (lane == 31) {
+            block_tot[blockIdx.x] = wi;
+            if (single) hist[nb] = wi;
+        }
+    }
+    __syncthreads();
+    const uint32_t off0 = warp_tot[wid] + (inc - sum);
+    if (base + SCAN_PER_THREAD <= nb) {
+        uint4* q = reinterpret_cast<uint4*>(hist + base);
+        uint4* qc = reinterpret_cast<uint4*>(cursor + base);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            uint4 t = make_uint4(v[4 * k] + off0, v[4 * k + 1] + off0, v[4 * k + 2] + off0, v[4 * k + 3] + off0);
+            q[k] = t;
+            if (single) qc[k] = t;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < (int)SCAN_PER_THREAD; k++)
+            if (base + k < nb) { hist[base + k] = v[k] + off0; if (single) cursor[base + k] = v[k] + off0; }
+    }
+}
+
+// multi-tile case: exclusive scan of the tile totals (<= 1024 tiles), then add them back
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tile_totals(uint32_t* __restrict__ block_tot, uint32_t ntiles,
+                                                                   uint32_t* __restrict__ hist, uint32_t nb) {
+    __shared__ uint32_t sm[SCAN_THREADS];
+    const uint32_t tid = threadIdx.x;
+    uint32_t v = tid < ntiles ? block_tot[tid] : 0u;
+    sm[tid] = v;
+    __syncthreads();
+    for (uint32_t off = 1; off < SCAN_THREADS; off <<= 1) {
+        uint32_t o = tid >= off ? sm[tid - off] : 0u;
         __syncthreads();
-        sums[tid] += v;
+        sm[tid] += o;
         __syncthreads();
     }
-    uint32_t run = sums[tid] - s;
-    for (uint32_t k = lo; k < hi; k++) {
-        uint32_t cnt = hist[k];
-        hist[k] = run;
-        cursor[k] = run;
-        run += cnt;
-    }
-    if (tid == 1023) hist[nb] = sums[1023];
+    if (tid < ntiles) block_tot[tid] = sm[tid] - v;
+    if (tid == SCAN_THREADS - 1) hist[nb] = sm[tid];
+}
+__global__ void __launch_bounds__(256) k_scan_add(uint32_t* __restrict__ hist, uint32_t* __restrict__ cursor, uint32_t nb,
+                                                   const uint32_t* __restrict__ block_tot) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nb) return;
+    uint32_t v = hist[i] + block_tot[i / SCAN_TILE];
+    hist[i] = v;
+    cursor[i] = v;
 }
 
 __global__ void __launch_bounds__(256) k_scatter(const Fr* __restrict__ canon, MsmPlan p, uint32_t* __restrict__ cursor,
@@ -259,6 +319,7 @@ size_t msm_workspace_bytes(const MsmPlan& p) {
     b += align_up((size_t)(p.nbuckets / p.slice) * sizeof(XYZZ));
     b += align_up((size_t)(p.nbuckets / p.slice) * sizeof(XYZZ));  // tree ping-pong
     b += align_up((size_t)p.sets * sizeof(XYZZ));
+    b += align_up(1024 * 4);  // scan tile totals
     return b;
 }
 
@@ -273,7 +334,8 @@ void msm_workspace_carve(const MsmPlan& p, void* base, MsmWorkspace* ws) {
     ws->buckets = (XYZZ*)c; c += align_up((size_t)p.nbuckets * sizeof(XYZZ));
     ws->partial = (XYZZ*)c; c += align_up((size_t)2 * p.acc_threads * sizeof(XYZZ));
     ws->slice_sums = (XYZZ*)c; c += 2 * align_up((size_t)(p.nbuckets / p.slice) * sizeof(XYZZ));
-    ws->set_sums = (XYZZ*)c;
+    ws->set_sums = (XYZZ*)c; c += align_up((size_t)p.sets * sizeof(XYZZ));
+    ws->tile_tot = (uint32_t*)c;
 }
 
 void msm_launch(const MsmPlan& p, const MsmWorkspace& ws, const Fr* scalars, bool scalars_canonical,
@@ -282,7 +344,15 @@ void msm_launch(const MsmPlan& p, const MsmWorkspace& ws, const Fr* scalars, boo
     uint32_t gb = (p.n + 255) / 256;
     if (p.n) { k_digits_hist<<<gb, 256, 0, st>>>(scalars, scalars_canonical, p, ws.canon, ws.hist); g_launch_count += 2; }
     g_launch_count += 4;  // scan, accumulate, bucket_fix, reduce_slices
-    k_scan<<<1, 1024, 0, st>>>(ws.hist, ws.cursor, p.nbuckets);
+    {
+        uint32_t ntiles = (p.nbuckets + SCAN_TILE - 1) / SCAN_TILE;
+        k_scan_tiles<<<ntiles, SCAN_THREADS, 0, st>>>(ws.hist, ws.cursor, p.nbuckets, ws.tile_tot, ntiles == 1);
+        if (ntiles > 1) {
+            k_scan_tile_totals<<<1, SCAN_THREADS, 0, st>>>(ws.tile_tot, ntiles, ws.hist, p.nbuckets);
+            k_scan_add<<<(p.nbuckets + 255) / 256, 256, 0, st>>>(ws.hist, ws.cursor, p.nbuckets, ws.tile_tot);
+            g_launch_count += 2;
+        }
+    }
     if (p.n) k_scatter<<<gb, 256, 0, st>>>(ws.canon, p, ws.cursor, ws.sorted);
     if (ev_acc_begin) cudaEventRecord(ev_acc_begin, st);
     k_accumulate<<<(p.acc_threads + 127) / 128, 128, 0, st>>>(ws.sorted, ws.hist, table, p, ws.buckets, ws.partial);

@@ -106,21 +106,16 @@ __device__ __forceinline__ void block_sum_fr(Fr v, Fr* out) {
     __syncthreads();
 }
 
+// ---- batched inversion of the n denominators d_i = z - w_i WITHOUT any field inversion on the GPU:
+// prod_i d_i = z^n - 1, so T^-1 = 1/(z^n - 1) is one host inversion per polynomial (z = w_m:
+// the zero factor is replaced by 1 and the product becomes n / z).  Then
+//     1/d_i = T^-1 * prod_{j != i} d_j ,
+// assembled from per-thread, per-warp, per-block and grid-level prefix/suffix products.
 // Batched over blockIdx.y (one polynomial of n evaluations per batch entry, its own z).
-// inv[i] = 1/(z - w_i) (1 where z == w_i, recorded in zidx = i + 1); partial[block] = sum f_i w_i inv[i]
-__global__ void __launch_bounds__(EVAL_THREADS) k_eval_inverses(const Fr* __restrict__ evals_all, uint32_t n, int logn,
-                                                                const Fr* __restrict__ z_all, const Fr* __restrict__ tw,
-                                                                int logN, Fr* __restrict__ inv_all, Fr* __restrict__ partial_all,
-                                                                uint32_t nparts, uint32_t* __restrict__ zidx_all) {
-    const uint32_t bi = blockIdx.y;
-    const Fr* evals = evals_all + (size_t)bi * n;
-    Fr* inv = inv_all + (size_t)bi * n;
-    Fr* partial = partial_all + (size_t)bi * nparts;
-    uint32_t* zidx = zidx_all + bi;
-    const Fr z = fe_load(&z_all[bi]);
-    const uint32_t base = blockIdx.x * EVAL_TILE + threadIdx.x;
-    const uint32_t lane = threadIdx.x & 31;
-    Fr d[EVAL_E], pp[EVAL_E];
+
+// d[k], running prefix pp[k] for this thread's EVAL_E denominators; returns which k (if any) was zero
+__device__ __forceinline__ uint32_t eval_thread_denoms(const Fr& z, const Fr* __restrict__ tw, uint32_t base, uint32_t n,
+                                                       int logn, int logN, Fr* d, Fr* pp, uint32_t* zidx) {
     Fr one; fe_one(one);
     uint32_t zero_k = 0xffffffffu;
 #pragma unroll
@@ -129,29 +124,134 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_eval_inverses(const Fr* __rest
         if (i < n) {
             Fr w = domain_root(tw, i, logn, logN);
             fe_sub(d[k], z, w);
-            if (fe_is_zero(d[k])) { d[k] = one; zero_k = k; zidx[0] = i + 1; }
+            if (fe_is_zero(d[k])) { d[k] = one; zero_k = k; if (zidx) zidx[0] = i + 1; }
         } else {
             d[k] = one;
         }
         if (k == 0) pp[0] = d[0]; else fe_mul(pp[k], pp[k - 1], d[k]);
     }
-    // warp product scans of the per-thread products
-    Fr inc = pp[EVAL_E - 1];
+    return zero_k;
+}
+
+// inclusive prefix (inc) and suffix (suf) products of v across the warp
+__device__ __forceinline__ void warp_scan_products(const Fr& v, uint32_t lane, Fr& inc, Fr& suf) {
+    inc = v;
     for (int off = 1; off < 32; off <<= 1) {
         Fr o;
 #pragma unroll
         for (int k = 0; k < 8; k++) o.l[k] = __shfl_up_sync(0xffffffffu, inc.l[k], off);
         if ((int)lane >= off) fe_mul(inc, inc, o);
     }
-    Fr suf = pp[EVAL_E - 1];
+    suf = v;
     for (int off = 1; off < 32; off <<= 1) {
         Fr o;
 #pragma unroll
         for (int k = 0; k < 8; k++) o.l[k] = __shfl_down_sync(0xffffffffu, suf.l[k], off);
         if ((int)lane + off < 32) fe_mul(suf, suf, o);
     }
-    Fr total = shfl_fe(inc, 31);
-    Fr tinv; fe_inv(tinv, total);  // one Fermat inversion per warp (uniform across lanes)
+}
+
+// E1: product of each block's 2048 denominators
+__global__ void __launch_bounds__(EVAL_THREADS) k_eval_block_products(uint32_t n, int logn, const Fr* __restrict__ z_all,
+                                                                      const Fr* __restrict__ tw, int logN,
+                                                                      Fr* __restrict__ bprod_all, uint32_t nparts,
+                                                                      uint32_t* __restrict__ zidx_all) {
+    __shared__ uint32_t wt[8][EVAL_THREADS / 32];
+    const uint32_t bi = blockIdx.y;
+    const Fr z = fe_load(&z_all[bi]);
+    const uint32_t base = blockIdx.x * EVAL_TILE + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    Fr d[EVAL_E], pp[EVAL_E];
+    eval_thread_denoms(z, tw, base, n, logn, logN, d, pp, zidx_all + bi);
+    Fr v = pp[EVAL_E - 1];
+    for (int off = 16; off >= 1; off >>= 1) {
+        Fr o;
+#pragma unroll
+        for (int k = 0; k < 8; k++) o.l[k] = __shfl_down_sync(0xffffffffu, v.l[k], off);
+        fe_mul(v, v, o);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) wt[k][wid] = v.l[k];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        Fr acc = v;
+        for (int w = 1; w < EVAL_THREADS / 32; w++) {
+            Fr o;
+#pragma unroll
+            for (int k = 0; k < 8; k++) o.l[k] = wt[k][w];
+            fe_mul(acc, acc, o);
+        }
+        fe_store(&bprod_all[(size_t)bi * nparts + blockIdx.x], acc);
+    }
+}
+
+// E2 (one block per polynomial): fac[j] = T^-1 * prod_{k != j} bprod[k]
+__global__ void __launch_bounds__(EVAL_THREADS) k_eval_block_factors(const Fr* __restrict__ bprod_all, uint32_t nparts,
+                                                                     const Fr* __restrict__ tinv_all, Fr* __restrict__ fac_all) {
+    __shared__ Fr pre[EVAL_THREADS], post[EVAL_THREADS];
+    const uint32_t bi = blockIdx.x, tid = threadIdx.x;
+    const Fr* bprod = bprod_all + (size_t)bi * nparts;
+    Fr* fac = fac_all + (size_t)bi * nparts;
+    const uint32_t per = (nparts + EVAL_THREADS - 1) / EVAL_THREADS;
+    const uint32_t lo = min(tid * per, nparts), hi = min(lo + per, nparts);
+    Fr one; fe_one(one);
+    Fr prod = one;
+    for (uint32_t j = lo; j < hi; j++) { Fr v = fe_load(&bprod[j]); fe_mul(prod, prod, v); }
+    pre[tid] = prod;
+    post[tid] = prod;
+    __syncthreads();
+    // Hillis-Steele inclusive scans (prefix in pre, suffix in post)
+    for (uint32_t off = 1; off < EVAL_THREADS; off <<= 1) {
+        Fr a = pre[tid], b = post[tid];
+        bool ha = tid >= off, hb = tid + off < EVAL_THREADS;
+        Fr oa = ha ? pre[tid - off] : one, ob = hb ? post[tid + off] : one;
+        __syncthreads();
+        if (ha) { fe_mul(a, a, oa); pre[tid] = a; }
+        if (hb) { fe_mul(b, b, ob); post[tid] = b; }
+        __syncthreads();
+    }
+    Fr before = tid > 0 ? pre[tid - 1] : one;                    // product of all parts owned by lower threads
+    Fr after = tid + 1 < EVAL_THREADS ? post[tid + 1] : one;     // ... by higher threads
+    Fr tinv = fe_load(&tinv_all[bi]);
+    fe_mul(after, after, tinv);
+    // forward: fac[j] = before * prod_{lo <= k < j}; backward: times prod_{j < k < hi} * after
+    Fr run = before;
+    for (uint32_t j = lo; j < hi; j++) { fe_store(&fac[j], run); Fr v = fe_load(&bprod[j]); fe_mul(run, run, v); }
+    run = after;
+    for (uint32_t j = hi; j-- > lo;) {
+        Fr f = fe_load(&fac[j]);
+        fe_mul(f, f, run);
+        fe_store(&fac[j], f);
+        Fr v = fe_load(&bprod[j]);
+        fe_mul(run, run, v);
+    }
+}
+
+// E3: inv[i] = 1/(z - w_i) (1 where z == w_i); partial[block] = sum f_i w_i inv[i]
+__global__ void __launch_bounds__(EVAL_THREADS) k_eval_inverses(const Fr* __restrict__ evals_all, uint32_t n, int logn,
+                                                                const Fr* __restrict__ z_all, const Fr* __restrict__ tw,
+                                                                int logN, const Fr* __restrict__ fac_all,
+                                                                Fr* __restrict__ inv_all, Fr* __restrict__ partial_all,
+                                                                uint32_t nparts) {
+    __shared__ uint32_t wt[8][EVAL_THREADS / 32];
+    const uint32_t bi = blockIdx.y;
+    const Fr* evals = evals_all + (size_t)bi * n;
+    Fr* inv = inv_all + (size_t)bi * n;
+    Fr* partial = partial_all + (size_t)bi * nparts;
+    const Fr z = fe_load(&z_all[bi]);
+    const uint32_t base = blockIdx.x * EVAL_TILE + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    Fr d[EVAL_E], pp[EVAL_E];
+    Fr one; fe_one(one);
+    const uint32_t zero_k = eval_thread_denoms(z, tw, base, n, logn, logN, d, pp, nullptr);
+    Fr inc, suf;
+    warp_scan_products(pp[EVAL_E - 1], lane, inc, suf);
+    if (lane == 31) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) wt[k][wid] = inc.l[k];
+    }
     Fr exc, sufx;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
@@ -160,8 +260,17 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_eval_inverses(const Fr* __rest
     }
     if (lane == 0) exc = one;
     if (lane == 31) sufx = one;
-    Fr run;
-    fe_mul(run, tinv, exc);
+    __syncthreads();
+    // product of the other warps of the block, times the grid-level factor of this block
+    Fr run = fe_load(&fac_all[(size_t)bi * nparts + blockIdx.x]);
+    for (uint32_t w = 0; w < EVAL_THREADS / 32; w++) {
+        if (w == wid) continue;
+        Fr o;
+#pragma unroll
+        for (int k = 0; k < 8; k++) o.l[k] = wt[k][w];
+        fe_mul(run, run, o);
+    }
+    fe_mul(run, run, exc);
     fe_mul(run, run, sufx);  // 1 / (product of this thread's denominators)
     Fr sum; fe_zero(sum);
 #pragma unroll
@@ -317,24 +426,29 @@ void fr_to_bytes_launch(const Fr* in, uint8_t* out, uint32_t n, cudaStream_t st)
 size_t eval_quotient_scratch_elems(uint32_t n, uint32_t batch) {
     uint32_t parts1 = (n + EVAL_TILE - 1) / EVAL_TILE;
     uint32_t parts2 = (n + EVAL_THREADS - 1) / EVAL_THREADS;
-    // inverses, partial sums (both kernels), zidx words (rounded up to whole Fr slots)
-    return (size_t)batch * ((size_t)n + parts1 + parts2) + ((size_t)batch * 4 + 31) / 32 + 1;
+    // inverses, block products, block factors, partial sums (both kernels), zidx words (whole Fr slots)
+    return (size_t)batch * ((size_t)n + 3 * (size_t)parts1 + parts2) + ((size_t)batch * 4 + 31) / 32 + 1;
 }
 
-void eval_quotient_launch(const Fr* evals, uint32_t n, int logn, uint32_t batch, const Fr* z_mont_dev, const Fr* tw,
-                          int logN, const Fr* ninv_mont_host, Fr* scratch, Fr* q_out, Fr* y_out, cudaStream_t st) {
+void eval_quotient_launch(const Fr* evals, uint32_t n, int logn, uint32_t batch, const Fr* z_mont_dev,
+                          const Fr* tinv_mont_dev, const Fr* tw, int logN, const Fr* ninv_mont_host, Fr* scratch,
+                          Fr* q_out, Fr* y_out, cudaStream_t st) {
     if (!batch) return;
     uint32_t parts1 = (n + EVAL_TILE - 1) / EVAL_TILE;
     uint32_t parts2 = (n + EVAL_THREADS - 1) / EVAL_THREADS;
     Fr* inv = scratch;
-    Fr* partial1 = inv + (size_t)batch * n;
+    Fr* bprod = inv + (size_t)batch * n;
+    Fr* fac = bprod + (size_t)batch * parts1;
+    Fr* partial1 = fac + (size_t)batch * parts1;
     Fr* partial2 = partial1 + (size_t)batch * parts1;
     uint32_t* zidx = reinterpret_cast<uint32_t*>(partial2 + (size_t)batch * parts2);
     cudaMemsetAsync(zidx, 0, (size_t)batch * 4, st);
-    k_eval_inverses<<<dim3(parts1, batch), EVAL_THREADS, 0, st>>>(evals, n, logn, z_mont_dev, tw, logN, inv, partial1,
-                                                                  parts1, zidx);
+    k_eval_block_products<<<dim3(parts1, batch), EVAL_THREADS, 0, st>>>(n, logn, z_mont_dev, tw, logN, bprod, parts1, zidx);
+    k_eval_block_factors<<<batch, EVAL_THREADS, 0, st>>>(bprod, parts1, tinv_mont_dev, fac);
+    k_eval_inverses<<<dim3(parts1, batch), EVAL_THREADS, 0, st>>>(evals, n, logn, z_mont_dev, tw, logN, fac, inv, partial1,
+                                                                  parts1);
     k_eval_finish<<<batch, EVAL_THREADS, 0, st>>>(evals, n, logn, z_mont_dev, *ninv_mont_host, partial1, parts1, zidx, y_out);
-    g_launch_count += 2;
+    g_launch_count += 4;
     if (q_out) {
         k_quotient<<<dim3(parts2, batch), EVAL_THREADS, 0, st>>>(evals, n, logn, tw, logN, inv, y_out, zidx, q_out,
                                                                  partial2, parts2);
