@@ -1,7 +1,7 @@
 // Integer-pipe roofline microbenchmarks ("the per-SM IMAD/IMAD.WIDE rate on
 // sm_100 must be measured ... and that measured figure used as the denominator").
 //   mode 0: independent 32-bit IMAD chains                (mad.lo.u32)
-//   mode 1: independent IMAD.WIDE.U32 chains               (mad.wide.u32, 64-bit accumulate)
+//   mode 1: IMAD.WIDE.U32 with a 64-bit accumulate, no carry flags (mad.wide.u32, data-dependent operands)
 //   mode 2: carry-chained IMAD.WIDE.U32.X                  (mad.lo.cc / madc.hi.cc pairs, as in fq_mul)
 // and the achieved rate of the real 136-IMAD Montgomery multiplication with 2 independent
 // chains per thread.
@@ -28,20 +28,22 @@ __global__ void __launch_bounds__(256) k_imad_peak(uint32_t* __restrict__ sink, 
         }
         sink[t] = x0 ^ x1 ^ x2 ^ x3 ^ x4 ^ x5 ^ x6 ^ x7;
     } else if (MODE == 1) {
-        uint64_t x0 = a, x1 = b, x2 = a + 1, x3 = b + 1, x4 = a + 2, x5 = b + 2, x6 = a + 3, x7 = b + 3;
+        // pure IMAD.WIDE.U32 issue rate: 32x32->64 products of data-dependent operands, folded into a
+        // 32-bit accumulator with one LOP3 (other pipe).  (A mad.wide accumulate chain with loop-invariant
+        // operands gets strength-reduced by ptxas to 64-bit adds and then reports the IADD rate.)
+        uint32_t x0 = a, x1 = b, x2 = a + 1, x3 = b + 1, x4 = a + 2, x5 = b + 2, x6 = a + 3, x7 = b + 3;
+#define KZ_MW(dst, src, m)                                                                                  \
+    asm volatile("{ .reg .u64 t; .reg .u32 lo, hi; mul.wide.u32 t, %1, %2; mov.b64 {lo, hi}, t; "            \
+                 "lop3.b32 %0, %0, lo, hi, 0x96; }" : "+r"(dst) : "r"(src), "r"(m))
         for (int i = 0; i < iters; i++) {
 #pragma unroll
             for (int k = 0; k < 16; k++) {
-                asm volatile("mad.wide.u32 %0, %8, %9, %0;\n\tmad.wide.u32 %1, %8, %9, %1;\n\t"
-                             "mad.wide.u32 %2, %8, %9, %2;\n\tmad.wide.u32 %3, %8, %9, %3;\n\t"
-                             "mad.wide.u32 %4, %8, %9, %4;\n\tmad.wide.u32 %5, %8, %9, %5;\n\t"
-                             "mad.wide.u32 %6, %8, %9, %6;\n\tmad.wide.u32 %7, %8, %9, %7;"
-                             : "+l"(x0), "+l"(x1), "+l"(x2), "+l"(x3), "+l"(x4), "+l"(x5), "+l"(x6), "+l"(x7)
-                             : "r"(a), "r"(b));
+                KZ_MW(x0, x1, b); KZ_MW(x2, x3, b); KZ_MW(x4, x5, b); KZ_MW(x6, x7, b);
+                KZ_MW(x1, x2, a); KZ_MW(x3, x4, a); KZ_MW(x5, x6, a); KZ_MW(x7, x0, a);
             }
         }
-        uint64_t x = x0 ^ x1 ^ x2 ^ x3 ^ x4 ^ x5 ^ x6 ^ x7;
-        sink[t] = (uint32_t)x ^ (uint32_t)(x >> 32);
+#undef KZ_MW
+        sink[t] = x0 ^ x1 ^ x2 ^ x3 ^ x4 ^ x5 ^ x6 ^ x7;
     } else {
         uint32_t x0 = a, x1 = b, x2 = a + 1, x3 = b + 1, x4 = a + 2, x5 = b + 2, x6 = a + 3, x7 = b + 3;
         uint32_t y0 = b, y1 = a, y2 = b + 5, y3 = a + 5, y4 = b + 6, y5 = a + 6, y6 = b + 7, y7 = a + 7;

@@ -13,6 +13,7 @@
 //   6. k_reduce_slices per-slice running sums  sum (k+1) * B_k  + small scalar fix-up
 //   7. k_tree_reduce   tree sum of the slice results -> one XYZZ point per bucket set
 // The caller copies `sets` XYZZ points (128 B each) back and finishes on the host.
+#include <cstdlib>
 #include "kzgb_internal.hpp"
 
 namespace kzgb {
@@ -167,9 +168,45 @@ __device__ __forceinline__ Affine load_point(const Affine* __restrict__ table, u
     return q;
 }
 
-__global__ void __launch_bounds__(128) k_accumulate(const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ offsets,
-                                                     const Affine* __restrict__ table, MsmPlan p,
-                                                     XYZZ* __restrict__ buckets, XYZZ* __restrict__ partial) {
+// Out-of-line multiplication for the accumulation loop (arguments and result in registers): the loop
+// body with 10 inlined multiplications is ~35 KB of SASS, more than the 32 KB L1.5 instruction cache.
+static __device__ __noinline__ Fq fq_mul_call(Fq a, Fq b) {
+    Fq r;
+    fe_mul(r, a, b);
+    return r;
+}
+// xyzz_madd (ec.cuh) with called multiplications; exceptional cases delegate to the complete version
+__device__ __forceinline__ void xyzz_madd_call(XYZZ& acc, const Affine& q) {
+    if (aff_is_inf(q)) return;
+    if (xyzz_is_inf(acc)) { acc.x = q.x; acc.y = q.y; fe_one(acc.zz); fe_one(acc.zzz); return; }
+    Fq U2 = fq_mul_call(q.x, acc.zz);
+    Fq S2 = fq_mul_call(q.y, acc.zzz);
+    Fq Pp, Rr;
+    fe_sub(Pp, U2, acc.x);
+    fe_sub(Rr, S2, acc.y);
+    if (fe_is_zero(Pp)) {
+        if (fe_is_zero(Rr)) xyzz_dbl_affine(acc, q);
+        else xyzz_set_inf(acc);
+        return;
+    }
+    Fq PP = fq_mul_call(Pp, Pp);
+    Fq PPP = fq_mul_call(Pp, PP);
+    Fq Q = fq_mul_call(acc.x, PP);
+    Fq t = fq_mul_call(Rr, Rr);
+    fe_sub(t, t, PPP); fe_sub(t, t, Q); fe_sub(t, t, Q);  // X3
+    fe_sub(Q, Q, t);
+    Q = fq_mul_call(Rr, Q);
+    S2 = fq_mul_call(acc.y, PPP);
+    fe_sub(acc.y, Q, S2);
+    acc.x = t;
+    acc.zz = fq_mul_call(acc.zz, PP);
+    acc.zzz = fq_mul_call(acc.zzz, PPP);
+}
+
+template <int MINB, bool CALL, bool PREFETCH>
+__global__ void __launch_bounds__(128, MINB) k_accumulate_t(const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ offsets,
+                                                              const Affine* __restrict__ table, MsmPlan p,
+                                                              XYZZ* __restrict__ buckets, XYZZ* __restrict__ partial) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= p.acc_threads) return;
     const uint32_t nb = p.nbuckets;
@@ -187,11 +224,12 @@ __global__ void __launch_bounds__(128) k_accumulate(const uint32_t* __restrict__
     uint32_t b = lo;
     uint32_t run_begin = offsets[b], next = offsets[b + 1];
     XYZZ acc; xyzz_set_inf(acc);
-    Affine q = load_point(table, sorted[start]);
+    Affine q;
+    if (PREFETCH) q = load_point(table, sorted[start]);
     for (uint32_t pos = start; pos < end; pos++) {
-        // prefetch the next point while this addition runs
         Affine qn;
-        if (pos + 1 < end) qn = load_point(table, sorted[pos + 1]);
+        if (PREFETCH) { if (pos + 1 < end) qn = load_point(table, sorted[pos + 1]); }  // next point in flight during this addition
+        else q = load_point(table, sorted[pos]);
         if (pos >= next) {
             bool complete = (run_begin >= start);  // its end (`next`) is <= pos < end
             if (complete) xyzz_store(&buckets[b], acc);
@@ -200,8 +238,8 @@ __global__ void __launch_bounds__(128) k_accumulate(const uint32_t* __restrict__
             do { b++; } while (offsets[b + 1] <= pos);
             run_begin = offsets[b]; next = offsets[b + 1];
         }
-        xyzz_madd(acc, q);
-        if (pos + 1 < end) q = qn;
+        if (CALL) xyzz_madd_call(acc, q); else xyzz_madd(acc, q);
+        if (PREFETCH) { if (pos + 1 < end) q = qn; }
     }
     {
         bool complete = (run_begin >= start) && (next <= end);
@@ -355,7 +393,25 @@ void msm_launch(const MsmPlan& p, const MsmWorkspace& ws, const Fr* scalars, boo
     }
     if (p.n) k_scatter<<<gb, 256, 0, st>>>(ws.canon, p, ws.cursor, ws.sorted);
     if (ev_acc_begin) cudaEventRecord(ev_acc_begin, st);
-    k_accumulate<<<(p.acc_threads + 127) / 128, 128, 0, st>>>(ws.sorted, ws.hist, table, p, ws.buckets, ws.partial);
+    {
+        static int variant = -1;
+        if (variant < 0) { const char* e = getenv("KZGB_ACC_VARIANT"); variant = e ? atoi(e) : 0; }
+        dim3 g((p.acc_threads + 127) / 128);
+#define KZ_ACC(MB, CALL, PF) k_accumulate_t<MB, CALL, PF><<<g, 128, 0, st>>>(ws.sorted, ws.hist, table, p, ws.buckets, ws.partial)
+        switch (variant) {
+            case 1: KZ_ACC(3, false, true); break;
+            case 8: KZ_ACC(4, false, false); break;
+            case 9: KZ_ACC(5, false, true); break;
+            case 2: KZ_ACC(3, true, true); break;
+            case 3: KZ_ACC(4, true, true); break;
+            case 4: KZ_ACC(5, true, true); break;
+            case 5: KZ_ACC(5, true, false); break;
+            case 6: KZ_ACC(6, true, false); break;
+            case 7: KZ_ACC(4, true, false); break;
+            default: KZ_ACC(4, false, false); break;  // best of the sweep in profiles/r01_accumulate_variants.txt
+        }
+#undef KZ_ACC
+    }
     if (ev_acc_end) cudaEventRecord(ev_acc_end, st);
     k_bucket_fix<<<(p.nbuckets + 127) / 128, 128, 0, st>>>(ws.hist, p, ws.buckets, ws.partial);
     uint32_t nslices = p.nbuckets / p.slice;
