@@ -148,9 +148,18 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--blobs-per-step", type=int, default=16)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4", "c5"],
+                    help="c2 (default, headline): 16 MiB blobs; c3: 1024 x 2^16-Fr blobs sharded by blob; "
+                         "c4: 2^26-point MSM sharded by point range; c5: batch-verify RLC over 4096 pairs")
+    ap.add_argument("--log-n", type=int, default=0, help="override the problem size of c3/c4/c5")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+        return
+    if args.config != "c2":
+        import bench_configs
+
+        getattr(bench_configs, "run_" + args.config)(args)
         return
 
     import numpy as np
@@ -253,6 +262,8 @@ def main():
     eng.check(lib.kzgb_microbench(eng.h, 0, C.byref(imad)))
     imadx = C.c_double(0)
     eng.check(lib.kzgb_microbench(eng.h, 2, C.byref(imadx)))
+    imadw = C.c_double(0)
+    eng.check(lib.kzgb_microbench(eng.h, 1, C.byref(imadw)))
     fqpeak = C.c_double(0)
     eng.check(lib.kzgb_microbench(eng.h, 3, C.byref(fqpeak)))
     peak = imad.value / IMAD_PER_FQMUL / 1e9
@@ -277,8 +288,10 @@ def main():
         "achieved_in_pipeline": achieved, "frac_in_pipeline": achieved / peak if peak else None,
         "launch_ms_isolated": iso_acc.value, "launch_ms_in_pipeline": avg_acc_ms, "msm_total_ms_isolated": iso_total.value,
         "algorithmic_fqmul_per_launch": FQMUL_PER_MADD * adds_per_launch, "point_adds_per_launch": adds_per_launch,
-        "peak_source": "measured live: dependency-free IMAD chains / 136 IMAD per 8x32-bit Montgomery multiplication",
-        "imad_per_s": imad.value, "carry_chain_imad_wide_per_s": imadx.value, "fqmul_microbench_per_s": fqpeak.value,
+        "peak_source": "measured live: dependency-free IMAD chains / 136 IMAD per 8x32-bit Montgomery multiplication (SURVEY.md 8d model)",
+        "peak_wide_multiply": imadw.value / 132.0 / 1e9, "frac_of_wide_multiply_peak": achieved_iso / (imadw.value / 132.0 / 1e9) if imadw.value else None,
+        "peak_wide_multiply_source": "measured live: IMAD.WIDE.U32 issues at half the IMAD rate on sm_100; a multiplication is 128 wide + 8 narrow multiplies",
+        "imad_per_s": imad.value, "imad_wide_per_s": imadw.value, "carry_chain_imad_wide_per_s": imadx.value, "fqmul_microbench_per_s": fqpeak.value,
         "hbm_gather_GBps_isolated": adds_per_launch * 64 / (iso_acc.value * 1e-3) / 1e9 if iso_acc.value else None,
     }
 

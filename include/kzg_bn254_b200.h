@@ -65,6 +65,9 @@ int kzgb_srs_load_gnark_be(kzgb_ctx* ctx, const uint8_t* bytes, size_t n_points)
 int kzgb_srs_load_affine_mont(kzgb_ctx* ctx, const uint64_t* xy, const uint8_t* inf, size_t n_points);
 /* Synthetic SRS_i = tau^i * G generated on the GPU (benches/tests; tau: 4 words Montgomery). */
 int kzgb_srs_load_synthetic(kzgb_ctx* ctx, const uint64_t tau_mont[4], size_t n_points);
+/* Point range of the same synthetic SRS: local point i is tau^(first+i) * G (point-range sharding of one
+ * large MSM across GPUs: each rank holds only its own range). */
+int kzgb_srs_load_synthetic_range(kzgb_ctx* ctx, const uint64_t tau_mont[4], size_t first, size_t n_points);
 /* Number of monomial points resident (== SRS.g1.len()). */
 size_t kzgb_srs_len(const kzgb_ctx* ctx);
 /* Read back decompressed points [start, start+count) to fill `SRS.g1` (pub field, srs.rs:13). */
@@ -80,6 +83,12 @@ int kzgb_msm_srs(kzgb_ctx* ctx, const uint64_t* scalars_mont, size_t n, uint64_t
 /* Same over a point range [first, first+n) of the SRS (point-range sharding of a large MSM). */
 int kzgb_msm_srs_range(kzgb_ctx* ctx, const uint64_t* scalars_mont, size_t first, size_t n, uint64_t out_xy[8],
                        uint8_t* out_inf);
+/* Same with the scalars already resident in device memory (n x 4 words, Montgomery). */
+int kzgb_msm_srs_range_dev(kzgb_ctx* ctx, const uint64_t* scalars_dev, size_t first, size_t n, uint64_t out_xy[8],
+                           uint8_t* out_inf);
+/* out_dev[i] = base^(first_exponent + i), Montgomery, written to DEVICE memory (helpers::compute_powers,
+ * primitives/src/helpers.rs:298-314; also the synthetic scalars of the MSM benchmark). */
+int kzgb_fr_powers_dev(kzgb_ctx* ctx, const uint64_t base_mont[4], size_t first_exponent, size_t n, uint64_t* out_dev);
 /* Variable-base MSM.  Replaces helpers::g1_lincomb (primitives/src/helpers.rs:328-337). */
 int kzgb_msm_var(kzgb_ctx* ctx, const uint64_t* bases_xy, const uint8_t* bases_inf, const uint64_t* scalars_mont,
                  size_t m, uint64_t out_xy[8], uint8_t* out_inf);

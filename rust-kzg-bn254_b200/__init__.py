@@ -365,10 +365,11 @@ class SRS:
         return s
 
     @classmethod
-    def synthetic(cls, n: int, tau: int, engine: Optional[Engine] = None) -> "SRS":
-        """SRS_i = tau^i * G generated on the GPU (SURVEY.md 8d synthetic inputs)."""
+    def synthetic(cls, n: int, tau: int, engine: Optional[Engine] = None, first: int = 0) -> "SRS":
+        """SRS_i = tau^(first+i) * G generated on the GPU (SURVEY.md 8d synthetic inputs); `first` selects a
+        point range of the same SRS for point-range sharding."""
         s = cls._blank(engine, n)
-        s.engine.check(lib.kzgb_srs_load_synthetic(s.engine.h, fr_to_mont_bytes([tau]), n))
+        s.engine.check(lib.kzgb_srs_load_synthetic_range(s.engine.h, fr_to_mont_bytes([tau]), first, n))
         return s
 
     def __len__(self):

@@ -34,11 +34,14 @@ SIGNATURES = {
     "kzgb_srs_load_gnark_be": (C.c_int, [ctx_p, buf, C.c_size_t]),
     "kzgb_srs_load_affine_mont": (C.c_int, [ctx_p, buf, buf, C.c_size_t]),
     "kzgb_srs_load_synthetic": (C.c_int, [ctx_p, buf, C.c_size_t]),
+    "kzgb_srs_load_synthetic_range": (C.c_int, [ctx_p, buf, C.c_size_t, C.c_size_t]),
     "kzgb_srs_len": (C.c_size_t, [ctx_p]),
     "kzgb_srs_get_affine_mont": (C.c_int, [ctx_p, C.c_size_t, C.c_size_t, buf, buf]),
     "kzgb_srs_precompute": (C.c_int, [ctx_p, C.c_size_t, C.c_int]),
     "kzgb_msm_srs": (C.c_int, [ctx_p, buf, C.c_size_t, buf, u8p]),
     "kzgb_msm_srs_range": (C.c_int, [ctx_p, buf, C.c_size_t, C.c_size_t, buf, u8p]),
+    "kzgb_msm_srs_range_dev": (C.c_int, [ctx_p, buf, C.c_size_t, C.c_size_t, buf, u8p]),
+    "kzgb_fr_powers_dev": (C.c_int, [ctx_p, buf, C.c_size_t, C.c_size_t, buf]),
     "kzgb_msm_var": (C.c_int, [ctx_p, buf, buf, buf, C.c_size_t, buf, u8p]),
     "kzgb_g1_add": (C.c_int, [buf, C.c_uint8, buf, C.c_uint8, buf, u8p]),
     "kzgb_ntt_fr": (C.c_int, [ctx_p, buf, C.c_size_t, C.c_int]),

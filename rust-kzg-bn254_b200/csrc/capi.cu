@@ -569,14 +569,18 @@ int kzgb_srs_load_affine_mont(kzgb_ctx* c, const uint64_t* xy, const uint8_t* in
     return srs_install(c, pts, n);
 }
 
+int kzgb_srs_load_synthetic_range(kzgb_ctx* c, const uint64_t tau_mont[4], size_t first, size_t n);
 int kzgb_srs_load_synthetic(kzgb_ctx* c, const uint64_t tau_mont[4], size_t n) {
+    return kzgb_srs_load_synthetic_range(c, tau_mont, 0, n);
+}
+int kzgb_srs_load_synthetic_range(kzgb_ctx* c, const uint64_t tau_mont[4], size_t first, size_t n) {
     Guard g(c);
     if (n == 0 || n > ((size_t)1 << 28)) return fail(c, KZGB_ERR_GENERIC, "invalid number of SRS points");
     Affine* pts = nullptr;
     CK(c, cudaMalloc((void**)&pts, n * sizeof(Affine)));
     Fr tau;
     memcpy(tau.l, tau_mont, 32);
-    srs_synthetic_launch(pts, (uint32_t)n, &tau, nullptr, c->lanes[0].st);
+    srs_synthetic_launch(pts, (uint32_t)n, &tau, (uint32_t)first, c->lanes[0].st);
     cudaError_t e = cudaStreamSynchronize(c->lanes[0].st);
     if (e != cudaSuccess) { cudaFree(pts); CK(c, e); }
     return srs_install(c, pts, n);
@@ -619,6 +623,26 @@ int kzgb_msm_srs_range(kzgb_ctx* c, const uint64_t* scalars, size_t first, size_
     int rc = msm_blocking(c, L, (Fr*)L.work.p, false, first, n, nullptr, &r);
     if (rc) return rc;
     affine_to_abi(r, out_xy, out_inf);
+    return KZGB_OK;
+}
+int kzgb_msm_srs_range_dev(kzgb_ctx* c, const uint64_t* scalars_dev, size_t first, size_t n, uint64_t out_xy[8],
+                           uint8_t* out_inf) {
+    Guard g(c);
+    Lane& L = c->lanes[0];
+    if (first + n > c->srs_n) return fail(c, KZGB_ERR_SERIALIZATION, "polynomial length is not correct");
+    Affine r;
+    int rc = msm_blocking(c, L, (const Fr*)scalars_dev, false, first, n, nullptr, &r);
+    if (rc) return rc;
+    affine_to_abi(r, out_xy, out_inf);
+    return KZGB_OK;
+}
+int kzgb_fr_powers_dev(kzgb_ctx* c, const uint64_t base_mont[4], size_t first_exponent, size_t n, uint64_t* out_dev) {
+    Guard g(c);
+    Fr b;
+    memcpy(b.l, base_mont, 32);
+    fr_powers_launch((Fr*)out_dev, (uint32_t)n, &b, c->lanes[0].st, (uint32_t)first_exponent);
+    CK(c, cudaStreamSynchronize(c->lanes[0].st));
+    CK(c, cudaGetLastError());
     return KZGB_OK;
 }
 int kzgb_msm_srs(kzgb_ctx* c, const uint64_t* scalars, size_t n, uint64_t out_xy[8], uint8_t* out_inf) {

@@ -62,8 +62,8 @@ void srs_precompute_launch(Affine* table, uint32_t n, uint32_t stride, int c, in
 size_t srs_precompute_scratch_bytes(uint32_t batch, int W);
 // point validation (on curve or identity): err[0] preset 0xffffffff -> 1 + lowest offending index
 void g1_validate_launch(const Affine* pts, uint32_t n, uint32_t* err, cudaStream_t st);
-// SRS_i = tau^i * G (synthetic SRS for benches/tests; tau in Montgomery form)
-void srs_synthetic_launch(Affine* out, uint32_t n, const Fr* tau_mont_host, XYZZ* scratch, cudaStream_t st);
+// SRS_i = tau^(first + i) * G (synthetic SRS for benches/tests; tau in Montgomery form)
+void srs_synthetic_launch(Affine* out, uint32_t n, const Fr* tau_mont_host, uint32_t first, cudaStream_t st);
 
 // ---- Fr NTT ---------------------------------------------------------------------
 // tw: omega_N^j for j < N/2 (Montgomery), N = 2^logN >= n.
@@ -88,8 +88,8 @@ void eval_quotient_launch(const Fr* evals, uint32_t n, int logn, uint32_t batch,
                           const Fr* tinv_mont_dev, const Fr* tw, int logN, const Fr* ninv_mont_host, Fr* scratch,
                           Fr* q_out, Fr* y_out, cudaStream_t st);
 size_t eval_quotient_scratch_elems(uint32_t n, uint32_t batch);
-// out[i] = base^i (Montgomery), i < n
-void fr_powers_launch(Fr* out, uint32_t n, const Fr* base_mont_host, cudaStream_t st);
+// out[i] = base^(first + i) (Montgomery), i < n
+void fr_powers_launch(Fr* out, uint32_t n, const Fr* base_mont_host, cudaStream_t st, uint32_t first = 0);
 // out[i] = a[i] * b[i]
 void fr_mul_vec_launch(Fr* out, const Fr* a, const Fr* b, uint32_t n, cudaStream_t st);
 // out[0] = sum a[i]*b[i]   (single block; n small: verifier batch)

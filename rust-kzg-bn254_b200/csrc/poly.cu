@@ -382,10 +382,10 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_quotient_fix(uint32_t n, int l
     }
 }
 
-__global__ void __launch_bounds__(256) k_fr_powers(Fr* __restrict__ out, uint32_t n, Fr base) {
+__global__ void __launch_bounds__(256) k_fr_powers(Fr* __restrict__ out, uint32_t n, Fr base, uint32_t first) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint32_t e[8] = {i, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t e[8] = {first + i, 0, 0, 0, 0, 0, 0, 0};
     Fr r;
     fe_pow(r, base, e);
     fe_store(&out[i], r);
@@ -457,9 +457,9 @@ void eval_quotient_launch(const Fr* evals, uint32_t n, int logn, uint32_t batch,
     }
 }
 
-void fr_powers_launch(Fr* out, uint32_t n, const Fr* base_mont_host, cudaStream_t st) {
+void fr_powers_launch(Fr* out, uint32_t n, const Fr* base_mont_host, cudaStream_t st, uint32_t first) {
     if (!n) return;
-    k_fr_powers<<<(n + 255) / 256, 256, 0, st>>>(out, n, *base_mont_host);
+    k_fr_powers<<<(n + 255) / 256, 256, 0, st>>>(out, n, *base_mont_host, first);
     g_launch_count++;
 }
 void fr_mul_vec_launch(Fr* out, const Fr* a, const Fr* b, uint32_t n, cudaStream_t st) {

@@ -95,10 +95,10 @@ __global__ void __launch_bounds__(128) k_validate(const Affine* __restrict__ pts
 }
 
 // out[i] = tau^i * G
-__global__ void __launch_bounds__(128) k_synthetic(Affine* __restrict__ out, uint32_t n, Fr tau) {
+__global__ void __launch_bounds__(128) k_synthetic(Affine* __restrict__ out, uint32_t n, Fr tau, uint32_t first) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint32_t e[8] = {i, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t e[8] = {first + i, 0, 0, 0, 0, 0, 0, 0};
     Fr s;
     fe_pow(s, tau, e);
     fe_from_mont(s, s);
@@ -144,9 +144,9 @@ void g1_validate_launch(const Affine* pts, uint32_t n, uint32_t* err, cudaStream
     g_launch_count++;
 }
 
-void srs_synthetic_launch(Affine* out, uint32_t n, const Fr* tau_mont_host, XYZZ*, cudaStream_t st) {
+void srs_synthetic_launch(Affine* out, uint32_t n, const Fr* tau_mont_host, uint32_t first, cudaStream_t st) {
     if (!n) return;
-    k_synthetic<<<(n + 127) / 128, 128, 0, st>>>(out, n, *tau_mont_host);
+    k_synthetic<<<(n + 127) / 128, 128, 0, st>>>(out, n, *tau_mont_host, first);
     g_launch_count++;
 }
 

@@ -1,0 +1,214 @@
+//! Drop-in for `rust_kzg_bn254_prover::{kzg::KZG, srs::SRS}` backed by the B200 engine.
+//! SOURCE ONLY (never compiled: no Rust toolchain in the build image).  Signatures follow
+//! prover/src/kzg.rs:25-309 and prover/src/srs.rs:10-49 of the reference line by line.
+//!
+//! `KZG` derives PartialEq + Clone over `expanded_roots_of_unity` and `SRS` has pub fields in the
+//! reference, so no device handle is stored inside them: contexts live in a process-global registry
+//! keyed by the address/length of the `SRS.g1` slice.
+mod ffi;
+
+use ark_bn254::{Fq, Fr, G1Affine};
+use ark_ec::AffineRepr;
+use ark_ff::Zero;
+use rust_kzg_bn254_primitives::{
+    blob::Blob,
+    errors::KzgError,
+    helpers,
+    polynomial::{PolynomialCoeffForm, PolynomialEvalForm},
+};
+use std::{borrow::Cow, collections::HashMap, ffi::CStr, ffi::CString, sync::Mutex};
+
+const _: () = assert!(core::mem::size_of::<Fr>() == 32 && core::mem::size_of::<Fq>() == 32);
+
+struct Ctx(*mut ffi::kzgb_ctx);
+unsafe impl Send for Ctx {}
+impl Drop for Ctx {
+    fn drop(&mut self) {
+        unsafe { ffi::kzgb_ctx_destroy(self.0) }
+    }
+}
+
+static REGISTRY: Mutex<Option<HashMap<(usize, usize), Ctx>>> = Mutex::new(None);
+
+fn to_err(ctx: *mut ffi::kzgb_ctx, rc: i32, poly_len: usize, srs_len: usize) -> KzgError {
+    let msg = unsafe { CStr::from_ptr(ffi::kzgb_last_error(ctx)) }.to_string_lossy().into_owned();
+    match rc {
+        ffi::KZGB_ERR_SRS_CAPACITY => KzgError::SrsCapacityExceeded { polynomial_len: poly_len, srs_len },
+        ffi::KZGB_ERR_SERIALIZATION => KzgError::SerializationError(msg),
+        ffi::KZGB_ERR_FFT => KzgError::FFTError(msg),
+        ffi::KZGB_ERR_NOT_ON_CURVE => KzgError::NotOnCurveError(msg),
+        ffi::KZGB_ERR_MSM => KzgError::MsmError(msg),
+        ffi::KZGB_ERR_INVALID_INPUT_LENGTH => KzgError::InvalidInputLength,
+        ffi::KZGB_ERR_DESERIALIZATION => KzgError::DeserializationError(msg),
+        ffi::KZGB_ERR_INVALID_FIELD_ELEMENT => KzgError::InvalidFieldElement(msg),
+        _ => KzgError::GenericError(msg),
+    }
+}
+
+/// arkworks `G1Affine {x, y, infinity}` is repr(Rust): repack to the ABI's x||y words + flag.
+fn pack_points(pts: &[G1Affine]) -> (Vec<u64>, Vec<u8>) {
+    let mut xy = Vec::with_capacity(pts.len() * 8);
+    let mut inf = Vec::with_capacity(pts.len());
+    for p in pts {
+        if p.is_zero() {
+            xy.extend_from_slice(&[0u64; 8]);
+            inf.push(1);
+        } else {
+            xy.extend_from_slice(&p.x.0 .0); // Montgomery limbs, as primitives/src/helpers.rs:158 reads them
+            xy.extend_from_slice(&p.y.0 .0);
+            inf.push(0);
+        }
+    }
+    (xy, inf)
+}
+
+fn unpack_point(xy: &[u64; 8], inf: u8) -> G1Affine {
+    if inf != 0 {
+        return G1Affine::zero();
+    }
+    let x = Fq::new_unchecked(ark_ff::BigInt([xy[0], xy[1], xy[2], xy[3]]));
+    let y = Fq::new_unchecked(ark_ff::BigInt([xy[4], xy[5], xy[6], xy[7]]));
+    G1Affine::new_unchecked(x, y)
+}
+
+fn fr_words(v: &[Fr]) -> *const u64 {
+    v.as_ptr() as *const u64 // Fp<MontBackend<_,4>,4> == [u64; 4], Montgomery form
+}
+
+#[derive(Debug, PartialEq)]
+pub struct SRS<'a> {
+    pub g1: Cow<'a, [G1Affine]>,
+    pub order: u32,
+}
+
+impl SRS<'_> {
+    /// prover/src/srs.rs:35-49: the file is read in one piece and decompressed on the GPU.
+    pub fn new(path_to_g1_points: &str, order: u32, points_to_load: u32) -> Result<Self, KzgError> {
+        let mut ctx = std::ptr::null_mut();
+        if unsafe { ffi::kzgb_ctx_create(&mut ctx, 0, std::ptr::null_mut()) } != 0 {
+            return Err(KzgError::GenericError("no usable CUDA device".into()));
+        }
+        let cpath = CString::new(path_to_g1_points).unwrap();
+        let rc = unsafe { ffi::kzgb_srs_load_file(ctx, cpath.as_ptr(), order, points_to_load) };
+        if rc != 0 {
+            let e = to_err(ctx, rc, 0, 0);
+            unsafe { ffi::kzgb_ctx_destroy(ctx) };
+            return Err(e);
+        }
+        let n = unsafe { ffi::kzgb_srs_len(ctx) };
+        let mut xy = vec![0u64; 8 * n];
+        let mut inf = vec![0u8; n];
+        unsafe { ffi::kzgb_srs_get_affine_mont(ctx, 0, n, xy.as_mut_ptr(), inf.as_mut_ptr()) };
+        let g1: Vec<G1Affine> = (0..n).map(|i| unpack_point(xy[8 * i..8 * i + 8].try_into().unwrap(), inf[i])).collect();
+        let key = (g1.as_ptr() as usize, g1.len());
+        REGISTRY.lock().unwrap().get_or_insert_with(HashMap::new).insert(key, Ctx(ctx));
+        Ok(Self { g1: Cow::Owned(g1), order })
+    }
+}
+
+fn with_ctx<T>(srs: &SRS, f: impl FnOnce(*mut ffi::kzgb_ctx) -> T) -> T {
+    let key = (srs.g1.as_ptr() as usize, srs.g1.len());
+    let mut reg = REGISTRY.lock().unwrap();
+    let map = reg.get_or_insert_with(HashMap::new);
+    let ctx = map.entry(key).or_insert_with(|| {
+        // an SRS built by the caller (pub fields): upload its points once
+        let mut ctx = std::ptr::null_mut();
+        unsafe { ffi::kzgb_ctx_create(&mut ctx, 0, std::ptr::null_mut()) };
+        let (xy, inf) = pack_points(&srs.g1);
+        unsafe { ffi::kzgb_srs_load_affine_mont(ctx, xy.as_ptr(), inf.as_ptr(), srs.g1.len()) };
+        Ctx(ctx)
+    });
+    f(ctx.0)
+}
+
+#[derive(Debug, PartialEq, Clone, Default)]
+pub struct KZG {
+    expanded_roots_of_unity: Vec<Fr>,
+}
+
+impl KZG {
+    pub fn new() -> Self {
+        Self { expanded_roots_of_unity: vec![] }
+    }
+    pub fn calculate_and_store_roots_of_unity(&mut self, length_of_data_after_padding: u64) -> Result<(), KzgError> {
+        self.expanded_roots_of_unity = helpers::calculate_roots_of_unity(length_of_data_after_padding)?;
+        Ok(())
+    }
+    pub fn get_roots_of_unities(&self) -> Vec<Fr> {
+        self.expanded_roots_of_unity.clone()
+    }
+    pub fn get_nth_root_of_unity(&self, i: usize) -> Option<&Fr> {
+        self.expanded_roots_of_unity.get(i)
+    }
+
+    pub fn commit_eval_form(&self, polynomial: &PolynomialEvalForm, srs: &SRS) -> Result<G1Affine, KzgError> {
+        let (mut xy, mut inf) = ([0u64; 8], 0u8);
+        let ev = polynomial.evaluations();
+        with_ctx(srs, |ctx| {
+            let rc = unsafe { ffi::kzgb_commit_eval(ctx, fr_words(ev), ev.len(), xy.as_mut_ptr(), &mut inf) };
+            if rc != 0 { Err(to_err(ctx, rc, ev.len(), srs.g1.len())) } else { Ok(unpack_point(&xy, inf)) }
+        })
+    }
+    pub fn commit_coeff_form(&self, polynomial: &PolynomialCoeffForm, srs: &SRS) -> Result<G1Affine, KzgError> {
+        let (mut xy, mut inf) = ([0u64; 8], 0u8);
+        let cf = polynomial.coeffs();
+        with_ctx(srs, |ctx| {
+            let rc = unsafe { ffi::kzgb_commit_coeff(ctx, fr_words(cf), cf.len(), xy.as_mut_ptr(), &mut inf) };
+            if rc != 0 { Err(to_err(ctx, rc, cf.len(), srs.g1.len())) } else { Ok(unpack_point(&xy, inf)) }
+        })
+    }
+    pub fn commit_blob(&self, blob: &Blob, srs: &SRS) -> Result<G1Affine, KzgError> {
+        let (mut xy, mut inf) = ([0u64; 8], 0u8);
+        let d = blob.data();
+        with_ctx(srs, |ctx| {
+            let rc = unsafe { ffi::kzgb_commit_blob(ctx, d.as_ptr(), d.len(), xy.as_mut_ptr(), &mut inf) };
+            if rc != 0 { Err(to_err(ctx, rc, d.len().div_ceil(32).next_power_of_two(), srs.g1.len())) } else { Ok(unpack_point(&xy, inf)) }
+        })
+    }
+    pub fn compute_proof(&self, polynomial: &PolynomialEvalForm, z_fr: &Fr, srs: &SRS) -> Result<G1Affine, KzgError> {
+        if polynomial.len() != self.expanded_roots_of_unity.len() {
+            return Err(KzgError::GenericError("inconsistent length between blob and root of unities".to_string()));
+        }
+        let (mut xy, mut inf) = ([0u64; 8], 0u8);
+        let ev = polynomial.evaluations();
+        with_ctx(srs, |ctx| {
+            let rc = unsafe {
+                ffi::kzgb_compute_proof(ctx, fr_words(ev), ev.len(), z_fr as *const Fr as *const u64, xy.as_mut_ptr(), &mut inf,
+                                        std::ptr::null_mut())
+            };
+            if rc != 0 { Err(to_err(ctx, rc, ev.len(), srs.g1.len())) } else { Ok(unpack_point(&xy, inf)) }
+        })
+    }
+    pub fn compute_proof_with_known_z_fr_index(&self, polynomial: &PolynomialEvalForm, index: u64, srs: &SRS) -> Result<G1Affine, KzgError> {
+        let z = self
+            .get_nth_root_of_unity(index as usize)
+            .ok_or_else(|| KzgError::GenericError("Root of unity not found".to_string()))?;
+        self.compute_proof(polynomial, z, srs)
+    }
+    pub fn g1_ifft(&self, length: usize, srs: &SRS) -> Result<Vec<G1Affine>, KzgError> {
+        if !length.is_power_of_two() {
+            return Err(KzgError::FFTError("length provided is not a power of 2".to_string()));
+        }
+        let mut xy = vec![0u64; 8 * length];
+        let mut inf = vec![0u8; length];
+        with_ctx(srs, |ctx| {
+            let rc = unsafe { ffi::kzgb_g1_ifft(ctx, length, xy.as_mut_ptr(), inf.as_mut_ptr()) };
+            if rc != 0 { return Err(to_err(ctx, rc, length, srs.g1.len())); }
+            Ok((0..length).map(|i| unpack_point(xy[8 * i..8 * i + 8].try_into().unwrap(), inf[i])).collect())
+        })
+    }
+    pub fn compute_blob_proof(&self, blob: &Blob, commitment: &G1Affine, srs: &SRS) -> Result<G1Affine, KzgError> {
+        helpers::validate_g1_point(commitment)?;
+        let n = blob.len().div_ceil(32).next_power_of_two();
+        if n != self.expanded_roots_of_unity.len() {
+            return Err(KzgError::GenericError("inconsistent length between blob and root of unities".to_string()));
+        }
+        let (cxy, cinf) = pack_points(std::slice::from_ref(commitment));
+        let (mut xy, mut inf) = ([0u64; 8], 0u8);
+        let d = blob.data();
+        with_ctx(srs, |ctx| {
+            let rc = unsafe { ffi::kzgb_compute_blob_proof(ctx, d.as_ptr(), d.len(), cxy.as_ptr(), cinf[0], xy.as_mut_ptr(), &mut inf) };
+            if rc != 0 { Err(to_err(ctx, rc, n, srs.g1.len())) } else { Ok(unpack_point(&xy, inf)) }
+        })
+    }
+}

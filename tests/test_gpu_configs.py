@@ -1,0 +1,142 @@
+"""GPU parity at BASELINE-config sizes through size-independent properties of the synthetic SRS
+(SRS_i = tau^i G with known tau): closed forms cost O(n) big-int work, no CPU MSM."""
+import ctypes as C
+import random
+
+import pytest
+
+import golden_data as g
+from __graft_entry__ import load_package
+from oracle import bn254 as o
+
+pytestmark = pytest.mark.gpu
+TAU = o.SYNTH_TAU
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    return load_package()
+
+
+def _barycentric(evals, z):
+    """p(z) for the interpolant of evals on the 2^k domain, O(n) with one batch inversion."""
+    n = len(evals)
+    w = o.PRIMITIVE_ROOTS_OF_UNITY[n.bit_length() - 1]
+    roots = [1] * n
+    for i in range(1, n):
+        roots[i] = roots[i - 1] * w % o.R
+    den = [(z - r) % o.R for r in roots]
+    pref, acc = [], 1
+    for d in den:
+        pref.append(acc)
+        acc = acc * d % o.R
+    inv = pow(acc, -1, o.R)
+    total = 0
+    for i in range(n - 1, -1, -1):
+        di = inv * pref[i] % o.R
+        inv = inv * den[i] % o.R
+        total = (total + evals[i] * roots[i] % o.R * di) % o.R
+    return total * (pow(z, n, o.R) - 1) % o.R * pow(n, -1, o.R) % o.R
+
+
+@pytest.mark.parametrize("logn", [16, 19])
+def test_commit_and_proof_closed_form_at_bench_sizes(pkg, logn):
+    """configs[1]/[2]: commitment = p(tau) G, proof = ((p(tau) - y)/(tau - z)) G, z from the real transcript."""
+    n = 1 << logn
+    eng = pkg.Engine(0)
+    srs = pkg.SRS.synthetic(n, TAU, engine=eng)
+    rnd = random.Random(logn)
+    seed = [rnd.randrange(o.R) for _ in range(512)]
+    evals = (seed * (n // 512))[:n]
+    for k in range(0, n, 997):  # break the periodicity
+        evals[k] = rnd.randrange(o.R)
+    data = b"".join(e.to_bytes(32, "big") for e in evals)
+    blob = pkg.Blob.from_unchecked(data)
+    cs, ps = pkg.KZG.commit_and_prove_blobs([blob, blob], srs)
+    ptau = _barycentric(evals, TAU)
+    c = o.g1_mul(o.G1_GEN, ptau)
+    assert cs[0] == cs[1] == o.g1_serialize_compressed(c)
+    z = o.hash_to_field_element(
+        o.FIAT_SHAMIR_PROTOCOL_DOMAIN + n.to_bytes(8, "big") + data + o.g1_serialize_compressed(c)
+    )
+    y = _barycentric(evals, z)
+    pi = o.g1_mul(o.G1_GEN, (ptau - y) * pow((TAU - z) % o.R, -1, o.R) % o.R)
+    assert ps[0] == ps[1] == o.g1_serialize_compressed(pi)
+    # the single-call API agrees with the batch pipeline
+    kzg = pkg.KZG()
+    kzg.expanded_roots_of_unity = [0] * n  # only its length is checked (kzg.rs:135)
+    assert kzg.commit_blob(blob, srs) == c
+    assert kzg.compute_blob_proof(blob, c, srs) == pi
+
+
+def test_point_range_sharded_msm_closed_form(pkg):
+    """config 4 at 2^20 on one GPU in variable-base mode, as 1 range and as 3 ranges added on the host:
+    scalars a^i => MSM = ((a tau)^N - 1)/(a tau - 1) G."""
+    import torch
+
+    sh = __import__("rust_kzg_bn254_b200.sharding", fromlist=["x"])
+    N = 1 << 20
+    a = 0x1234567890ABCDEF1234567890ABCDEF1234567890ABCDEF % o.R
+    at = a * TAU % o.R
+    expect = o.g1_mul(o.G1_GEN, (pow(at, N, o.R) - 1) * pow(at - 1, -1, o.R) % o.R)
+    for world in (1, 3):
+        partials = []
+        for rank in range(world):
+            first, count = sh.shard_range(N, rank, world)
+            eng = pkg.Engine(0)
+            srs = pkg.SRS.synthetic(count, TAU, engine=eng, first=first)
+            srs.precompute(0, -1)
+            scal = torch.empty(count * 32, dtype=torch.uint8, device="cuda")
+            eng.check(pkg.lib.kzgb_fr_powers_dev(eng.h, pkg.fr_to_mont_bytes([a]), first, count, scal.data_ptr()))
+            out = C.create_string_buffer(64)
+            inf = C.c_uint8(0)
+            eng.check(pkg.lib.kzgb_msm_srs_range_dev(eng.h, scal.data_ptr(), 0, count, out, C.byref(inf)))
+            partials.append(out.raw + bytes([inf.value]))
+            eng.close()
+        assert sh.reduce_g1_partials(pkg, partials) == expect
+
+
+def test_fixed_base_equals_variable_base(pkg):
+    """The window-table MSM and the table-free MSM give the same point (2^16 points, random scalars)."""
+    n = 1 << 16
+    rnd = random.Random(5)
+    sc = [rnd.randrange(o.R) for _ in range(n)]
+    expect = o.tau_trick_msm(sc)
+    e1 = pkg.Engine(0)
+    s1 = pkg.SRS.synthetic(n, TAU, engine=e1)
+    s1.precompute(n, 0)
+    assert pkg.KZG().commit_coeff_form(pkg.PolynomialCoeffForm(sc), s1) == expect
+    e2 = pkg.Engine(0)
+    s2 = pkg.SRS.synthetic(n, TAU, engine=e2)
+    s2.precompute(0, -1)
+    assert pkg.KZG().commit_coeff_form(pkg.PolynomialCoeffForm(sc), s2) == expect
+    # a different window width gives the same point too
+    s1.precompute(n, 11)
+    assert pkg.KZG().commit_coeff_form(pkg.PolynomialCoeffForm(sc), s1) == expect
+
+
+def test_batch_verify_rlc_pairing_relation(pkg):
+    """config 5 shape (m = 64 pairs of 2^12-Fr blobs): rhs = tau * lhs, and a tampered proof breaks it."""
+    n = 1 << 12
+    m = 64
+    eng = pkg.Engine(0)
+    srs = pkg.SRS.synthetic(n, TAU, engine=eng)
+    rnd = random.Random(12)
+    blobs = []
+    for i in range(m):
+        ev = [rnd.randrange(o.R) for _ in range(64)] * (n // 64)
+        ev[i] = rnd.randrange(o.R)
+        blobs.append(pkg.Blob.new(b"".join(e.to_bytes(32, "big") for e in ev)))
+    blobs[3] = pkg.Blob.new(g.blobs_txt())
+    cs, ps = pkg.KZG.commit_and_prove_blobs(blobs, srs)
+    cpts = [o.g1_deserialize_compressed(c) for c in cs]
+    ppts = [o.g1_deserialize_compressed(p) for p in ps]
+    lhs, rhs = pkg.verify_blob_kzg_proof_batch_rlc(blobs, cpts, ppts, eng)
+    assert lhs is not None and o.g1_mul(lhs, TAU) == rhs
+    bad = list(ppts)
+    bad[5] = o.g1_add(bad[5], o.G1_GEN)
+    lhs2, rhs2 = pkg.verify_blob_kzg_proof_batch_rlc(blobs, cpts, bad, eng)
+    assert o.g1_mul(lhs2, TAU) != rhs2
+    # a small prefix against the full oracle restatement of batch.rs
+    bo = [o.Blob(b.data()) for b in blobs[:3]]
+    assert pkg.verify_blob_kzg_proof_batch_rlc(blobs[:3], cpts[:3], ppts[:3], eng) == o.verify_blob_kzg_proof_batch_rlc(bo, cpts[:3], ppts[:3])
