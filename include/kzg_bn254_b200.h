@@ -176,6 +176,13 @@ int kzgb_timer_end(kzgb_ctx* ctx, double* ms_out);
 /* Bucket-accumulation kernel statistics since the last reset: summed CUDA-event duration of the
  * launches (each bracketed on its own stream), launch count, and point additions performed. */
 int kzgb_stats(kzgb_ctx* ctx, double* acc_ms, uint64_t* acc_launches, uint64_t* acc_point_adds, int reset);
+/* Bucket-accumulation tuning (process-wide): number of batch-affine levels in front of the XYZZ
+ * accumulation (default 0 = off: measured slower than XYZZ
+ * accumulation on B200), the minimum average bucket occupancy at which they are used
+ * (default 64), pairs per thread at level 0 (0 = default: sized so every level is one full wave of
+ * the GPU).  Negative values keep the current setting.
+ * Results never depend on it (exact group arithmetic); tests use it to force every code path. */
+int kzgb_msm_tuning(int batch_affine_levels, int min_avg_bucket, int pairs_per_thread);
 /* Fixed-base table in use: window bits c, windows W, points covered (0 = none). */
 int kzgb_msm_config(const kzgb_ctx* ctx, int* window_bits, int* windows, size_t* table_points);
 

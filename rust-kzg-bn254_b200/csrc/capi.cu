@@ -72,6 +72,7 @@ struct kzgb_ctx {
     size_t wt_n = 0;
     int wt_c = 0, wt_W = 0;
     bool auto_precompute = true;
+    DevBuf batch_bytes;  // blob bytes of the batch in flight (commit_and_prove_blobs)
     // twiddles
     Fr* tw = nullptr;
     int logN = 0;
@@ -498,6 +499,7 @@ void kzgb_ctx_destroy(kzgb_ctx* c) {
     if (c->srs) cudaFree(c->srs);
     if (c->wtable) cudaFree(c->wtable);
     if (c->tw) cudaFree(c->tw);
+    c->batch_bytes.release();
     if (c->t0) cudaEventDestroy(c->t0);
     if (c->t1) cudaEventDestroy(c->t1);
     cudaSetDevice(prev);
@@ -944,32 +946,82 @@ static int batch_impl(kzgb_ctx* c, const uint8_t* const* blobs_dev, const uint8_
         });
     }
 
+    // Blob bytes stay resident on the device between a blob's commit and its proof (one H2D per blob).
+    std::vector<size_t> byte_off(count, 0);
+    bool resident = false;
+    if (!blobs_dev) {
+        size_t total = 0;
+        for (size_t i = 0; i < count; i++) { byte_off[i] = total; total += (lens[i] + 255) & ~(size_t)255; }
+        if (total <= ((size_t)16 << 30) && c->batch_bytes.reserve(total) == cudaSuccess) resident = true;
+        else cudaGetLastError();
+    }
+
+    // Task scheduler.  commit(i) needs nothing; proof(i) needs commit(i) and the transcript midstate of
+    // blob i (host SHA-256, ~9 ms for 16 MiB).  A lane takes the lowest ready proof, else the next
+    // commit, so the GPU never idles behind the hashing pool.
     std::vector<int> lane_rc(n_lanes, KZGB_OK);
-    std::vector<std::string> lane_err(n_lanes);
-    std::atomic<size_t> next_blob{0};
+    std::vector<uint8_t> commit_done(count, 0), proof_taken(count, 0);
+    std::vector<Affine> commits(count);
+    size_t next_commit = 0, proofs_taken = 0, proof_scan = 0;
+    bool failed = false;
     auto lane_main = [&](int li) {
         cudaSetDevice(c->device);
         Lane& L = c->lanes[li];
         for (;;) {
-            size_t i = next_blob.fetch_add(1);
-            if (i >= count) break;
-            size_t len = lens[i], n = blob_poly_len(len);
-            int r = blob_to_evals(c, L, blobs_host[i], blobs_dev ? blobs_dev[i] : nullptr, len, n);
-            MsmJob job;
-            Affine C, Pi;
-            if (!r) r = commit_evals_enqueue(c, L, (Fr*)L.evals.p, n, &job);
-            if (!r) r = msm_finish(c, L, job, &C);
-            if (r) { lane_rc[li] = r; break; }
+            size_t i = 0;
+            bool is_proof = false;
             {
                 std::unique_lock<std::mutex> lk(mu);
-                cv.wait(lk, [&] { return ready[i] != 0; });
+                for (;;) {
+                    if (failed) return;
+                    while (proof_scan < count && proof_taken[proof_scan]) proof_scan++;
+                    bool found = false;
+                    for (size_t k = proof_scan; k < count && k < next_commit; k++) {
+                        if (!proof_taken[k] && commit_done[k] && ready[k]) { i = k; found = true; break; }
+                    }
+                    if (found) {
+                        proof_taken[i] = 1; proofs_taken++; is_proof = true;
+                        if (proofs_taken == count) cv.notify_all();  // lanes with nothing left to take can leave
+                        break;
+                    }
+                    if (next_commit < count) { i = next_commit++; break; }
+                    if (proofs_taken == count) return;
+                    cv.wait(lk);
+                }
             }
-            Fr z = challenge_finish(mid[i], C);
-            r = proof_enqueue(c, L, (Fr*)L.evals.p, n, z, &job);
-            if (!r) r = msm_finish(c, L, job, &Pi);
-            if (r) { lane_rc[li] = r; break; }
-            serialize_compressed(C, commitments32 + 32 * i);
-            serialize_compressed(Pi, proofs32 + 32 * i);
+            size_t len = lens[i], n = blob_poly_len(len);
+            const uint8_t* dev_bytes = blobs_dev ? blobs_dev[i] : nullptr;
+            int r = KZGB_OK;
+            if (!dev_bytes && resident) {
+                uint8_t* slot = (uint8_t*)c->batch_bytes.p + byte_off[i];
+                if (!is_proof && len) {
+                    if (cudaMemcpyAsync(slot, blobs_host[i], len, cudaMemcpyHostToDevice, L.st) != cudaSuccess)
+                        r = fail(c, KZGB_ERR_DEVICE, "CUDA error: H2D copy of a blob failed");
+                }
+                dev_bytes = slot;
+            }
+            MsmJob job;
+            Affine out;
+            if (!r) r = blob_to_evals(c, L, blobs_host[i], dev_bytes, len, n);
+            if (!r && !is_proof) r = commit_evals_enqueue(c, L, (Fr*)L.evals.p, n, &job);
+            if (!r && is_proof) {
+                Fr z = challenge_finish(mid[i], commits[i]);
+                r = proof_enqueue(c, L, (Fr*)L.evals.p, n, z, &job);
+            }
+            if (!r) r = msm_finish(c, L, job, &out);
+            if (r) {
+                std::lock_guard<std::mutex> lk(mu);
+                lane_rc[li] = r; failed = true;
+                cv.notify_all();
+                return;
+            }
+            if (is_proof) {
+                serialize_compressed(out, proofs32 + 32 * i);
+            } else {
+                serialize_compressed(out, commitments32 + 32 * i);
+                { std::lock_guard<std::mutex> lk(mu); commits[i] = out; commit_done[i] = 1; }
+                cv.notify_all();
+            }
         }
     };
     std::vector<std::thread> lane_threads;
@@ -1241,6 +1293,11 @@ int kzgb_stats(kzgb_ctx* c, double* acc_ms, uint64_t* acc_launches, uint64_t* ac
     if (acc_point_adds) *acc_point_adds = na;
     return KZGB_OK;
 }
+int kzgb_msm_tuning(int batch_affine_levels, int min_avg_bucket, int pairs_per_thread) {
+    msm_set_tuning(batch_affine_levels, min_avg_bucket, pairs_per_thread);
+    return KZGB_OK;
+}
+
 int kzgb_msm_config(const kzgb_ctx* c, int* window_bits, int* windows, size_t* table_points) {
     if (window_bits) *window_bits = c->wt_c;
     if (windows) *windows = c->wt_W;

@@ -150,7 +150,7 @@ KZ_HD void xyzz_to_affine_with_inv(Affine& r, const XYZZ& p, const Fq& inv_zzz) 
 }
 KZ_HD void xyzz_to_affine(Affine& r, const XYZZ& p) {
     if (xyzz_is_inf(p)) { aff_set_inf(r); return; }
-    Fq inv; fe_inv(inv, p.zzz);
+    Fq inv; fe_inv_fast(inv, p.zzz);
     xyzz_to_affine_with_inv(r, p, inv);
 }
 KZ_HD bool aff_on_curve(const Affine& p) {
@@ -168,6 +168,22 @@ KZ_D Affine aff_load_ro(const Affine* p) {
     Affine r;
     r.x = fe_load_ro(&p->x);
     r.y = fe_load_ro(&p->y);
+    return r;
+}
+// Random 64-byte gather from a table far larger than L2: ask L2 to fetch only the 64 B that are used
+// (the default promotes a miss to the whole 128 B line, doubling DRAM traffic of the MSM gather).
+KZ_D Affine aff_gather_ro(const Affine* p) {
+    Affine r;
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        asm volatile("ld.global.nc.L2::64B.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(v[k].x), "=r"(v[k].y), "=r"(v[k].z), "=r"(v[k].w) : "l"(q + k));
+    r.x.l[0] = v[0].x; r.x.l[1] = v[0].y; r.x.l[2] = v[0].z; r.x.l[3] = v[0].w;
+    r.x.l[4] = v[1].x; r.x.l[5] = v[1].y; r.x.l[6] = v[1].z; r.x.l[7] = v[1].w;
+    r.y.l[0] = v[2].x; r.y.l[1] = v[2].y; r.y.l[2] = v[2].z; r.y.l[3] = v[2].w;
+    r.y.l[4] = v[3].x; r.y.l[5] = v[3].y; r.y.l[6] = v[3].z; r.y.l[7] = v[3].w;
     return r;
 }
 KZ_D void aff_store(Affine* p, const Affine& v) { fe_store(&p->x, v.x); fe_store(&p->y, v.y); }

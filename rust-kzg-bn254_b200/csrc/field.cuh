@@ -199,6 +199,135 @@ template <int F> KZ_HD void fe_inv(Fe<F>& r, const Fe<F>& a) {
     uint32_t e[8]; FeConst<F>::pm2(e);
     fe_pow(r, a, e);
 }
+// ---------------------------------------------------------------------------------
+// Fast modular inverse (0 -> 0): Bernstein-Yang "safegcd" division steps in batches of 30 on
+// signed 30-bit limbs, ~20 outer iterations of word-sized work instead of the ~380 dependent
+// Montgomery multiplications of the Fermat inverse.  Used where ONE inversion is on the critical
+// path of a whole kernel level (batch-affine MSM levels, final XYZZ -> affine on the host).
+// Input and output in Montgomery form.
+// ---------------------------------------------------------------------------------
+namespace safegcd {
+struct S30 { int32_t v[9]; };
+struct T2x2 { int32_t u, v, q, r; };
+constexpr int32_t M30 = (int32_t)((1u << 30) - 1u);
+
+KZ_HD void from_limbs(S30& r, const uint32_t* l) {
+    // 8 x 32-bit -> 9 x 30-bit
+    for (int i = 0; i < 9; i++) {
+        int bit = 30 * i, w = bit >> 5, b = bit & 31;
+        uint64_t x = l[w];
+        if (w + 1 < 8) x |= (uint64_t)l[w + 1] << 32;
+        r.v[i] = (int32_t)((x >> b) & (uint32_t)M30);
+    }
+}
+KZ_HD void to_limbs(uint32_t* l, const S30& a) {  // a normalised: every limb in [0, 2^30)
+    for (int i = 0; i < 8; i++) l[i] = 0;
+    for (int i = 0; i < 9; i++) {
+        int bit = 30 * i, w = bit >> 5, b = bit & 31;
+        uint64_t x = (uint64_t)(uint32_t)a.v[i] << b;
+        l[w] |= (uint32_t)x;
+        if (w + 1 < 8) l[w + 1] |= (uint32_t)(x >> 32);
+    }
+}
+// 30 division steps on the low bits of f, g.  eta = -delta.  Returns the new eta and the
+// transition matrix t with  2^30 * [f'; g'] = t * [f; g].
+KZ_HD int32_t divsteps_30(int32_t eta, uint32_t f0, uint32_t g0, T2x2& t) {
+    uint32_t u = 1, v = 0, q = 0, r = 1;
+    uint32_t f = f0, g = g0;
+    for (int i = 0; i < 30; i++) {
+        uint32_t c1 = (uint32_t)(eta >> 31);   // all ones if delta > 0
+        uint32_t c2 = (uint32_t)0 - (g & 1u);  // all ones if g odd
+        uint32_t x = (f ^ c1) - c1, y = (u ^ c1) - c1, z = (v ^ c1) - c1;
+        g += x & c2; q += y & c2; r += z & c2;
+        c1 &= c2;
+        eta = (int32_t)(((uint32_t)eta ^ c1) - (c1 + 1u));
+        f += g & c1; u += q & c1; v += r & c1;
+        g >>= 1; u <<= 1; v <<= 1;
+    }
+    t.u = (int32_t)u; t.v = (int32_t)v; t.q = (int32_t)q; t.r = (int32_t)r;
+    return eta;
+}
+// [f; g] <- t * [f; g] / 2^30 (exact)
+KZ_HD void update_fg(S30& f, S30& g, const T2x2& t) {
+    const int32_t u = t.u, v = t.v, q = t.q, r = t.r;  // 32 x 32 -> 64 products
+#define KZ_MW(a, b) ((int64_t)(a) * (int64_t)(b))
+    int64_t cf = KZ_MW(u, f.v[0]) + KZ_MW(v, g.v[0]);
+    int64_t cg = KZ_MW(q, f.v[0]) + KZ_MW(r, g.v[0]);
+    cf >>= 30; cg >>= 30;
+    for (int i = 1; i < 9; i++) {
+        cf += KZ_MW(u, f.v[i]) + KZ_MW(v, g.v[i]);
+        cg += KZ_MW(q, f.v[i]) + KZ_MW(r, g.v[i]);
+        f.v[i - 1] = (int32_t)cf & M30; cf >>= 30;
+        g.v[i - 1] = (int32_t)cg & M30; cg >>= 30;
+    }
+    f.v[8] = (int32_t)cf;
+    g.v[8] = (int32_t)cg;
+}
+// [d; e] <- t * [d; e] / 2^30 mod m, with d, e kept in (-2m, m)
+KZ_HD void update_de(S30& d, S30& e, const T2x2& t, const S30& m, uint32_t m_inv30) {
+    const int32_t u = t.u, v = t.v, q = t.q, r = t.r;
+    int32_t sd = d.v[8] >> 31, se = e.v[8] >> 31;
+    int32_t md = (t.u & sd) + (t.v & se);
+    int32_t me = (t.q & sd) + (t.r & se);
+    int64_t cd = KZ_MW(u, d.v[0]) + KZ_MW(v, e.v[0]);
+    int64_t ce = KZ_MW(q, d.v[0]) + KZ_MW(r, e.v[0]);
+    md -= (int32_t)((m_inv30 * (uint32_t)cd + (uint32_t)md) & (uint32_t)M30);
+    me -= (int32_t)((m_inv30 * (uint32_t)ce + (uint32_t)me) & (uint32_t)M30);
+    cd += KZ_MW(m.v[0], md);
+    ce += KZ_MW(m.v[0], me);
+    cd >>= 30; ce >>= 30;
+    for (int i = 1; i < 9; i++) {
+        cd += KZ_MW(u, d.v[i]) + KZ_MW(v, e.v[i]) + KZ_MW(m.v[i], md);
+        ce += KZ_MW(q, d.v[i]) + KZ_MW(r, e.v[i]) + KZ_MW(m.v[i], me);
+        d.v[i - 1] = (int32_t)cd & M30; cd >>= 30;
+        e.v[i - 1] = (int32_t)ce & M30; ce >>= 30;
+    }
+    d.v[8] = (int32_t)cd;
+    e.v[8] = (int32_t)ce;
+#undef KZ_MW
+}
+// r in (-2m, m), optionally negated, -> [0, m)
+KZ_HD void normalize(S30& r, int32_t sign, const S30& m) {
+    int32_t cond_add = r.v[8] >> 31;
+    for (int i = 0; i < 9; i++) r.v[i] += m.v[i] & cond_add;
+    int32_t cond_neg = sign >> 31;
+    for (int i = 0; i < 9; i++) r.v[i] = (r.v[i] ^ cond_neg) - cond_neg;
+    for (int i = 0; i < 8; i++) { r.v[i + 1] += r.v[i] >> 30; r.v[i] &= M30; }
+    cond_add = r.v[8] >> 31;
+    for (int i = 0; i < 9; i++) r.v[i] += m.v[i] & cond_add;
+    for (int i = 0; i < 8; i++) { r.v[i + 1] += r.v[i] >> 30; r.v[i] &= M30; }
+}
+}  // namespace safegcd
+
+template <int F> KZ_HD void fe_inv_fast(Fe<F>& r, const Fe<F>& a) {
+    using namespace safegcd;
+    if (fe_is_zero(a)) { fe_zero(r); return; }
+    uint32_t ml[8]; FeConst<F>::mod(ml);
+    S30 m, f, g, d, e;
+    from_limbs(m, ml);
+    from_limbs(g, a.l);
+    f = m;
+    for (int i = 0; i < 9; i++) { d.v[i] = 0; e.v[i] = 0; }
+    e.v[0] = 1;
+    const uint32_t m_inv30 = ((uint32_t)0 - (uint32_t)FeConst<F>::NP0) & (uint32_t)M30;  // m^-1 mod 2^30
+    int32_t eta = -1;
+    for (int it = 0; it < 25; it++) {  // 25 * 30 = 750 >= 741 division steps suffice for 256-bit inputs
+        T2x2 t;
+        eta = divsteps_30(eta, (uint32_t)f.v[0], (uint32_t)g.v[0], t);
+        update_de(d, e, t, m, m_inv30);
+        update_fg(f, g, t);
+        int32_t nz = 0;
+        for (int i = 0; i < 9; i++) nz |= g.v[i];
+        if (nz == 0) break;
+    }
+    // f = +-1, d = +-(a^-1) (a in Montgomery form: d = (a R)^-1)
+    normalize(d, f.v[8], m);
+    Fe<F> y, r3;
+    to_limbs(y.l, d);
+    FeConst<F>::r3(r3.l);
+    fe_mul(r, y, r3);  // (a R)^-1 * R^3 / R = a^-1 R
+}
+
 // canonical(a) > (p-1)/2 ?  (reference primitives/src/helpers.rs:151-173)
 template <int F> KZ_HD bool fe_lexicographically_largest(const Fe<F>& a_mont) {
     Fe<F> c; fe_from_mont(c, a_mont);

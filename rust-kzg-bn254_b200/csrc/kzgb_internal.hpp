@@ -28,6 +28,11 @@ struct MsmPlan {
     uint32_t acc_threads;   // threads of the accumulate kernel (fixed-size chunks)
     uint32_t chunk;         // sorted entries per accumulate thread
     uint32_t slice;         // buckets per bucket-reduce thread
+    // batch-affine front end (msm.cu): ba_levels pairwise affine levels over the padded sorted list,
+    // then the XYZZ accumulation of what is left (1 / 2^ba_levels of the entries)
+    int ba_levels;          // 0 = XYZZ accumulation straight from the table
+    uint32_t ba_k[4];       // pairs per thread at each level
+    uint32_t max_entries;   // upper bound of the (padded) sorted list: n*W + nbuckets * (2^ba_levels - 1)
 };
 
 struct MsmWorkspace {
@@ -40,11 +45,20 @@ struct MsmWorkspace {
     XYZZ* slice_sums;   // nbuckets / slice
     XYZZ* set_sums;     // sets (device), copied to host by the caller
     uint32_t* tile_tot; // scan tile totals (<= 1024)
+    Affine* ba_pts[2];  // level outputs, ping-pong: max_entries/2 and max_entries/4 points
+    Fq* ba_prefix;      // max_entries/2
+    Fq* ba_others;      // one per thread of the widest level
+    Fq* ba_blk_tot;     // one per block of the widest level
+    Fq* ba_blk_inv;
 };
 
 size_t msm_workspace_bytes(const MsmPlan& p);
 void msm_workspace_carve(const MsmPlan& p, void* base, MsmWorkspace* ws);
 MsmPlan msm_make_plan(uint32_t n, int c, bool fixed_base, uint32_t table_stride, uint32_t base_offset);
+// Batch-affine tuning: levels (default 0 = off), minimum average bucket occupancy for it to be
+// used (default 64), pairs per thread at level 0 (0 = default: one wave per level).  Negative values keep
+// the current setting.
+void msm_set_tuning(int ba_levels, int ba_min_avg_bucket, int ba_k0);
 
 // scalars: n Fr (Montgomery unless scalars_canonical).  Result: ws.set_sums[0..sets) on the device.
 // The optional events bracket the bucket-accumulation kernel (roofline timing).

@@ -63,8 +63,12 @@ static constexpr uint32_t SCAN_PER_THREAD = 32;
 static constexpr uint32_t SCAN_THREADS = 1024;
 static constexpr uint32_t SCAN_TILE = SCAN_PER_THREAD * SCAN_THREADS;
 
+// pad_mask = 2^L - 1 rounds every bucket's count up to a multiple of 2^L (batch-affine levels pair
+// entries (2p, 2p+1) globally, so every bucket must start on a multiple of 2^L; the padding slots hold
+// REF_IDENT).
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(uint32_t* __restrict__ hist, uint32_t* __restrict__ cursor,
-                                                             uint32_t nb, uint32_t* __restrict__ block_tot, bool single) {
+                                                             uint32_t nb, uint32_t* __restrict__ block_tot, bool single,
+                                                             uint32_t pad_mask) {
     __shared__ uint32_t warp_tot[32];
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t base = blockIdx.x * SCAN_TILE + tid * SCAN_PER_THREAD;
@@ -77,6 +81,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(uint32_t* __restric
 #pragma unroll
         for (int k = 0; k < (int)SCAN_PER_THREAD; k++) v[k] = (base + k < nb) ? hist[base + k] : 0u;
     }
+#pragma unroll
+    for (int k = 0; k < (int)SCAN_PER_THREAD; k++) v[k] = (v[k] + pad_mask) & ~pad_mask;
     uint32_t sum = 0;
 #pragma unroll
     for (int k = 0; k < (int)SCAN_PER_THREAD; k++) { uint32_t t = v[k]; v[k] = sum; sum += t; }
@@ -162,8 +168,11 @@ __global__ void __launch_bounds__(256) k_scatter(const Fr* __restrict__ canon, M
     }
 }
 
+static constexpr uint32_t REF_IDENT = 0xffffffffu;  // padding slot of the sorted list: the identity
+
 __device__ __forceinline__ Affine load_point(const Affine* __restrict__ table, uint32_t ref) {
-    Affine q = aff_load_ro(&table[ref & 0x7fffffffu]);
+    if (ref == REF_IDENT) { Affine z; aff_set_inf(z); return z; }
+    Affine q = aff_gather_ro(&table[ref & 0x7fffffffu]);
     if (ref & 0x80000000u) fe_neg(q.y, q.y);  // identity (0,0) stays (0,0)
     return q;
 }
@@ -203,40 +212,47 @@ __device__ __forceinline__ void xyzz_madd_call(XYZZ& acc, const Affine& q) {
     acc.zzz = fq_mul_call(acc.zzz, PPP);
 }
 
-template <int MINB, bool CALL, bool PREFETCH>
+// Source of the entries: SRC_REFS = sorted refs into the table (gather), SRC_POINTS = the affine
+// points left by the batch-affine levels (entry `pos` is points[pos]; bucket offsets are the level-0
+// offsets >> shift).
+template <int MINB, bool CALL, bool PREFETCH, bool DIRECT>
 __global__ void __launch_bounds__(128, MINB) k_accumulate_t(const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ offsets,
-                                                              const Affine* __restrict__ table, MsmPlan p,
+                                                              const Affine* __restrict__ table, uint32_t nb, uint32_t acc_threads,
+                                                              uint32_t chunk, int shift,
                                                               XYZZ* __restrict__ buckets, XYZZ* __restrict__ partial) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= p.acc_threads) return;
-    const uint32_t nb = p.nbuckets;
-    const uint32_t M = offsets[nb];
-    uint64_t start64 = (uint64_t)t * p.chunk;
+    if (t >= acc_threads) return;
+    const uint32_t M = offsets[nb] >> shift;
+    uint64_t start64 = (uint64_t)t * chunk;
     if (start64 >= M) return;  // k_bucket_fix only reads slots of chunks that hold entries
     uint32_t start = (uint32_t)start64;
-    uint32_t end = (uint32_t)min((uint64_t)M, start64 + p.chunk);
+    uint32_t end = (uint32_t)min((uint64_t)M, start64 + chunk);
     // largest b with offsets[b] <= start
     uint32_t lo = 0, hi = nb;  // invariant: offsets[lo] <= start < offsets[hi] (offsets[nb] = M > start)
     while (hi - lo > 1) {
         uint32_t mid = (lo + hi) >> 1;
-        if (offsets[mid] <= start) lo = mid; else hi = mid;
+        if ((offsets[mid] >> shift) <= start) lo = mid; else hi = mid;
     }
     uint32_t b = lo;
-    uint32_t run_begin = offsets[b], next = offsets[b + 1];
+    uint32_t run_begin = offsets[b] >> shift, next = offsets[b + 1] >> shift;
     XYZZ acc; xyzz_set_inf(acc);
     Affine q;
-    if (PREFETCH) q = load_point(table, sorted[start]);
+    auto fetch = [&](uint32_t pos) -> Affine {
+        if (DIRECT) return aff_load_ro(&table[pos]);
+        return load_point(table, sorted[pos]);
+    };
+    if (PREFETCH) q = fetch(start);
     for (uint32_t pos = start; pos < end; pos++) {
         Affine qn;
-        if (PREFETCH) { if (pos + 1 < end) qn = load_point(table, sorted[pos + 1]); }  // next point in flight during this addition
-        else q = load_point(table, sorted[pos]);
+        if (PREFETCH) { if (pos + 1 < end) qn = fetch(pos + 1); }  // next point in flight during this addition
+        else q = fetch(pos);
         if (pos >= next) {
             bool complete = (run_begin >= start);  // its end (`next`) is <= pos < end
             if (complete) xyzz_store(&buckets[b], acc);
             else xyzz_store(&partial[2 * t], acc);
             xyzz_set_inf(acc);
-            do { b++; } while (offsets[b + 1] <= pos);
-            run_begin = offsets[b]; next = offsets[b + 1];
+            do { b++; } while ((offsets[b + 1] >> shift) <= pos);
+            run_begin = offsets[b] >> shift; next = offsets[b + 1] >> shift;
         }
         if (CALL) xyzz_madd_call(acc, q); else xyzz_madd(acc, q);
         if (PREFETCH) { if (pos + 1 < end) q = qn; }
@@ -249,25 +265,278 @@ __global__ void __launch_bounds__(128, MINB) k_accumulate_t(const uint32_t* __re
     }
 }
 
-__global__ void __launch_bounds__(128) k_bucket_fix(const uint32_t* __restrict__ offsets, MsmPlan p,
+__global__ void __launch_bounds__(128) k_bucket_fix(const uint32_t* __restrict__ offsets, uint32_t nbuckets, uint32_t chunk, int shift,
                                                      XYZZ* __restrict__ buckets, const XYZZ* __restrict__ partial) {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= p.nbuckets) return;
-    uint32_t s = offsets[b], e = offsets[b + 1];
+    if (b >= nbuckets) return;
+    uint32_t s = offsets[b] >> shift, e = offsets[b + 1] >> shift;
     if (s == e) {
         XYZZ inf; xyzz_set_inf(inf);
         xyzz_store(&buckets[b], inf);
         return;
     }
-    uint32_t t_lo = s / p.chunk, t_hi = (e - 1) / p.chunk;
+    uint32_t t_lo = s / chunk, t_hi = (e - 1) / chunk;
     if (t_lo == t_hi) return;  // written directly by k_accumulate
     XYZZ acc; xyzz_set_inf(acc);
     for (uint32_t t = t_lo; t <= t_hi; t++) {
-        uint32_t slot = ((uint64_t)s <= (uint64_t)t * p.chunk) ? 0u : 1u;
+        uint32_t slot = ((uint64_t)s <= (uint64_t)t * chunk) ? 0u : 1u;
         XYZZ v = xyzz_load(&partial[2 * t + slot]);
         xyzz_add(acc, v);
     }
     xyzz_store(&buckets[b], acc);
+}
+
+// ---------------------------------------------------------------------------------
+// Batch-affine levels.  The padded sorted list is reduced pairwise, bucket-agnostically:
+//   level l:  out[p] = in[2p] + in[2p+1]   for p < M >> (l+1)
+// (every bucket starts on a multiple of 2^L, so a pair never straddles two buckets; padding is the
+// identity).  Affine + affine needs 1/(x2 - x1): Montgomery's trick over the whole level --
+//   k_ba_prefix  per thread: running products e_j of its K denominators (stored), then the product
+//                of all OTHER threads' totals in the block (warp shuffles) and the block total
+//   k_ba_invert  one block: inverse of every block total (one Fermat inversion per level)
+//   k_ba_apply   per thread: u = 1/(own total); walks its pairs backwards: 1/d_j = e_{j-1} * u,
+//                u *= d_j; lambda, x3, y3 (3 more multiplications)
+// = 6 Fq-mul per addition + ~15/K for the block scan, against 10 for XYZZ += affine.
+// Exceptional pairs are exact: identity operands pass through (d = 1), P + P uses d = 2y and the
+// tangent slope, P + (-P) gives the identity (d = 1).
+// ---------------------------------------------------------------------------------
+static constexpr int BA_THREADS = 128;
+enum { BA_ADD = 0, BA_DBL = 1, BA_PASS_A = 2, BA_PASS_B = 3, BA_INF = 4 };
+
+struct BaArgs {
+    const uint32_t* refs;    // level 0: padded sorted refs; deeper levels: nullptr
+    const Affine* in;        // level 0: table; deeper: points of the previous level
+    Affine* out;
+    Fq* prefix;              // one per pair
+    Fq* others;              // one per thread: product of the other threads' totals in its block
+    Fq* blk_tot;             // one per block
+    Fq* blk_inv;
+    const uint32_t* m_ptr;   // padded entry count at level 0 (device)
+    int level;
+    int K;                   // pairs per thread
+};
+
+__device__ __forceinline__ int ba_classify(const Affine& a, const Affine& b, Fq& d) {
+    bool ai = aff_is_inf(a), bi = aff_is_inf(b);
+    if (ai || bi) { fe_one(d); return ai ? (bi ? BA_INF : BA_PASS_B) : BA_PASS_A; }
+    fe_sub(d, b.x, a.x);
+    if (!fe_is_zero(d)) return BA_ADD;
+    if (fe_eq(a.y, b.y) && !fe_is_zero(a.y)) { fe_dbl(d, a.y); return BA_DBL; }
+    fe_one(d);
+    return BA_INF;
+}
+
+template <bool L0>
+__device__ __forceinline__ void ba_load_pair(const BaArgs& g, uint32_t p, Affine& a, Affine& b) {
+    if (L0) {
+        uint2 r = *reinterpret_cast<const uint2*>(g.refs + 2 * (size_t)p);
+        a = load_point(g.in, r.x);
+        b = load_point(g.in, r.y);
+    } else {
+        a = aff_load_ro(&g.in[2 * (size_t)p]);
+        b = aff_load_ro(&g.in[2 * (size_t)p + 1]);
+    }
+}
+
+// denominator only: the y coordinates are fetched just for the exceptional pairs
+template <bool L0>
+__device__ __forceinline__ int ba_pair_denominator(const BaArgs& g, uint32_t p, Fq& d) {
+    const Fq *pax, *pbx;
+    bool a_id = false, b_id = false;
+    if (L0) {
+        uint2 r = *reinterpret_cast<const uint2*>(g.refs + 2 * (size_t)p);
+        a_id = r.x == REF_IDENT; b_id = r.y == REF_IDENT;
+        pax = &g.in[r.x & 0x7fffffffu].x; pbx = &g.in[r.y & 0x7fffffffu].x;
+    } else {
+        pax = &g.in[2 * (size_t)p].x; pbx = &g.in[2 * (size_t)p + 1].x;
+    }
+    if (!a_id && !b_id) {
+        Fq ax = fe_load_ro(pax), bx = fe_load_ro(pbx);
+        fe_sub(d, bx, ax);
+        if (!fe_is_zero(ax) && !fe_is_zero(bx) && !fe_is_zero(d)) return BA_ADD;
+    }
+    Affine a, b;
+    ba_load_pair<L0>(g, p, a, b);
+    return ba_classify(a, b, d);
+}
+
+__device__ __forceinline__ Fq fq_shfl_up(const Fq& v, int off) {
+    Fq r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = __shfl_up_sync(0xffffffffu, v.l[i], off);
+    return r;
+}
+__device__ __forceinline__ Fq fq_shfl_down(const Fq& v, int off) {
+    Fq r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = __shfl_down_sync(0xffffffffu, v.l[i], off);
+    return r;
+}
+
+// For every thread of a block of NW warps: the product of the totals of all OTHER threads; returns
+// the block total too (valid in every thread).  smem: NW Fq.
+template <int NW>
+__device__ __forceinline__ void block_product_of_others(const Fq& T, Fq* smem, Fq& others, Fq& total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    Fq pre = T, suf = T;
+#pragma unroll 1
+    for (int off = 1; off < 32; off <<= 1) {
+        Fq o = fq_shfl_up(pre, off);
+        if (lane >= off) fe_mul(pre, pre, o);
+    }
+#pragma unroll 1
+    for (int off = 1; off < 32; off <<= 1) {
+        Fq o = fq_shfl_down(suf, off);
+        if (lane + off < 32) fe_mul(suf, suf, o);
+    }
+    if (lane == 31) smem[wid] = pre;  // warp total
+    Fq pe = fq_shfl_up(pre, 1), se = fq_shfl_down(suf, 1);
+    Fq one; fe_one(one);
+    if (lane == 0) pe = one;
+    if (lane == 31) se = one;
+    fe_mul(others, pe, se);
+    __syncthreads();
+    Fq ow;  // product of the other warps' totals
+    if (NW <= 4) {
+        ow = one;
+#pragma unroll 1
+        for (int v = 0; v < NW; v++) {
+            if (v != wid) { Fq w = smem[v]; fe_mul(ow, ow, w); }
+        }
+        fe_mul(total, ow, smem[wid]);
+    } else {  // NW == 32: second-level shuffle scan over the warp totals (every warp does it redundantly)
+        Fq wt = smem[lane < NW ? lane : 0];
+        if (lane >= NW) wt = one;
+        Fq wp = wt, ws = wt;
+#pragma unroll 1
+        for (int off = 1; off < 32; off <<= 1) {
+            Fq o = fq_shfl_up(wp, off);
+            if (lane >= off) fe_mul(wp, wp, o);
+        }
+#pragma unroll 1
+        for (int off = 1; off < 32; off <<= 1) {
+            Fq o = fq_shfl_down(ws, off);
+            if (lane + off < 32) fe_mul(ws, ws, o);
+        }
+        Fq wpe = fq_shfl_up(wp, 1), wse = fq_shfl_down(ws, 1);
+        if (lane == 0) wpe = one;
+        if (lane == 31) wse = one;
+        Fq mine; fe_mul(mine, wpe, wse);  // lane v: product of the totals of all warps but v
+        // broadcast lane `wid`'s value and the grand total (lane 31's inclusive prefix)
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            ow.l[i] = __shfl_sync(0xffffffffu, mine.l[i], wid);
+            total.l[i] = __shfl_sync(0xffffffffu, wp.l[i], 31);
+        }
+    }
+    fe_mul(others, others, ow);
+    __syncthreads();
+}
+
+template <bool L0>
+__global__ void __launch_bounds__(BA_THREADS) k_ba_prefix(BaArgs g) {
+    __shared__ Fq sm[BA_THREADS / 32];
+    const uint32_t P = (*g.m_ptr) >> (g.level + 1);
+    const uint32_t base = blockIdx.x * (uint32_t)(BA_THREADS * g.K);
+    if (base >= P) return;
+    Fq e; fe_one(e);
+    for (int j = 0; j < g.K; j++) {
+        uint32_t p = base + (uint32_t)j * BA_THREADS + threadIdx.x;
+        if (p < P) {
+            Fq d;
+            int cls = ba_pair_denominator<L0>(g, p, d);
+            if (cls <= BA_DBL) fe_mul(e, e, d);
+            fe_store(&g.prefix[p], e);
+        }
+    }
+    Fq others, total;
+    block_product_of_others<BA_THREADS / 32>(e, sm, others, total);
+    fe_store(&g.others[blockIdx.x * BA_THREADS + threadIdx.x], others);
+    if (threadIdx.x == 0) fe_store(&g.blk_tot[blockIdx.x], total);
+}
+
+// one block of 1024 threads: blk_inv[i] = 1 / blk_tot[i] for the active blocks of the level
+static constexpr int BA_INV_THREADS = 1024;
+static constexpr int BA_INV_MAXQ = 8;  // up to 8192 blocks per level
+__global__ void __launch_bounds__(BA_INV_THREADS) k_ba_invert(BaArgs g) {
+    __shared__ Fq sm[BA_INV_THREADS / 32];
+    __shared__ Fq sm_inv;
+    const uint32_t P = (*g.m_ptr) >> (g.level + 1);
+    const uint32_t per_block = (uint32_t)(BA_THREADS * g.K);
+    const uint32_t nblk = (P + per_block - 1) / per_block;
+    const uint32_t q = (nblk + BA_INV_THREADS - 1) / BA_INV_THREADS;  // <= BA_INV_MAXQ (host guarantees)
+    const uint32_t first = threadIdx.x * q;
+    Fq v[BA_INV_MAXQ];
+    Fq T; fe_one(T);
+    for (uint32_t k = 0; k < q; k++) {
+        if (first + k < nblk) { v[k] = fe_load(&g.blk_tot[first + k]); fe_mul(T, T, v[k]); }
+        else fe_one(v[k]);
+    }
+    Fq others, total;
+    block_product_of_others<BA_INV_THREADS / 32>(T, sm, others, total);
+    if (threadIdx.x == 0) { Fq inv; fe_inv_fast(inv, total); sm_inv = inv; }
+    __syncthreads();
+    Fq u;  // 1 / T
+    fe_mul(u, others, sm_inv);
+    // local batch inversion, backwards: 1/v_k = (v_0..v_{k-1}) * u_k, u_{k-1} = u_k * v_k
+    for (int k = (int)q - 1; k >= 0; k--) {
+        Fq pre; fe_one(pre);
+        for (int i = 0; i < k; i++) fe_mul(pre, pre, v[i]);
+        Fq inv; fe_mul(inv, pre, u);
+        if (first + k < nblk) fe_store(&g.blk_inv[first + k], inv);
+        fe_mul(u, u, v[k]);
+    }
+}
+
+template <bool L0>
+__global__ void __launch_bounds__(BA_THREADS) k_ba_apply(BaArgs g) {
+    const uint32_t P = (*g.m_ptr) >> (g.level + 1);
+    const uint32_t base = blockIdx.x * (uint32_t)(BA_THREADS * g.K);
+    if (base >= P) return;
+    Fq u;
+    {
+        Fq o = fe_load(&g.others[blockIdx.x * BA_THREADS + threadIdx.x]);
+        Fq bi = fe_load(&g.blk_inv[blockIdx.x]);
+        fe_mul(u, o, bi);
+    }
+    for (int j = g.K - 1; j >= 0; j--) {
+        uint32_t p = base + (uint32_t)j * BA_THREADS + threadIdx.x;
+        if (p >= P) continue;
+        Affine a, b, r;
+        ba_load_pair<L0>(g, p, a, b);
+        Fq d;
+        int cls = ba_classify(a, b, d);
+        if (cls >= BA_PASS_A) {
+            if (cls == BA_PASS_A) r = a;
+            else if (cls == BA_PASS_B) r = b;
+            else aff_set_inf(r);
+            aff_store(&g.out[p], r);
+            continue;
+        }
+        Fq inv;
+        if (j > 0) {
+            Fq e = fe_load(&g.prefix[p - BA_THREADS]);  // e_{j-1}
+            fe_mul(inv, e, u);
+            fe_mul(u, u, d);
+        } else {
+            inv = u;
+        }
+        Fq lam, t;
+        if (cls == BA_ADD) {
+            fe_sub(t, b.y, a.y);
+            fe_mul(lam, t, inv);
+        } else {  // tangent: 3 x^2 / (2 y)
+            fe_sqr(t, a.x);
+            fe_dbl(lam, t); fe_add(t, lam, t);
+            fe_mul(lam, t, inv);
+        }
+        fe_sqr(r.x, lam);
+        fe_sub(r.x, r.x, a.x); fe_sub(r.x, r.x, b.x);
+        fe_sub(t, a.x, r.x);
+        fe_mul(t, lam, t);
+        fe_sub(r.y, t, a.y);
+        aff_store(&g.out[p], r);
+    }
 }
 
 // slice j covers buckets [j*slice, (j+1)*slice) of one set; bucket index k (in set) has weight k+1
@@ -323,7 +592,35 @@ __global__ void k_tree_reduce(const XYZZ* __restrict__ in, XYZZ* __restrict__ ou
 }
 
 // ---------------------------------------------------------------------------------
+static int g_ba_levels = 0, g_ba_min_avg = 64, g_ba_k0 = 0;  // k0 = 0: pairs per thread chosen so each level is one wave
+static bool g_tuning_env_read = false;
+void msm_set_tuning(int ba_levels, int ba_min_avg_bucket, int ba_k0) {
+    g_tuning_env_read = true;
+    if (ba_levels >= 0) g_ba_levels = ba_levels > 4 ? 4 : ba_levels;
+    if (ba_min_avg_bucket >= 0) g_ba_min_avg = ba_min_avg_bucket;
+    if (ba_k0 >= 0) g_ba_k0 = ba_k0;
+}
+// blocks of k_ba_apply resident on the whole GPU (one wave)
+static uint32_t ba_wave_blocks() {
+    static uint32_t cached = 0;
+    if (!cached) {
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ba_apply<true>, BA_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 6;
+        cached = (uint32_t)per_sm * SM_COUNT;
+    }
+    return cached;
+}
+static void tuning_from_env() {
+    if (g_tuning_env_read) return;
+    g_tuning_env_read = true;
+    const char* e;
+    if ((e = getenv("KZGB_BA_LEVELS"))) g_ba_levels = atoi(e) > 4 ? 4 : (atoi(e) < 0 ? 0 : atoi(e));
+    if ((e = getenv("KZGB_BA_MIN_AVG"))) g_ba_min_avg = atoi(e);
+    if ((e = getenv("KZGB_BA_K0")) && atoi(e) >= 0) g_ba_k0 = atoi(e);
+}
+
 MsmPlan msm_make_plan(uint32_t n, int c, bool fixed_base, uint32_t table_stride, uint32_t base_offset) {
+    tuning_from_env();
     MsmPlan p;
     p.c = c;
     p.W = (255 + c - 1) / c;
@@ -333,11 +630,30 @@ MsmPlan msm_make_plan(uint32_t n, int c, bool fixed_base, uint32_t table_stride,
     p.table_stride = fixed_base ? table_stride : 0;
     p.base_offset = fixed_base ? base_offset : 0;
     uint64_t entries = (uint64_t)n * p.W;
+    // batch-affine levels pay off when buckets are well filled (padding <= 2^L - 1 slots per bucket)
+    p.ba_levels = 0;
+    if (g_ba_levels > 0 && entries >= (uint64_t)g_ba_min_avg * p.nbuckets && entries <= ((uint64_t)1 << 27)) p.ba_levels = g_ba_levels;
+    uint64_t padded = entries + (uint64_t)p.nbuckets * ((1u << p.ba_levels) - 1u);
+    p.max_entries = (uint32_t)padded;
+    for (int l = 0; l < 4; l++) {
+        uint64_t pairs = padded >> (l + 1);
+        uint64_t k;
+        if (g_ba_k0 > 0) { k = (uint64_t)g_ba_k0 >> l; if (k < 4) k = 4; }
+        else {  // one full wave of the apply kernel, at least 8 pairs per thread
+            uint64_t slots = (uint64_t)ba_wave_blocks() * BA_THREADS;
+            k = (pairs + slots - 1) / slots;
+            if (k < 8) k = 8;
+        }
+        uint64_t kmin = (pairs + (uint64_t)BA_THREADS * BA_INV_THREADS * BA_INV_MAXQ - 1) / ((uint64_t)BA_THREADS * BA_INV_THREADS * BA_INV_MAXQ);
+        if (k < kmin) k = kmin;
+        p.ba_k[l] = (uint32_t)k;
+    }
+    uint64_t tail = padded >> p.ba_levels;
     uint64_t max_threads = (uint64_t)SM_COUNT * 512;
-    uint64_t want = (entries + 15) / 16;
+    uint64_t want = (tail + 15) / 16;
     if (want < 1) want = 1;
     p.acc_threads = (uint32_t)(want < max_threads ? want : max_threads);
-    p.chunk = (uint32_t)((entries + p.acc_threads - 1) / p.acc_threads);
+    p.chunk = (uint32_t)((tail + p.acc_threads - 1) / p.acc_threads);
     if (p.chunk == 0) p.chunk = 1;
     uint32_t half = 1u << (c - 1);
     p.slice = half >= 1024 ? 4 : (half >= 4 ? 2 : 1);
@@ -346,45 +662,75 @@ MsmPlan msm_make_plan(uint32_t n, int c, bool fixed_base, uint32_t table_stride,
 
 static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
+static uint32_t ba_max_blocks(const MsmPlan& p) {
+    uint32_t mb = 1;
+    for (int l = 0; l < p.ba_levels; l++) {
+        uint64_t pairs = (uint64_t)p.max_entries >> (l + 1);
+        uint64_t per = (uint64_t)BA_THREADS * p.ba_k[l];
+        uint32_t nb = (uint32_t)((pairs + per - 1) / per);
+        if (nb > mb) mb = nb;
+    }
+    return mb;
+}
+
 size_t msm_workspace_bytes(const MsmPlan& p) {
     size_t b = 0;
     b += align_up((size_t)p.n * sizeof(Fr));
     b += align_up(((size_t)p.nbuckets + 1) * 4);
     b += align_up((size_t)p.nbuckets * 4);
-    b += align_up((size_t)p.n * p.W * 4);
+    b += align_up((size_t)p.max_entries * 4);
     b += align_up((size_t)p.nbuckets * sizeof(XYZZ));
     b += align_up((size_t)2 * p.acc_threads * sizeof(XYZZ));
     b += align_up((size_t)(p.nbuckets / p.slice) * sizeof(XYZZ));
     b += align_up((size_t)(p.nbuckets / p.slice) * sizeof(XYZZ));  // tree ping-pong
     b += align_up((size_t)p.sets * sizeof(XYZZ));
     b += align_up(1024 * 4);  // scan tile totals
+    if (p.ba_levels) {
+        uint32_t mb = ba_max_blocks(p);
+        b += align_up((size_t)(p.max_entries / 2 + 1) * sizeof(Affine));
+        b += align_up((size_t)(p.max_entries / 4 + 1) * sizeof(Affine));
+        b += align_up((size_t)(p.max_entries / 2 + 1) * sizeof(Fq));
+        b += align_up((size_t)mb * BA_THREADS * sizeof(Fq));
+        b += 2 * align_up((size_t)mb * sizeof(Fq));
+    }
     return b;
 }
-
-struct TreeScratch { XYZZ* pong; };
 
 void msm_workspace_carve(const MsmPlan& p, void* base, MsmWorkspace* ws) {
     char* c = (char*)base;
     ws->canon = (Fr*)c; c += align_up((size_t)p.n * sizeof(Fr));
     ws->hist = (uint32_t*)c; c += align_up(((size_t)p.nbuckets + 1) * 4);
     ws->cursor = (uint32_t*)c; c += align_up((size_t)p.nbuckets * 4);
-    ws->sorted = (uint32_t*)c; c += align_up((size_t)p.n * p.W * 4);
+    ws->sorted = (uint32_t*)c; c += align_up((size_t)p.max_entries * 4);
     ws->buckets = (XYZZ*)c; c += align_up((size_t)p.nbuckets * sizeof(XYZZ));
     ws->partial = (XYZZ*)c; c += align_up((size_t)2 * p.acc_threads * sizeof(XYZZ));
     ws->slice_sums = (XYZZ*)c; c += 2 * align_up((size_t)(p.nbuckets / p.slice) * sizeof(XYZZ));
     ws->set_sums = (XYZZ*)c; c += align_up((size_t)p.sets * sizeof(XYZZ));
-    ws->tile_tot = (uint32_t*)c;
+    ws->tile_tot = (uint32_t*)c; c += align_up(1024 * 4);
+    ws->ba_pts[0] = ws->ba_pts[1] = nullptr;
+    ws->ba_prefix = ws->ba_others = ws->ba_blk_tot = ws->ba_blk_inv = nullptr;
+    if (p.ba_levels) {
+        uint32_t mb = ba_max_blocks(p);
+        ws->ba_pts[0] = (Affine*)c; c += align_up((size_t)(p.max_entries / 2 + 1) * sizeof(Affine));
+        ws->ba_pts[1] = (Affine*)c; c += align_up((size_t)(p.max_entries / 4 + 1) * sizeof(Affine));
+        ws->ba_prefix = (Fq*)c; c += align_up((size_t)(p.max_entries / 2 + 1) * sizeof(Fq));
+        ws->ba_others = (Fq*)c; c += align_up((size_t)mb * BA_THREADS * sizeof(Fq));
+        ws->ba_blk_tot = (Fq*)c; c += align_up((size_t)mb * sizeof(Fq));
+        ws->ba_blk_inv = (Fq*)c;
+    }
 }
 
 void msm_launch(const MsmPlan& p, const MsmWorkspace& ws, const Fr* scalars, bool scalars_canonical,
                 const Affine* table, cudaStream_t st, cudaEvent_t ev_acc_begin, cudaEvent_t ev_acc_end) {
+    const int L = p.ba_levels;
     cudaMemsetAsync(ws.hist, 0, ((size_t)p.nbuckets + 1) * 4, st);
+    if (L) cudaMemsetAsync(ws.sorted, 0xff, (size_t)p.max_entries * 4, st);  // padding slots = REF_IDENT
     uint32_t gb = (p.n + 255) / 256;
     if (p.n) { k_digits_hist<<<gb, 256, 0, st>>>(scalars, scalars_canonical, p, ws.canon, ws.hist); g_launch_count += 2; }
     g_launch_count += 4;  // scan, accumulate, bucket_fix, reduce_slices
     {
         uint32_t ntiles = (p.nbuckets + SCAN_TILE - 1) / SCAN_TILE;
-        k_scan_tiles<<<ntiles, SCAN_THREADS, 0, st>>>(ws.hist, ws.cursor, p.nbuckets, ws.tile_tot, ntiles == 1);
+        k_scan_tiles<<<ntiles, SCAN_THREADS, 0, st>>>(ws.hist, ws.cursor, p.nbuckets, ws.tile_tot, ntiles == 1, (1u << L) - 1u);
         if (ntiles > 1) {
             k_scan_tile_totals<<<1, SCAN_THREADS, 0, st>>>(ws.tile_tot, ntiles, ws.hist, p.nbuckets);
             k_scan_add<<<(p.nbuckets + 255) / 256, 256, 0, st>>>(ws.hist, ws.cursor, p.nbuckets, ws.tile_tot);
@@ -393,27 +739,52 @@ void msm_launch(const MsmPlan& p, const MsmWorkspace& ws, const Fr* scalars, boo
     }
     if (p.n) k_scatter<<<gb, 256, 0, st>>>(ws.canon, p, ws.cursor, ws.sorted);
     if (ev_acc_begin) cudaEventRecord(ev_acc_begin, st);
+    const Affine* tail_src = table;
+    for (int l = 0; l < L; l++) {
+        BaArgs g;
+        g.refs = l == 0 ? ws.sorted : nullptr;
+        g.in = l == 0 ? table : ws.ba_pts[(l - 1) & 1];
+        g.out = ws.ba_pts[l & 1];
+        g.prefix = ws.ba_prefix; g.others = ws.ba_others; g.blk_tot = ws.ba_blk_tot; g.blk_inv = ws.ba_blk_inv;
+        g.m_ptr = ws.hist + p.nbuckets;
+        g.level = l;
+        g.K = (int)p.ba_k[l];
+        uint64_t pairs = (uint64_t)p.max_entries >> (l + 1);
+        uint64_t per = (uint64_t)BA_THREADS * p.ba_k[l];
+        uint32_t nblk = (uint32_t)((pairs + per - 1) / per);
+        if (nblk == 0) nblk = 1;
+        if (l == 0) {
+            k_ba_prefix<true><<<nblk, BA_THREADS, 0, st>>>(g);
+            k_ba_invert<<<1, BA_INV_THREADS, 0, st>>>(g);
+            k_ba_apply<true><<<nblk, BA_THREADS, 0, st>>>(g);
+        } else {
+            k_ba_prefix<false><<<nblk, BA_THREADS, 0, st>>>(g);
+            k_ba_invert<<<1, BA_INV_THREADS, 0, st>>>(g);
+            k_ba_apply<false><<<nblk, BA_THREADS, 0, st>>>(g);
+        }
+        g_launch_count += 3;
+        tail_src = g.out;
+    }
     {
         static int variant = -1;
         if (variant < 0) { const char* e = getenv("KZGB_ACC_VARIANT"); variant = e ? atoi(e) : 0; }
         dim3 g((p.acc_threads + 127) / 128);
-#define KZ_ACC(MB, CALL, PF) k_accumulate_t<MB, CALL, PF><<<g, 128, 0, st>>>(ws.sorted, ws.hist, table, p, ws.buckets, ws.partial)
-        switch (variant) {
-            case 1: KZ_ACC(3, false, true); break;
-            case 8: KZ_ACC(4, false, false); break;
-            case 9: KZ_ACC(5, false, true); break;
-            case 2: KZ_ACC(3, true, true); break;
-            case 3: KZ_ACC(4, true, true); break;
-            case 4: KZ_ACC(5, true, true); break;
-            case 5: KZ_ACC(5, true, false); break;
-            case 6: KZ_ACC(6, true, false); break;
-            case 7: KZ_ACC(4, true, false); break;
-            default: KZ_ACC(4, false, false); break;  // best of the sweep in profiles/r01_accumulate_variants.txt
+#define KZ_ACC(MB, CALL, PF, DIRECT) \
+    k_accumulate_t<MB, CALL, PF, DIRECT><<<g, 128, 0, st>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, L, ws.buckets, ws.partial)
+        if (L) {
+            KZ_ACC(4, false, false, true);
+        } else {
+            switch (variant) {  // sweep in profiles/r01_accumulate_variants.txt
+                case 1: KZ_ACC(3, false, true, false); break;
+                case 3: KZ_ACC(4, true, true, false); break;
+                case 9: KZ_ACC(5, false, true, false); break;
+                default: KZ_ACC(4, false, false, false); break;
+            }
         }
 #undef KZ_ACC
     }
     if (ev_acc_end) cudaEventRecord(ev_acc_end, st);
-    k_bucket_fix<<<(p.nbuckets + 127) / 128, 128, 0, st>>>(ws.hist, p, ws.buckets, ws.partial);
+    k_bucket_fix<<<(p.nbuckets + 127) / 128, 128, 0, st>>>(ws.hist, p.nbuckets, p.chunk, L, ws.buckets, ws.partial);
     uint32_t nslices = p.nbuckets / p.slice;
     k_reduce_slices<<<(nslices + 127) / 128, 128, 0, st>>>(ws.buckets, p, ws.slice_sums);
     // tree-reduce each set's slice results down to one point

@@ -12,6 +12,8 @@ void t_fr_add(uint32_t* r, const uint32_t* a, const uint32_t* b) { fe_add(*(Fr*)
 void t_fr_sub(uint32_t* r, const uint32_t* a, const uint32_t* b) { fe_sub(*(Fr*)r, *(const Fr*)a, *(const Fr*)b); }
 void t_fq_inv(uint32_t* r, const uint32_t* a) { fe_inv(*(Fq*)r, *(const Fq*)a); }
 void t_fr_inv(uint32_t* r, const uint32_t* a) { fe_inv(*(Fr*)r, *(const Fr*)a); }
+void t_fq_inv_fast(uint32_t* r, const uint32_t* a) { fe_inv_fast(*(Fq*)r, *(const Fq*)a); }
+void t_fr_inv_fast(uint32_t* r, const uint32_t* a) { fe_inv_fast(*(Fr*)r, *(const Fr*)a); }
 void t_fq_to_mont(uint32_t* r, const uint32_t* a) { fe_to_mont(*(Fq*)r, *(const Fq*)a); }
 void t_fr_to_mont(uint32_t* r, const uint32_t* a) { fe_to_mont(*(Fr*)r, *(const Fr*)a); }
 void t_fq_from_mont(uint32_t* r, const uint32_t* a) { fe_from_mont(*(Fq*)r, *(const Fq*)a); }

@@ -297,3 +297,38 @@ def test_verify_batch_rlc(pkg, ref_srs, ref_srs_points):
     assert e.value.variant == "NotOnCurveError"
     with pytest.raises(pkg.KzgError):
         pkg.verify_blob_kzg_proof_batch_rlc(blobs, cs[:2], ps, ref_srs.engine)
+
+
+@pytest.mark.parametrize("levels,k0", [(1, 8), (2, 4), (3, 32), (4, 16), (3, 0)])
+def test_batch_affine_levels_exact(pkg, eng, ref_srs, ref_srs_points, levels, k0):
+    """The batch-affine bucket accumulation (pairwise affine additions sharing one inversion per
+    level) forced on at small sizes: results must equal the oracle for random inputs and for every
+    exceptional pair -- identity bases and padding slots (pass-through), duplicate bases with equal
+    digits (P + P -> tangent), P and -P (-> identity), all-equal scalars (one hot bucket), zeros."""
+    rnd = random.Random(100 + levels)
+    try:
+        pkg.lib.kzgb_msm_tuning(levels, 0, k0)
+        P1, P2, P3 = ref_srs_points[1], ref_srs_points[2], ref_srs_points[3]
+        # variable-base: duplicates / negations / identity with equal scalars land in the same buckets
+        pts = [P1, P1, P2, o.g1_neg(P2), None, P1, P2, P2, P3, P3, P3, P3, None, o.g1_neg(P1), P1, P1]
+        sc = [5, 5, 77, 77, 123456, 0, o.R - 1, 1, 9, 9, 9, 9, 3, 5, 5, 5]
+        assert pkg.g1_lincomb(pts, sc, eng) == o.msm(pts, sc)
+        same = [ref_srs_points[7]] * 100
+        big = [rnd.randrange(o.R) for _ in range(100)]
+        assert pkg.g1_lincomb(same, big, eng) == o.g1_mul(ref_srs_points[7], sum(big) % o.R)
+        assert pkg.g1_lincomb(same, [12345] * 100, eng) == o.g1_mul(ref_srs_points[7], 1234500)
+        assert pkg.g1_lincomb([P1, o.g1_neg(P1)] * 8, [7] * 16, eng) is None
+        for m in (1, 2, 3, 33, 300):
+            pts = ref_srs_points[:m]
+            sc = [rnd.randrange(o.R) for _ in range(m)]
+            assert pkg.g1_lincomb(pts, sc, eng) == o.msm(pts, sc)
+        # fixed-base table path
+        kzg = pkg.KZG()
+        for n in (1, 2, 64, 1024):
+            sc = [rnd.randrange(o.R) for _ in range(n)]
+            assert kzg.commit_coeff_form(pkg.PolynomialCoeffForm(sc), ref_srs) == o.msm(ref_srs_points[:n], sc)
+        sc = [0x1234567890ABCDEF1234567890ABCDEF] * 2048
+        assert kzg.commit_coeff_form(pkg.PolynomialCoeffForm(sc), ref_srs) == o.msm(ref_srs_points[:2048], sc)
+        assert kzg.commit_coeff_form(pkg.PolynomialCoeffForm([0] * 64), ref_srs) is None
+    finally:
+        pkg.lib.kzgb_msm_tuning(0, 64, 0)

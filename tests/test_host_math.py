@@ -157,3 +157,17 @@ def test_sha256_matches_hashlib(hm):
             if n and n <= 5000:
                 hm.t_sha256_chunked(data, n, step, out)
                 assert out.raw == hashlib.sha256(data).digest()
+
+
+def test_safegcd_inverse_matches_bigint(hm):
+    """fe_inv_fast (Bernstein-Yang division steps, 30-bit batches) against pow(a, -1, p): edge values,
+    every bit length, random elements; 0 -> 0 like the Fermat inverse."""
+    rnd = random.Random(11)
+    for mod, fn in ((o.P, hm.t_fq_inv_fast), (o.R, hm.t_fr_inv_fast)):
+        vals = [1, 2, 3, mod - 1, mod - 2, (mod - 1) // 2, (mod + 1) // 2, 1 << 253, (1 << 253) + 1, MONT % mod,
+                pow(MONT, -1, mod)]
+        vals += [rnd.randrange(1, mod) for _ in range(3000)]
+        vals += [rnd.randrange(1 << (k - 1), 1 << k) for k in range(1, 254)]
+        for a in vals:
+            assert call1(fn, a * MONT % mod) == pow(a, -1, mod) * MONT % mod, hex(a)
+        assert call1(fn, 0) == 0
