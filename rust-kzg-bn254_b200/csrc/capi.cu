@@ -45,7 +45,10 @@ struct DevBuf {
 };
 
 struct Lane {
-    cudaStream_t st = nullptr;
+    cudaStream_t st = nullptr;      // everything but the bucket accumulation (high priority when owned)
+    cudaStream_t st_acc = nullptr;  // bucket accumulation: low priority, so other lanes' short kernels
+                                    // slip in between its blocks instead of queueing behind the whole grid
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool own_stream = false;
     DevBuf bytes, evals, work, ntt_scratch, eval_scratch, msm_ws, small, bases;
     XYZZ* h_sets = nullptr;   // pinned
@@ -197,7 +200,18 @@ int choose_c_fixed(size_t n) {
 // ---------------------------------------------------------------- lanes
 int lane_init(kzgb_ctx* c, Lane& L, cudaStream_t st) {
     if (st) { L.st = st; L.own_stream = false; }
-    else { CK(c, cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking)); L.own_stream = true; }
+    else {
+        int lo = 0, hi = 0;
+        CK(c, cudaDeviceGetStreamPriorityRange(&lo, &hi));  // numerically lower = higher priority
+        CK(c, cudaStreamCreateWithPriority(&L.st, cudaStreamNonBlocking, hi));
+        L.own_stream = true;
+        static const bool split = getenv("KZGB_NO_PRIORITY") == nullptr;
+        if (split && lo != hi) {
+            CK(c, cudaStreamCreateWithPriority(&L.st_acc, cudaStreamNonBlocking, lo));
+            CK(c, cudaEventCreateWithFlags(&L.ev_fork, cudaEventDisableTiming));
+            CK(c, cudaEventCreateWithFlags(&L.ev_join, cudaEventDisableTiming));
+        }
+    }
     CK(c, cudaMallocHost((void**)&L.h_sets, sizeof(XYZZ) * MAX_SETS));
     CK(c, cudaMallocHost((void**)&L.h_fr, sizeof(Fr) * 16));
     CK(c, cudaEventCreate(&L.ev0));
@@ -213,6 +227,9 @@ void lane_destroy(Lane& L) {
     if (L.ev0) cudaEventDestroy(L.ev0);
     if (L.ev1) cudaEventDestroy(L.ev1);
     if (L.ev_done) cudaEventDestroy(L.ev_done);
+    if (L.ev_fork) cudaEventDestroy(L.ev_fork);
+    if (L.ev_join) cudaEventDestroy(L.ev_join);
+    if (L.st_acc) cudaStreamDestroy(L.st_acc);
     if (L.own_stream && L.st) cudaStreamDestroy(L.st);
     L = Lane();
 }
@@ -322,7 +339,7 @@ int msm_enqueue(kzgb_ctx* c, Lane& L, const Fr* d_scalars, bool canonical, size_
     MsmWorkspace ws;
     msm_workspace_carve(p, L.msm_ws.p, &ws);
     lane_collect_acc(L);
-    msm_launch(p, ws, d_scalars, canonical, table, L.st, L.ev0, L.ev1);
+    msm_launch(p, ws, d_scalars, canonical, table, L.st, L.ev0, L.ev1, L.st_acc, L.ev_fork, L.ev_join);
     L.ev_pending = true;
     L.acc_adds += (uint64_t)n * p.W;
     CK(c, cudaMemcpyAsync(L.h_sets, ws.set_sums, sizeof(XYZZ) * p.sets, cudaMemcpyDeviceToHost, L.st));

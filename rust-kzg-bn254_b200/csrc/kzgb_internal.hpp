@@ -64,7 +64,10 @@ void msm_set_tuning(int ba_levels, int ba_min_avg_bucket, int ba_k0);
 // The optional events bracket the bucket-accumulation kernel (roofline timing).
 void msm_launch(const MsmPlan& p, const MsmWorkspace& ws, const Fr* scalars, bool scalars_canonical,
                 const Affine* table, cudaStream_t st, cudaEvent_t ev_acc_begin = nullptr,
-                cudaEvent_t ev_acc_end = nullptr);
+                cudaEvent_t ev_acc_end = nullptr, cudaStream_t st_acc = nullptr, cudaEvent_t ev_fork = nullptr,
+                cudaEvent_t ev_join = nullptr);
+// st_acc (optional): a second, lower-priority stream for the bucket accumulation, fenced against `st`
+// with ev_fork / ev_join.
 
 // ---- SRS ------------------------------------------------------------------------
 // gnark big-endian compressed points -> affine Montgomery.  err[] must be preset to 0xffffffff;

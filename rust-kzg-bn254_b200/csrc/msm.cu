@@ -649,7 +649,9 @@ MsmPlan msm_make_plan(uint32_t n, int c, bool fixed_base, uint32_t table_stride,
         p.ba_k[l] = (uint32_t)k;
     }
     uint64_t tail = padded >> p.ba_levels;
-    uint64_t max_threads = (uint64_t)SM_COUNT * 512;
+    static int waves = -1;
+    if (waves < 0) { const char* e = getenv("KZGB_ACC_WAVES"); waves = e ? atoi(e) : 4; if (waves < 1) waves = 1; }
+    uint64_t max_threads = (uint64_t)SM_COUNT * 512 * waves;  // 4 blocks of 128 threads per SM and wave
     uint64_t want = (tail + 15) / 16;
     if (want < 1) want = 1;
     p.acc_threads = (uint32_t)(want < max_threads ? want : max_threads);
@@ -721,8 +723,11 @@ void msm_workspace_carve(const MsmPlan& p, void* base, MsmWorkspace* ws) {
 }
 
 void msm_launch(const MsmPlan& p, const MsmWorkspace& ws, const Fr* scalars, bool scalars_canonical,
-                const Affine* table, cudaStream_t st, cudaEvent_t ev_acc_begin, cudaEvent_t ev_acc_end) {
+                const Affine* table, cudaStream_t st, cudaEvent_t ev_acc_begin, cudaEvent_t ev_acc_end,
+                cudaStream_t st_acc, cudaEvent_t ev_fork, cudaEvent_t ev_join) {
     const int L = p.ba_levels;
+    const bool split = st_acc && ev_fork && ev_join;
+    cudaStream_t sa = split ? st_acc : st;
     cudaMemsetAsync(ws.hist, 0, ((size_t)p.nbuckets + 1) * 4, st);
     if (L) cudaMemsetAsync(ws.sorted, 0xff, (size_t)p.max_entries * 4, st);  // padding slots = REF_IDENT
     uint32_t gb = (p.n + 255) / 256;
@@ -738,7 +743,8 @@ void msm_launch(const MsmPlan& p, const MsmWorkspace& ws, const Fr* scalars, boo
         }
     }
     if (p.n) k_scatter<<<gb, 256, 0, st>>>(ws.canon, p, ws.cursor, ws.sorted);
-    if (ev_acc_begin) cudaEventRecord(ev_acc_begin, st);
+    if (split) { cudaEventRecord(ev_fork, st); cudaStreamWaitEvent(sa, ev_fork, 0); }
+    if (ev_acc_begin) cudaEventRecord(ev_acc_begin, sa);
     const Affine* tail_src = table;
     for (int l = 0; l < L; l++) {
         BaArgs g;
@@ -754,13 +760,13 @@ void msm_launch(const MsmPlan& p, const MsmWorkspace& ws, const Fr* scalars, boo
         uint32_t nblk = (uint32_t)((pairs + per - 1) / per);
         if (nblk == 0) nblk = 1;
         if (l == 0) {
-            k_ba_prefix<true><<<nblk, BA_THREADS, 0, st>>>(g);
-            k_ba_invert<<<1, BA_INV_THREADS, 0, st>>>(g);
-            k_ba_apply<true><<<nblk, BA_THREADS, 0, st>>>(g);
+            k_ba_prefix<true><<<nblk, BA_THREADS, 0, sa>>>(g);
+            k_ba_invert<<<1, BA_INV_THREADS, 0, sa>>>(g);
+            k_ba_apply<true><<<nblk, BA_THREADS, 0, sa>>>(g);
         } else {
-            k_ba_prefix<false><<<nblk, BA_THREADS, 0, st>>>(g);
-            k_ba_invert<<<1, BA_INV_THREADS, 0, st>>>(g);
-            k_ba_apply<false><<<nblk, BA_THREADS, 0, st>>>(g);
+            k_ba_prefix<false><<<nblk, BA_THREADS, 0, sa>>>(g);
+            k_ba_invert<<<1, BA_INV_THREADS, 0, sa>>>(g);
+            k_ba_apply<false><<<nblk, BA_THREADS, 0, sa>>>(g);
         }
         g_launch_count += 3;
         tail_src = g.out;
@@ -770,7 +776,7 @@ void msm_launch(const MsmPlan& p, const MsmWorkspace& ws, const Fr* scalars, boo
         if (variant < 0) { const char* e = getenv("KZGB_ACC_VARIANT"); variant = e ? atoi(e) : 0; }
         dim3 g((p.acc_threads + 127) / 128);
 #define KZ_ACC(MB, CALL, PF, DIRECT) \
-    k_accumulate_t<MB, CALL, PF, DIRECT><<<g, 128, 0, st>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, L, ws.buckets, ws.partial)
+    k_accumulate_t<MB, CALL, PF, DIRECT><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, L, ws.buckets, ws.partial)
         if (L) {
             KZ_ACC(4, false, false, true);
         } else {
@@ -783,7 +789,8 @@ void msm_launch(const MsmPlan& p, const MsmWorkspace& ws, const Fr* scalars, boo
         }
 #undef KZ_ACC
     }
-    if (ev_acc_end) cudaEventRecord(ev_acc_end, st);
+    if (ev_acc_end) cudaEventRecord(ev_acc_end, sa);
+    if (split) { cudaEventRecord(ev_join, sa); cudaStreamWaitEvent(st, ev_join, 0); }
     k_bucket_fix<<<(p.nbuckets + 127) / 128, 128, 0, st>>>(ws.hist, p.nbuckets, p.chunk, L, ws.buckets, ws.partial);
     uint32_t nslices = p.nbuckets / p.slice;
     k_reduce_slices<<<(nslices + 127) / 128, 128, 0, st>>>(ws.buckets, p, ws.slice_sums);
