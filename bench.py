@@ -281,8 +281,30 @@ def main():
             traffic = json.load(open(tpath)).get("k_accumulate_dram_bytes_per_launch")
         except Exception:
             traffic = None
+    # Fr NTT: the batched 2^16 transforms of config 3 (2 GiB, far beyond L2) are the HBM-bound case;
+    # the single 16 MiB transform of this config is L2-resident and integer-bound
+    ntt_ms, ntt1_ms = C.c_double(0), C.c_double(0)
+    eng.check(lib.kzgb_bench_ntt(eng.h, 16, 1024, 6, C.byref(ntt_ms)))
+    eng.check(lib.kzgb_bench_ntt(eng.h, LOG_N, 1, 20, C.byref(ntt1_ms)))
+    hbm_peak = None
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs")
+    except Exception:
+        pass
+    hbm_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if hbm_peak else "fallback 6650 GB/s (of fallback)"
+    hbm_peak = hbm_peak or 6650.0
+    ntt_bytes = 64.0 * (1024 << 16)  # algorithmic: one read + one write of every element
+    ntt_gbs = ntt_bytes / (ntt_ms.value * 1e-3) / 1e9
+    roofline_ntt = {
+        "kernel": "k_ntt_pass (Fr inverse/forward NTT, 1024 x 2^16 batched, 2 passes)", "bound": "hbm",
+        "achieved": ntt_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ntt_gbs / hbm_peak, "traffic": None,
+        "peak_source": hbm_src, "ms_per_batched_call": ntt_ms.value, "algorithmic_bytes_per_call": ntt_bytes,
+        "butterfly_fr_mul_per_s": (1024 << 16) * 8.0 / (ntt_ms.value * 1e-3),
+        "single_2p19_ntt_ms": ntt1_ms.value,
+        "single_2p19_butterfly_fr_mul_per_s": (1 << LOG_N) * LOG_N / 2.0 / (ntt1_ms.value * 1e-3),
+    }
     roofline = {
-        "kernel": "k_accumulate (MSM bucket accumulation, XYZZ += affine)", "bound": "integer-pipe (IMAD)",
+        "kernel": "k_accumulate_t (MSM bucket accumulation, XYZZ += affine)", "bound": "integer-pipe (IMAD)",
         "achieved": achieved_iso, "peak": peak, "unit": "GFqmul/s", "frac": achieved_iso / peak if peak else None,
         "traffic": traffic,
         "achieved_in_pipeline": achieved, "frac_in_pipeline": achieved / peak if peak else None,
@@ -323,7 +345,8 @@ def main():
                    "l2": f"inputs larger than L2: {B * n * 32 >> 20} MiB of blobs + {cwin.value * n * 64 >> 20} MiB window table per step"},
         "e2e": {"value": e2e_value, "unit": "blobs/s", "h2d_bytes_per_step": B * n * 32, "d2h_bytes_per_step": B * 2 * 128,
                 "ms_per_step": e2e_ms / args.steps, "wall_ms_per_step": e2e_wall / args.steps},
-        "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "roofline_ntt": roofline_ntt,
+        "cpu_baseline": cpu_baseline,
         "wall_ms_per_step": dev_wall / args.steps, "setup_s": setup_s,
     }
     print(json.dumps(line))

@@ -167,6 +167,9 @@ int kzgb_microbench(kzgb_ctx* ctx, int kind, double* ops_per_second);
  * context's stream; returns mean milliseconds per MSM of the whole pipeline and of the bucket
  * accumulation kernel alone. */
 int kzgb_bench_msm(kzgb_ctx* ctx, size_t n, int reps, double* ms_total, double* ms_accumulate);
+/* Times `reps` (I)NTTs of `batch` transforms of size 2^logn back to back on device-resident data
+ * (alternating forward / inverse) with CUDA events; returns mean milliseconds per batched call. */
+int kzgb_bench_ntt(kzgb_ctx* ctx, int logn, size_t batch, int reps, double* ms_per_call);
 /* Number of kernels this library has launched since it was loaded. */
 uint64_t kzgb_launch_count(const kzgb_ctx* ctx);
 /* Device-side stopwatch (CUDA events) spanning every stream of the context: all work queued between

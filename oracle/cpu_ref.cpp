@@ -105,23 +105,37 @@ template <const Params& P> Fp pow_u64(const Fp& a, uint64_t e) {
 // Binary extended Euclid on the Montgomery representation (ark-ff `inverse`): returns a^-1 in
 // Montgomery form (0 -> 0).
 inline void shr1(uint64_t* a) { for (int i = 0; i < 3; i++) a[i] = (a[i] >> 1) | (a[i + 1] << 63); a[3] >>= 1; }
+inline bool is_one4(const uint64_t* a) { return a[0] == 1 && (a[1] | a[2] | a[3]) == 0; }
+// x >>= k for 0 < k < 64
+inline void shrk(uint64_t* a, unsigned k) {
+    for (int i = 0; i < 3; i++) a[i] = (a[i] >> k) | (a[i + 1] << (64 - k));
+    a[3] >>= k;
+}
 template <const Params& P>
 Fp inv(const Fp& a) {
     if (is_zero(a)) return a;
     uint64_t u[4], v[4], b[4], c[4] = {0, 0, 0, 0};
-    const uint64_t onev[4] = {1, 0, 0, 0};
     memcpy(u, a.v, 32); memcpy(v, P.mod, 32); memcpy(b, P.r2, 32);  // b = R^2 so that the result is a^-1 * R
     auto halve = [&](uint64_t* x) {
         if (x[0] & 1) { uint64_t cy = add4(x, x, P.mod); shr1(x); x[3] |= cy << 63; } else shr1(x);
     };
-    while (memcmp(u, onev, 32) != 0 && memcmp(v, onev, 32) != 0) {
-        while (!(u[0] & 1)) { shr1(u); halve(b); }
-        while (!(v[0] & 1)) { shr1(v); halve(c); }
+    // same algorithm and the same sequence of values as ark-ff; the runs of halvings of u / v are taken
+    // k bits at a time with a count-trailing-zeros (the coefficient still needs one modular halving per bit)
+    auto strip = [&](uint64_t* x, uint64_t* coef) {
+        while (!(x[0] & 1)) {
+            unsigned k = x[0] ? (unsigned)__builtin_ctzll(x[0]) : 63u;
+            shrk(x, k);
+            for (unsigned i = 0; i < k; i++) halve(coef);
+        }
+    };
+    while (!is_one4(u) && !is_one4(v)) {
+        strip(u, b);
+        strip(v, c);
         if (geq(u, v)) { sub4(u, u, v); if (sub4(b, b, c)) add4(b, b, P.mod); }
         else { sub4(v, v, u); if (sub4(c, c, b)) add4(c, c, P.mod); }
     }
     Fp r;
-    memcpy(r.v, memcmp(u, onev, 32) == 0 ? b : c, 32);
+    memcpy(r.v, is_one4(u) ? b : c, 32);
     return r;
 }
 

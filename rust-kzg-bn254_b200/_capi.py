@@ -73,6 +73,7 @@ SIGNATURES = {
     "kzgb_validate_g1_points": (C.c_int, [ctx_p, buf, buf, C.c_size_t]),
     "kzgb_microbench": (C.c_int, [ctx_p, C.c_int, C.POINTER(C.c_double)]),
     "kzgb_bench_msm": (C.c_int, [ctx_p, C.c_size_t, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "kzgb_bench_ntt": (C.c_int, [ctx_p, C.c_int, C.c_size_t, C.c_int, C.POINTER(C.c_double)]),
     "kzgb_launch_count": (C.c_uint64, [ctx_p]),
     "kzgb_timer_begin": (C.c_int, [ctx_p]),
     "kzgb_timer_end": (C.c_int, [ctx_p, C.POINTER(C.c_double)]),

@@ -26,7 +26,7 @@ using namespace kzgb;
 
 namespace {
 
-constexpr int MAX_LANES = 4;
+constexpr int MAX_LANES = 8;
 constexpr int MAX_SETS = 96;
 
 struct DevBuf {
@@ -932,7 +932,11 @@ static int batch_impl(kzgb_ctx* c, const uint8_t* const* blobs_dev, const uint8_
         }
         max_n = std::max(max_n, n);
     }
-    int n_lanes = (int)std::min<size_t>(count, 3);
+    // lanes in flight: 3 keep the GPU full on 16 MiB blobs; small blobs are latency-bound per lane
+    // (bucket reduction, host hand-offs), so they get more
+    static const int lanes_env = getenv("KZGB_LANES") ? atoi(getenv("KZGB_LANES")) : 0;
+    int want_lanes = lanes_env > 0 ? lanes_env : (max_n >= ((size_t)1 << 18) ? 3 : 6);
+    int n_lanes = (int)std::min<size_t>(count, (size_t)std::min(want_lanes, MAX_LANES));
     int rc = ensure_lanes(c, n_lanes);
     if (rc) return rc;
     rc = ensure_twiddles(c, log2_exact(max_n));
@@ -1274,6 +1278,30 @@ int kzgb_bench_msm(kzgb_ctx* c, size_t n, int reps, double* ms_total, double* ms
     return KZGB_OK;
 }
 
+int kzgb_bench_ntt(kzgb_ctx* c, int logn, size_t batch, int reps, double* ms_per_call) {
+    Guard g(c);
+    Lane& L = c->lanes[0];
+    if (logn < 1 || logn > 28 || batch == 0 || reps < 1) return fail(c, KZGB_ERR_GENERIC, "bad NTT bench shape");
+    int rc = ensure_twiddles(c, logn);
+    if (rc) return rc;
+    size_t total = batch << logn;
+    CK(c, L.work.reserve(total * sizeof(Fr)));
+    CK(c, L.ntt_scratch.reserve(total * sizeof(Fr)));
+    Fr base = fr_from_u64(0x9e3779b97f4a7c15ull);
+    fr_powers_launch((Fr*)L.work.p, (uint32_t)std::min<size_t>(total, 0xffffffffu), &base, L.st);
+    Fr ninv = ninv_mont(logn);
+    ntt_launch((Fr*)L.work.p, logn, (uint32_t)batch, true, c->tw, c->logN, &ninv, (Fr*)L.ntt_scratch.p, L.st);  // warm-up
+    CK(c, cudaEventRecord(c->t0, L.st));
+    for (int i = 0; i < reps; i++)
+        ntt_launch((Fr*)L.work.p, logn, (uint32_t)batch, (i & 1) == 0, c->tw, c->logN, &ninv, (Fr*)L.ntt_scratch.p, L.st);
+    CK(c, cudaEventRecord(c->t1, L.st));
+    CK(c, cudaEventSynchronize(c->t1));
+    CK(c, cudaGetLastError());
+    float ms = 0;
+    CK(c, cudaEventElapsedTime(&ms, c->t0, c->t1));
+    *ms_per_call = ms / reps;
+    return KZGB_OK;
+}
 
 // Device-side stopwatch over ALL lanes: everything queued between begin and end is inside [t0, t1].
 int kzgb_timer_begin(kzgb_ctx* c) {
