@@ -99,6 +99,8 @@ class Prog:
                 regs[dst] = v[0] & v[1]
             elif op == "or.b32":
                 regs[dst] = v[0] | v[1]
+            elif op == "xor.b32":
+                regs[dst] = v[0] ^ v[1]
             else:
                 raise ValueError(op)
             assert 0 <= regs[dst] <= MASK
@@ -216,6 +218,193 @@ def gen_mul(field: str, sqr: bool = False) -> Prog:
     return pr
 
 
+# ---------------------------------------------------------------------------------------------
+# Karatsuba product + separate Montgomery reduction ("mulk").  IMAD.WIDE issues at a quarter of the
+# scheduler rate on sm_100 (measured: half the 32-bit IMAD rate), so the integer pipe is the
+# bound: one Karatsuba level turns the 64 wide multiplies of the 8x8 product into 3 x 16 = 48 plus
+# ~90 additions; the reduction keeps its 64.  NEGATIVE RESULT (B200, profiles/r01_accumulate_variants.txt):
+# 5.60e10 mul/s against 6.70e10 for the CIOS routine -- every added IADD3/LOP3 costs an issue cycle
+# (cycles ~ 4 x IMAD.WIDE + 2 x IMAD + 1 x everything else), so 16 fewer wide multiplies (64 cycles)
+# do not pay for ~110 extra ALU instructions.  Not emitted into field_gen.cuh; kept with its
+# emulator check because the separate product / reduction blocks are what lazy reduction would need.
+# ---------------------------------------------------------------------------------------------
+class Namer:
+    def __init__(self, pr, prefix):
+        self.pr, self.prefix, self.k = pr, prefix, 0
+
+    def new(self, n=1):
+        out = []
+        for _ in range(n):
+            out.append(self.pr.tmp(f"{self.prefix}{self.k}"))
+            self.k += 1
+        return out if n > 1 else out[0]
+
+
+def emit_mulw(pr: Prog, nm: Namer, a, b, n):
+    """Schoolbook n x n -> 2n limbs (n even) with two shifting accumulators (lo-aligned A, hi-aligned B),
+    the CIOS skeleton of gen_mul without the reduction; every (lo, hi) pair fuses into one IMAD.WIDE."""
+    T = []
+    A = nm.new(n)
+    B = nm.new(n)
+    for j in range(0, n, 2):
+        pr.op("mul.lo.u32", A[j], a[j], b[0])
+        pr.op("mul.hi.u32", A[j + 1], a[j], b[0])
+    for j in range(0, n, 2):
+        pr.op("mul.lo.u32", B[j], a[j + 1], b[0])
+        pr.op("mul.hi.u32", B[j + 1], a[j + 1], b[0])
+    T.append(A[0])
+    for i in range(1, n):
+        oldA, oldB = A, B
+        nA0 = nm.new()
+        pr.op("add.cc.u32", nA0, oldB[0], oldA[1])
+        nB = nm.new(n)
+        for j in range(0, n - 2, 2):
+            pr.op("madc.lo.cc.u32", nB[j], a[j + 1], b[i], oldA[j + 2])
+            pr.op("madc.hi.cc.u32", nB[j + 1], a[j + 1], b[i], oldA[j + 3])
+        pr.op("madc.lo.cc.u32", nB[n - 2], a[n - 1], b[i], 0)
+        pr.op("madc.hi.u32", nB[n - 1], a[n - 1], b[i], 0)
+        nA = nm.new(n)
+        pr.op("mad.lo.cc.u32", nA[0], a[0], b[i], nA0)
+        pr.op("madc.hi.cc.u32", nA[1], a[0], b[i], oldB[1])
+        for j in range(2, n, 2):
+            pr.op("madc.lo.cc.u32", nA[j], a[j], b[i], oldB[j])
+            pr.op("madc.hi.cc.u32", nA[j + 1], a[j], b[i], oldB[j + 1])
+        top = nm.new()
+        pr.op("addc.u32", top, nB[n - 1], 0)
+        nB = nB[: n - 1] + [top]
+        A, B = nA, nB
+        T.append(A[0])
+    # remaining window: (A >> 32) + B
+    hi = nm.new(n)
+    pr.op("add.cc.u32", hi[0], A[1], B[0])
+    for k in range(1, n - 1):
+        pr.op("addc.cc.u32", hi[k], A[k + 1], B[k])
+    pr.op("addc.u32", hi[n - 1], B[n - 1], 0)
+    return T + hi
+
+
+def emit_absdiff(pr: Prog, nm: Namer, x, y, n):
+    """|x - y| (n limbs) and the mask (all ones if x < y)."""
+    d = nm.new(n)
+    pr.op("sub.cc.u32", d[0], x[0], y[0])
+    for i in range(1, n):
+        pr.op("subc.cc.u32", d[i], x[i], y[i])
+    m = nm.new()
+    pr.op("subc.u32", m, 0, 0)  # 0xffffffff on borrow
+    e = nm.new(n)
+    for i in range(n):
+        pr.op("xor.b32", e[i], d[i], m)
+    r = nm.new(n)
+    pr.op("sub.cc.u32", r[0], e[0], m)
+    for i in range(1, n):
+        pr.op("subc.cc.u32" if i < n - 1 else "subc.u32", r[i], e[i], m)
+    return r, m
+
+
+def emit_karatsuba8(pr: Prog, nm: Namer, a, b):
+    """8 x 8 -> 16 limbs: z0 = lo*lo, z2 = hi*hi, middle = z0 + z2 - (a_lo - a_hi)(b_lo - b_hi)."""
+    z0 = emit_mulw(pr, nm, a[0:4], b[0:4], 4)
+    z2 = emit_mulw(pr, nm, a[4:8], b[4:8], 4)
+    da, ma = emit_absdiff(pr, nm, a[0:4], a[4:8], 4)
+    db, mb = emit_absdiff(pr, nm, b[4:8], b[0:4], 4)  # (a_lo - a_hi)(b_hi - b_lo) = a_lo b_hi + a_hi b_lo - z0 - z2
+    z1 = emit_mulw(pr, nm, da, db, 4)
+    ms = nm.new()
+    pr.op("xor.b32", ms, ma, mb)  # all ones: the product above is negative
+    # S = z0 + z2 (9 limbs)
+    S = nm.new(9)
+    pr.op("add.cc.u32", S[0], z0[0], z2[0])
+    for i in range(1, 8):
+        pr.op("addc.cc.u32", S[i], z0[i], z2[i])
+    pr.op("addc.u32", S[8], 0, 0)
+    # M = S + (ms ? -z1 : z1) = S + (z1 ^ ms) + (ms & 1), 9 limbs, never negative
+    zx = nm.new(8)
+    for i in range(8):
+        pr.op("xor.b32", zx[i], z1[i], ms)
+    dummy = nm.new()
+    pr.op("add.cc.u32", dummy, ms, 1)  # carry = 1 iff ms is all ones
+    M = nm.new(9)
+    for i in range(8):
+        pr.op("addc.cc.u32", M[i], S[i], zx[i])
+    pr.op("addc.u32", M[8], S[8], ms)
+    # T = z0 + M << 128 + z2 << 256
+    T = list(z0[0:4]) + nm.new(12)
+    pr.op("add.cc.u32", T[4], z0[4], M[0])
+    for i in range(1, 4):
+        pr.op("addc.cc.u32", T[4 + i], z0[4 + i], M[i])
+    for i in range(4):
+        pr.op("addc.cc.u32", T[8 + i], z2[i], M[4 + i])
+    pr.op("addc.cc.u32", T[12], z2[4], M[8])
+    pr.op("addc.cc.u32", T[13], z2[5], 0)
+    pr.op("addc.cc.u32", T[14], z2[6], 0)
+    pr.op("addc.u32", T[15], z2[7], 0)
+    return T
+
+
+def emit_redc(pr: Prog, nm: Namer, T, mod, out, tag):
+    """Montgomery reduction of a 16-limb T < mod * 2^256: out = T / 2^256 mod p (fully reduced).
+    Word-serial on the low half with the two shifting accumulators of gen_mul, then + T_hi."""
+    pl = limbs(mod)
+    np0 = (-pow(mod, -1, 1 << 32)) & MASK
+    A = list(T[0:8])
+    B = None
+    for i in range(8):
+        if i == 0:
+            t0 = A[0]
+            m = nm.new()
+            pr.op("mul.lo.u32", m, t0, np0)
+            nB = nm.new(8)
+            for j in (0, 2, 4, 6):
+                pr.op("mul.lo.u32", nB[j], pl[j + 1], m)
+                pr.op("mul.hi.u32", nB[j + 1], pl[j + 1], m)
+            src = A
+        else:
+            oldA, oldB = A, B
+            t0 = nm.new()
+            pr.op("add.cc.u32", t0, oldB[0], oldA[1])
+            m = nm.new()
+            pr.op("mul.lo.u32", m, t0, np0)  # does not touch the carry flag
+            nB = nm.new(8)
+            for j in (0, 2, 4):
+                pr.op("madc.lo.cc.u32", nB[j], pl[j + 1], m, oldA[j + 2])
+                pr.op("madc.hi.cc.u32", nB[j + 1], pl[j + 1], m, oldA[j + 3])
+            pr.op("madc.lo.cc.u32", nB[6], pl[7], m, 0)
+            pr.op("madc.hi.u32", nB[7], pl[7], m, 0)
+            src = [t0] + list(oldB[1:8])
+        nA = nm.new(8)
+        pr.op("mad.lo.cc.u32", nA[0], pl[0], m, src[0])
+        pr.op("madc.hi.cc.u32", nA[1], pl[0], m, src[1])
+        for j in (2, 4, 6):
+            pr.op("madc.lo.cc.u32", nA[j], pl[j], m, src[j])
+            pr.op("madc.hi.cc.u32", nA[j + 1], pl[j], m, src[j + 1])
+        top = nm.new()
+        pr.op("addc.u32", top, nB[7], 0)
+        A, B = nA, nB[:7] + [top]
+    # (A >> 32) + B + T_hi  (< 2p), one conditional subtraction
+    s = nm.new(8)
+    pr.op("add.cc.u32", s[0], A[1], B[0])
+    for j in range(1, 7):
+        pr.op("addc.cc.u32", s[j], A[j + 1], B[j])
+    pr.op("addc.u32", s[7], B[7], 0)
+    u = nm.new(8)
+    pr.op("add.cc.u32", u[0], s[0], T[8])
+    for j in range(1, 7):
+        pr.op("addc.cc.u32", u[j], s[j], T[8 + j])
+    pr.op("addc.u32", u[7], s[7], T[15])
+    cond_sub(pr, u, mod, out, tag)
+
+
+def gen_mulk(field: str) -> Prog:
+    mod = FIELDS[field]
+    a = [f"a{i}" for i in range(8)]
+    b = [f"b{i}" for i in range(8)]
+    r = [f"r{i}" for i in range(8)]
+    pr = Prog(f"{field}_mulk", a + b, r)
+    nm = Namer(pr, "t")
+    T = emit_karatsuba8(pr, nm, a, b)
+    emit_redc(pr, nm, T, mod, r, "c")
+    return pr
+
+
 def gen_add(field: str) -> Prog:
     mod = FIELDS[field]
     a = [f"a{i}" for i in range(8)]
@@ -269,6 +458,7 @@ def gen_reduce_once(field: str) -> Prog:
 
 ROUTINES = {
     "mul": gen_mul,
+    "mulk": gen_mulk,
     "add": gen_add,
     "sub": gen_sub,
     "reduce_once": gen_reduce_once,
@@ -308,7 +498,7 @@ def emit_header() -> str:
     out.append("")
     out.append("#ifdef __CUDACC__")
     for field in ("fq", "fr"):
-        for what in ("mul", "add", "sub", "reduce_once"):
+        for what in ("mul", "add", "sub", "reduce_once"):  # "mulk" is kept in the generator only (measured slower)
             pr = ROUTINES[what](field)
             two = what in ("mul", "add", "sub")
             sig = f"{field}_{what}_ptx(uint32_t* r, const uint32_t* a" + (
@@ -330,15 +520,18 @@ def selftest(iters: int = 300) -> None:
         cases += [(rnd.randrange(mod), rnd.randrange(mod)) for _ in range(iters)]
         for x, y in cases:
             assert emulate(field, "mul", x, y) == x * y * rinv % mod, (field, "mul", x, y)
+            assert emulate(field, "mulk", x, y) == x * y * rinv % mod, (field, "mulk", x, y)
             assert emulate(field, "add", x, y) == (x + y) % mod, (field, "add", x, y)
             assert emulate(field, "sub", x, y) == (x - y) % mod, (field, "sub", x, y)
         # multiplicand a < p, word operand b ANY 256-bit value (used for bytes -> Fr)
         for _ in range(iters):
             x, y = rnd.randrange(mod), rnd.randrange(1 << 256)
             assert emulate(field, "mul", x, y) == x * y * rinv % mod, (field, "mulwide", x, y)
+            assert emulate(field, "mulk", x, y) == x * y * rinv % mod, (field, "mulkwide", x, y)
         for x in (mod - 1, (1 << 256) % mod, rnd.randrange(mod)):
             for y in ((1 << 256) - 1, (1 << 256) - 2, 1 << 255, mod, 2 * mod, 5 * mod + 7):
                 assert emulate(field, "mul", x, y) == x * y * rinv % mod, (field, "mulwide", x, y)
+                assert emulate(field, "mulk", x, y) == x * y * rinv % mod, (field, "mulkwide", x, y)
         for x in edge + [rnd.randrange(2 * mod) for _ in range(iters)] + [mod, mod + 1, 2 * mod - 1]:
             assert emulate(field, "reduce_once", x) == x % mod
     print("gen_field selftest OK")
