@@ -801,27 +801,31 @@ int kzgb_commit_blob(kzgb_ctx* c, const uint8_t* blob, size_t len, uint64_t out_
     return KZGB_OK;
 }
 
-// The reference computes the Lagrange SRS with (n/2) log n + n scalar multiplications per commit
-// (kzg.rs:263-285).  Here it is only a public API: L_i = MSM(SRS[..n], column i of the inverse DFT
-// matrix) = commit_eval_form(unit vector e_i); done as n small commits would be wasteful, so we use
-// n fixed-base MSMs only for tiny n and otherwise... (g1_ifft is a "next" row).
+// KZG::g1_ifft (kzg.rs:263-285): the Lagrange-basis SRS, a G1-point inverse NTT on the GPU (g1ntt.cu).
+// Only a public API here -- commitments use the Fr-IFFT + monomial MSM identity instead.
 int kzgb_g1_ifft(kzgb_ctx* c, size_t n, uint64_t* out_xy, uint8_t* out_inf) {
     if (n == 0 || (n & (n - 1))) return fail(c, KZGB_ERR_FFT, "length provided is not a power of 2");
-    if (n > kzgb_srs_len(c)) return fail(c, KZGB_ERR_GENERIC, "g1_ifft length exceeds the SRS");
-    if (n > 4096) return fail(c, KZGB_ERR_GENERIC, "g1_ifft: sizes above 4096 are not implemented on the GPU path yet");
-    // L_i = sum_j (1/n) w^{-ij} SRS_j : one MSM per output point with scalars from the inverse DFT matrix
-    int logn = log2_exact(n);
-    Fr w = root_of_unity_mont(logn), winv, ninv = ninv_mont(logn);
-    fe_inv(winv, w);
-    std::vector<Fr> col(n);
-    for (size_t i = 0; i < n; i++) {
-        Fr wi, cur = ninv;
-        uint32_t e[8] = {(uint32_t)i, 0, 0, 0, 0, 0, 0, 0};
-        fe_pow(wi, winv, e);
-        for (size_t j = 0; j < n; j++) { col[j] = cur; fe_mul(cur, cur, wi); }
-        int rc = kzgb_msm_srs_range(c, (const uint64_t*)col.data(), 0, n, out_xy + 8 * i, out_inf ? out_inf + i : nullptr);
-        if (rc) return rc;
+    Guard g(c);
+    Lane& L = c->lanes[0];
+    if (n > c->srs_n) {
+        char msg[160];
+        snprintf(msg, sizeof msg, "SRS capacity exceeded: polynomial_len=%zu srs_len=%zu", n, c->srs_n);
+        return fail(c, KZGB_ERR_SRS_CAPACITY, msg);
     }
+    if (n > ((size_t)1 << 28)) return fail(c, KZGB_ERR_GENERIC, "power must be <= 28");
+    int logn = log2_exact(n);
+    int rc = ensure_twiddles(c, logn);
+    if (rc) return rc;
+    CK(c, L.work.reserve(n * sizeof(XYZZ)));
+    CK(c, L.bases.reserve(n * sizeof(Affine)));
+    Fr ninv = ninv_mont(logn), ninv_canon;
+    fe_from_mont(ninv_canon, ninv);
+    g1_intt_launch(c->srs, logn, (XYZZ*)L.work.p, (Affine*)L.bases.p, c->tw, c->logN, &ninv_canon, L.st);
+    std::vector<Affine> host(n);
+    CK(c, cudaMemcpyAsync(host.data(), L.bases.p, n * sizeof(Affine), cudaMemcpyDeviceToHost, L.st));
+    CK(c, cudaStreamSynchronize(L.st));
+    CK(c, cudaGetLastError());
+    for (size_t i = 0; i < n; i++) affine_to_abi(host[i], out_xy + 8 * i, out_inf ? out_inf + i : nullptr);
     return KZGB_OK;
 }
 

@@ -90,6 +90,12 @@ void ntt_twiddles_launch(Fr* tw, int logN, const Fr* omega_mont_host, cudaStream
 void ntt_launch(Fr* data, int logn, uint32_t batch, bool inverse, const Fr* tw, int logN, const Fr* ninv_mont_host,
                 Fr* scratch, cudaStream_t st);
 
+// ---- G1 inverse NTT (KZG::g1_ifft, prover/src/kzg.rs:263-285) --------------------------
+// srs: 2^logn affine points; work: 2^logn XYZZ scratch; out: 2^logn affine points (natural order).
+// ninv_canon_host: 1/n as a CANONICAL (non-Montgomery) scalar.
+void g1_intt_launch(const Affine* srs, int logn, XYZZ* work, Affine* out, const Fr* tw, int logN,
+                    const Fr* ninv_canon_host, cudaStream_t st);
+
 // ---- polynomial glue ------------------------------------------------------------
 // bytes (big-endian 32 B chunks, last chunk zero-right-padded) -> n Fr Montgomery (zero padded to n)
 void bytes_to_fr_launch(const uint8_t* in, uint64_t len_bytes, Fr* out, uint32_t n, cudaStream_t st);

@@ -332,3 +332,37 @@ def test_batch_affine_levels_exact(pkg, eng, ref_srs, ref_srs_points, levels, k0
         assert kzg.commit_coeff_form(pkg.PolynomialCoeffForm([0] * 64), ref_srs) is None
     finally:
         pkg.lib.kzgb_msm_tuning(0, 64, 0)
+
+
+def test_g1_ifft_kernel_sizes_and_identities(pkg, eng, ref_srs, ref_srs_points):
+    """The G1 inverse-NTT kernels (kzg.rs:263-285) beyond the 64-point fixture: tiny sizes against the
+    big-int oracle, the defining identity commit_eval_form(f) == MSM(g1_ifft(n), f) (prover/src/lib.rs:36-49)
+    at n = 1024, an SRS containing the identity and repeated points, and the error paths."""
+    kzg = pkg.KZG()
+    rnd = random.Random(21)
+    for n in (1, 2, 4, 16):
+        assert kzg.g1_ifft(n, ref_srs) == o.g1_ifft(n, ref_srs_points[:n])
+    n = 1024
+    lag = kzg.g1_ifft(n, ref_srs)
+    evals = [rnd.randrange(o.R) for _ in range(n)]
+    assert pkg.g1_lincomb(lag, evals, eng) == kzg.commit_eval_form(pkg.PolynomialEvalForm(evals), ref_srs)
+    # sum of the Lagrange basis = commitment to the constant polynomial 1 = SRS[0]
+    assert pkg.g1_lincomb(lag, [1] * n, eng) == ref_srs_points[0]
+    odd = [ref_srs_points[1], None, ref_srs_points[1], o.g1_neg(ref_srs_points[1]), ref_srs_points[2], None, None, ref_srs_points[2]]
+    srs2 = pkg.SRS.from_points(odd, engine=pkg.Engine(0))
+    assert kzg.g1_ifft(8, srs2) == o.g1_ifft(8, odd)
+    with pytest.raises(pkg.KzgError) as e:
+        kzg.g1_ifft(4096, ref_srs)  # only 3000 points loaded
+    assert e.value.variant == "SrsCapacityExceeded"
+
+
+def test_g1_ifft_closed_form_large(pkg):
+    """n = 2^14 on the synthetic SRS tau^j G: L_i = l_i(tau) G with l_i(tau) = (tau^n - 1) / (n (tau w^-i - 1))."""
+    n = 1 << 14
+    srs = pkg.SRS.synthetic(n, o.SYNTH_TAU)
+    lag = pkg.KZG().g1_ifft(n, srs)
+    w = o.PRIMITIVE_ROOTS_OF_UNITY[14]
+    tn = (pow(o.SYNTH_TAU, n, o.R) - 1) % o.R
+    for i in (0, 1, 2, 77, n // 2, n - 1):
+        den = n * ((o.SYNTH_TAU * pow(w, -i, o.R) - 1) % o.R) % o.R
+        assert lag[i] == o.g1_mul(o.G1_GEN, tn * o.fr_inv(den) % o.R), i
