@@ -1109,13 +1109,14 @@ int kzgb_verify_batch_rlc(kzgb_ctx* c, const uint8_t* const* blobs, const size_t
     int rc = ensure_twiddles(c, log2_exact(max_n));
     if (rc) return rc;
     std::vector<Fr> zs(m), ys(m);
+    // host SHA-256 pool (one transcript per blob) runs while the blobs are uploaded and converted
+    std::atomic<size_t> next{0};
+    std::vector<std::thread> hashers;
     {
-        std::atomic<size_t> next{0};
         unsigned hw = std::thread::hardware_concurrency();
         size_t nt = std::max<size_t>(1, std::min<size_t>({m, (size_t)(hw > 2 ? hw - 1 : 1), (size_t)32}));
-        std::vector<std::thread> th;
         for (size_t t = 0; t < nt; t++)
-            th.emplace_back([&]() {
+            hashers.emplace_back([&]() {
                 for (;;) {
                     size_t i = next.fetch_add(1);
                     if (i >= m) return;
@@ -1124,8 +1125,15 @@ int kzgb_verify_batch_rlc(kzgb_ctx* c, const uint8_t* const* blobs, const size_t
                     zs[i] = challenge_finish(sh, Cs[i]);
                 }
             });
-        for (auto& t : th) t.join();
     }
+    struct Joiner {
+        std::vector<std::thread>& t;
+        std::atomic<size_t>& next;
+        size_t m;
+        bool joined = false;
+        void join() { if (!joined) { for (auto& x : t) x.join(); joined = true; } }
+        ~Joiner() { next.store(m); join(); }  // error paths: stop handing out work, then wait
+    } joiner{hashers, next, m};
     const size_t budget_elems = (size_t)1 << 24;  // evaluations resident per GPU batch
     size_t i0 = 0;
     while (i0 < m) {
@@ -1137,11 +1145,19 @@ int kzgb_verify_batch_rlc(kzgb_ctx* c, const uint8_t* const* blobs, const size_t
         CK(c, L.bytes.reserve(b * n * 32));
         CK(c, L.eval_scratch.reserve(eval_quotient_scratch_elems((uint32_t)n, (uint32_t)b) * sizeof(Fr)));
         CK(c, L.work.reserve(3 * b * sizeof(Fr)));
-        for (size_t k = 0; k < b; k++) {
+        bool full = (uint64_t)b * n < 0xffffffffull;  // every blob fills its polynomial: one conversion launch
+        for (size_t k = 0; k < b && full; k++) full = lens[i0 + k] == n * 32;
+        for (size_t k = 0; k < b;) {
             uint8_t* dst = (uint8_t*)L.bytes.p + k * n * 32;
-            CK(c, cudaMemcpyAsync(dst, blobs[i0 + k], lens[i0 + k], cudaMemcpyHostToDevice, L.st));
-            bytes_to_fr_launch(dst, lens[i0 + k], (Fr*)L.evals.p + k * n, (uint32_t)n, L.st);
+            size_t run = 1;  // blobs that are adjacent in host memory go up in one copy
+            while (full && k + run < b && blobs[i0 + k + run] == blobs[i0 + k] + run * n * 32) run++;
+            size_t bytes = full ? run * n * 32 : lens[i0 + k];
+            CK(c, cudaMemcpyAsync(dst, blobs[i0 + k], bytes, cudaMemcpyHostToDevice, L.st));
+            if (!full) bytes_to_fr_launch(dst, lens[i0 + k], (Fr*)L.evals.p + k * n, (uint32_t)n, L.st);
+            k += run;
         }
+        if (full) bytes_to_fr_launch((const uint8_t*)L.bytes.p, (uint64_t)b * n * 32, (Fr*)L.evals.p, (uint32_t)(b * n), L.st);
+        joiner.join();  // the challenges z_i are needed from here on
         Fr* d_z = (Fr*)L.work.p;
         Fr* d_t = d_z + b;
         Fr* d_y = d_t + b;

@@ -140,3 +140,75 @@ def test_batch_verify_rlc_pairing_relation(pkg):
     # a small prefix against the full oracle restatement of batch.rs
     bo = [o.Blob(b.data()) for b in blobs[:3]]
     assert pkg.verify_blob_kzg_proof_batch_rlc(blobs[:3], cpts[:3], ppts[:3], eng) == o.verify_blob_kzg_proof_batch_rlc(bo, cpts[:3], ppts[:3])
+
+
+def _geom(n):
+    """sum_{i<n} tau^i mod r."""
+    return (pow(TAU, n, o.R) - 1) * pow(TAU - 1, -1, o.R) % o.R
+
+
+@pytest.mark.parametrize("levels", [0, 3])
+def test_adversarial_scalar_distributions_2p16(pkg, levels):
+    """SURVEY.md 8d 'D3' inputs at n = 2^16 on the fixed-base table, with and without the batch-affine
+    front end: all scalars equal (every point of a window in ONE bucket -> buckets spanning thousands
+    of chunks), all r - 1 (all digits negative / carries through every window), a single non-zero
+    scalar, all zero (identity), and two distinct values (two hot buckets per window).  Closed forms
+    from SRS_i = tau^i G."""
+    n = 1 << 16
+    eng = pkg.Engine(0)
+    srs = pkg.SRS.synthetic(n, TAU, engine=eng)
+    srs.precompute(n, 0)
+    kzg = pkg.KZG()
+    G = o.G1_GEN
+    s = 0x2F0E1D3C4B5A69788796A5B4C3D2E1F00112233445566778899AABBCCDDEEFF % o.R
+    try:
+        pkg.lib.kzgb_msm_tuning(levels, 0, 0)
+        assert kzg.commit_coeff_form(pkg.PolynomialCoeffForm([s] * n), srs) == o.g1_mul(G, s * _geom(n) % o.R)
+        assert kzg.commit_coeff_form(pkg.PolynomialCoeffForm([o.R - 1] * n), srs) == o.g1_mul(G, (o.R - 1) * _geom(n) % o.R)
+        one = [0] * n
+        one[12345] = s
+        assert kzg.commit_coeff_form(pkg.PolynomialCoeffForm(one), srs) == o.g1_mul(G, s * pow(TAU, 12345, o.R) % o.R)
+        assert kzg.commit_coeff_form(pkg.PolynomialCoeffForm([0] * n), srs) is None
+        t = (s * 7 + 1) % o.R
+        even = (pow(TAU, n, o.R) - 1) * pow(TAU * TAU % o.R - 1, -1, o.R) % o.R  # sum of tau^(2i)
+        two = [s, t] * (n // 2)
+        assert kzg.commit_coeff_form(pkg.PolynomialCoeffForm(two), srs) == o.g1_mul(G, (s * even + t * TAU % o.R * even) % o.R)
+    finally:
+        pkg.lib.kzgb_msm_tuning(0, 64, 0)
+
+
+def test_zero_and_constant_blobs_2p16(pkg):
+    """verifier/tests/tests.rs:239-269 at size: the zero blob commits to the identity and proves to the
+    identity; a constant polynomial c commits to c * G (the Lagrange basis sums to SRS_0) and its
+    quotient is zero."""
+    n = 1 << 16
+    eng = pkg.Engine(0)
+    srs = pkg.SRS.synthetic(n, TAU, engine=eng)
+    zero = pkg.Blob.new(bytes(32 * n))
+    cval = 0x0123456789ABCDEF0123456789ABCDEF0123456789ABCDEF0123456789AB
+    const = pkg.Blob.new(cval.to_bytes(32, "big") * n)
+    cs, ps = pkg.KZG.commit_and_prove_blobs([zero, const, zero], srs)
+    ident = o.g1_serialize_compressed(None)
+    assert cs[0] == cs[2] == ident and ps[0] == ps[2] == ident
+    assert cs[1] == o.g1_serialize_compressed(o.g1_mul(o.G1_GEN, cval))
+    assert ps[1] == ident
+
+
+def test_ntt_linearity_2p19(pkg):
+    """ifft(a + 3 b) == ifft(a) + 3 ifft(b) element-wise at n = 2^19 (size-independent property)."""
+    import numpy as np
+
+    n = 1 << 19
+    eng = pkg.Engine(0)
+    rnd = random.Random(19)
+    sa = [rnd.randrange(o.R) for _ in range(128)]
+    sb = [rnd.randrange(o.R) for _ in range(128)]
+    sc = [(x + 3 * y) % o.R for x, y in zip(sa, sb)]
+    outs = []
+    for seed in (sa, sb, sc):
+        buf = C.create_string_buffer(pkg.fr_to_mont_bytes(seed) * (n // 128), 32 * n)
+        eng.check(pkg.lib.kzgb_ntt_fr(eng.h, buf, n, 1))
+        outs.append(buf.raw)
+    for i in list(range(0, n, n // 64)) + [1, 2, 3, n - 1]:
+        a, b, c = (pkg.fr_from_mont_bytes(o_[32 * i : 32 * i + 32])[0] for o_ in outs)
+        assert c == (a + 3 * b) % o.R
