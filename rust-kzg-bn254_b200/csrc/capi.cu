@@ -10,6 +10,7 @@
 #include <condition_variable>
 #include <cstdio>
 #include <cstring>
+#include <ctime>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -348,10 +349,25 @@ int msm_enqueue(kzgb_ctx* c, Lane& L, const Fr* d_scalars, bool canonical, size_
     return KZGB_OK;
 }
 
+bool lane_wait_polls();
 // Wait for the lane and finish on the host: Horner over the window sums, then to affine.
 int msm_finish(kzgb_ctx* c, Lane& L, const MsmJob& job, Affine* out) {
     if (!job.active) { aff_set_inf(*out); return KZGB_OK; }
-    CK(c, cudaStreamSynchronize(L.st));  // spinning wait: a blocking-sync event costs 0.3 ms per MSM in wake-up latency
+    // Spinning wait by default (a blocking-sync event costs ~0.3 ms per MSM in wake-up latency).  When the
+    // ranks on this host have more lane threads than spare cores, spinning lanes starve the SHA-256
+    // pool (8 GPUs x 4 lanes on 32 cores): poll with short sleeps instead.
+    if (lane_wait_polls()) {
+        CK(c, cudaEventRecord(L.ev_done, L.st));
+        for (;;) {
+            cudaError_t q = cudaEventQuery(L.ev_done);
+            if (q == cudaSuccess) break;
+            if (q != cudaErrorNotReady) CK(c, q);
+            struct timespec ts = {0, 30000};
+            nanosleep(&ts, nullptr);
+        }
+    } else {
+        CK(c, cudaStreamSynchronize(L.st));
+    }
     CK(c, cudaGetLastError());
     lane_collect_acc(L);
     const MsmPlan& p = job.plan;
@@ -455,6 +471,22 @@ Fr challenge_finish(Sha256 sh, const Affine& commitment) {
     sh.update(cb, 32);
     sh.finish(dg);
     return fr_from_be_bytes(dg);  // hash_to_field_element (helpers.rs:382-390)
+}
+
+bool lane_wait_polls() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("KZGB_LANE_WAIT");
+        if (e && !strcmp(e, "spin")) mode = 0;
+        else if (e && !strcmp(e, "poll")) mode = 1;
+        else {
+            unsigned hw = std::thread::hardware_concurrency();
+            int local = 1;
+            if (const char* w = getenv("LOCAL_WORLD_SIZE")) { int v = atoi(w); if (v > 0) local = v; }
+            mode = ((unsigned)local * 4u > hw / 2u) ? 1 : 0;
+        }
+    }
+    return mode == 1;
 }
 
 // Host threads for the SHA-256 pool of one context.  One transcript hash is sequential (~9 ms per 16 MiB
@@ -950,7 +982,7 @@ static int batch_impl(kzgb_ctx* c, const uint8_t* const* blobs_dev, const uint8_
     // lanes in flight: 3 keep the GPU full on 16 MiB blobs; small blobs are latency-bound per lane
     // (bucket reduction, host hand-offs), so they get more
     static const int lanes_env = getenv("KZGB_LANES") ? atoi(getenv("KZGB_LANES")) : 0;
-    int want_lanes = lanes_env > 0 ? lanes_env : (max_n >= ((size_t)1 << 18) ? 3 : 6);
+    int want_lanes = lanes_env > 0 ? lanes_env : ((max_n >= ((size_t)1 << 18) && !lane_wait_polls()) ? 4 : 6);
     int n_lanes = (int)std::min<size_t>(count, (size_t)std::min(want_lanes, MAX_LANES));
     int rc = ensure_lanes(c, n_lanes);
     if (rc) return rc;
