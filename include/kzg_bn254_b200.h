@@ -186,6 +186,12 @@ int kzgb_stats(kzgb_ctx* ctx, double* acc_ms, uint64_t* acc_launches, uint64_t* 
  * the GPU).  Negative values keep the current setting.
  * Results never depend on it (exact group arithmetic); tests use it to force every code path. */
 int kzgb_msm_tuning(int batch_affine_levels, int min_avg_bucket, int pairs_per_thread);
+/* Process-wide switches that never change results, only which exact code path produces them:
+ *   "fs_device"            -1 auto (default), 0 host SHA-256 pool, 1 device kernel for the per-blob
+ *                          Fiat-Shamir challenges of kzgb_verify_batch_rlc (auto: >= 256 blobs of <= 2^13 Fr)
+ *   "batch_affine_levels"  as in kzgb_msm_tuning
+ * Unknown names return KZGB_ERR_GENERIC. */
+int kzgb_set_option(const char* name, long value);
 /* Fixed-base table in use: window bits c, windows W, points covered (0 = none). */
 int kzgb_msm_config(const kzgb_ctx* ctx, int* window_bits, int* windows, size_t* table_points);
 

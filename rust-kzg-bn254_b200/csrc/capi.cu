@@ -87,6 +87,8 @@ struct kzgb_ctx {
 namespace {
 
 std::mutex g_err_mu;
+// -1: choose per call, 0: host SHA-256 pool, 1: device kernel (verify_batch_rlc challenges)
+std::atomic<int> g_fs_device{getenv("KZGB_FS_DEVICE") ? atoi(getenv("KZGB_FS_DEVICE")) : -1};
 int fail(kzgb_ctx* c, int code, const std::string& msg) {
     if (c) { std::lock_guard<std::mutex> lk(g_err_mu); c->err = msg; }
     return code;
@@ -1151,11 +1153,15 @@ int kzgb_verify_batch_rlc(kzgb_ctx* c, const uint8_t* const* blobs, const size_t
     int rc = ensure_twiddles(c, log2_exact(max_n));
     if (rc) return rc;
     std::vector<Fr> zs(m), ys(m);
-    // host SHA-256 pool (one transcript per blob) runs while the blobs are uploaded and converted
-    std::atomic<size_t> next{0};
+    // Thousands of small transcripts: hash them on the GPU, one thread per blob, from the evaluations that
+    // are resident anyway (fs.cu).  Otherwise a host SHA-256 pool (one transcript per blob) runs while the
+    // blobs are uploaded and converted.
+    const int fs_opt = g_fs_device.load();
+    const bool fs_device = fs_opt >= 0 ? fs_opt != 0 : (m >= 256 && max_n <= ((size_t)1 << 13));
+    std::atomic<size_t> next{fs_device ? m : 0};
     std::vector<std::thread> hashers;
     {
-        size_t nt = std::max<size_t>(1, std::min<size_t>(m, hash_pool_threads() + 1));
+        size_t nt = fs_device ? 0 : std::max<size_t>(1, std::min<size_t>(m, hash_pool_threads() + 1));
         for (size_t t = 0; t < nt; t++)
             hashers.emplace_back([&]() {
                 for (;;) {
@@ -1185,7 +1191,7 @@ int kzgb_verify_batch_rlc(kzgb_ctx* c, const uint8_t* const* blobs, const size_t
         CK(c, L.evals.reserve(b * n * sizeof(Fr)));
         CK(c, L.bytes.reserve(b * n * 32));
         CK(c, L.eval_scratch.reserve(eval_quotient_scratch_elems((uint32_t)n, (uint32_t)b) * sizeof(Fr)));
-        CK(c, L.work.reserve(3 * b * sizeof(Fr)));
+        CK(c, L.work.reserve(4 * b * sizeof(Fr)));
         bool full = (uint64_t)b * n < 0xffffffffull;  // every blob fills its polynomial: one conversion launch
         for (size_t k = 0; k < b && full; k++) full = lens[i0 + k] == n * 32;
         for (size_t k = 0; k < b;) {
@@ -1202,11 +1208,22 @@ int kzgb_verify_batch_rlc(kzgb_ctx* c, const uint8_t* const* blobs, const size_t
         Fr* d_z = (Fr*)L.work.p;
         Fr* d_t = d_z + b;
         Fr* d_y = d_t + b;
-        std::vector<Fr> tinvs(b);
-        for (size_t k = 0; k < b; k++) tinvs[k] = eval_tinv(zs[i0 + k], logn);
-        CK(c, cudaMemcpyAsync(d_z, &zs[i0], b * sizeof(Fr), cudaMemcpyHostToDevice, L.st));
-        CK(c, cudaMemcpyAsync(d_t, tinvs.data(), b * sizeof(Fr), cudaMemcpyHostToDevice, L.st));
         Fr ninv = ninv_mont(logn);
+        std::vector<Fr> tinvs;
+        std::vector<uint8_t> cbytes;
+        if (fs_device) {
+            uint8_t* d_c32 = (uint8_t*)(d_y + b);
+            cbytes.resize(b * 32);
+            for (size_t k = 0; k < b; k++) serialize_compressed(Cs[i0 + k], &cbytes[32 * k]);
+            CK(c, cudaMemcpyAsync(d_c32, cbytes.data(), b * 32, cudaMemcpyHostToDevice, L.st));
+            fs_challenges_launch((Fr*)L.evals.p, (uint32_t)n, logn, (uint32_t)b, d_c32, &ninv, d_z, d_t, L.st);
+            CK(c, cudaMemcpyAsync(&zs[i0], d_z, b * sizeof(Fr), cudaMemcpyDeviceToHost, L.st));
+        } else {
+            tinvs.resize(b);
+            for (size_t k = 0; k < b; k++) tinvs[k] = eval_tinv(zs[i0 + k], logn);
+            CK(c, cudaMemcpyAsync(d_z, &zs[i0], b * sizeof(Fr), cudaMemcpyHostToDevice, L.st));
+            CK(c, cudaMemcpyAsync(d_t, tinvs.data(), b * sizeof(Fr), cudaMemcpyHostToDevice, L.st));
+        }
         eval_quotient_launch((Fr*)L.evals.p, (uint32_t)n, logn, (uint32_t)b, d_z, d_t, c->tw, c->logN, &ninv,
                              (Fr*)L.eval_scratch.p, nullptr, d_y, L.st);
         CK(c, cudaMemcpyAsync(&ys[i0], d_y, b * sizeof(Fr), cudaMemcpyDeviceToHost, L.st));
@@ -1399,6 +1416,13 @@ int kzgb_stats(kzgb_ctx* c, double* acc_ms, uint64_t* acc_launches, uint64_t* ac
     if (acc_point_adds) *acc_point_adds = na;
     return KZGB_OK;
 }
+int kzgb_set_option(const char* name, long value) {
+    if (!name) return KZGB_ERR_GENERIC;
+    if (!strcmp(name, "fs_device")) { g_fs_device.store((int)value); return KZGB_OK; }
+    if (!strcmp(name, "batch_affine_levels")) { msm_set_tuning((int)value, -1, -1); return KZGB_OK; }
+    return KZGB_ERR_GENERIC;
+}
+
 int kzgb_msm_tuning(int batch_affine_levels, int min_avg_bucket, int pairs_per_thread) {
     msm_set_tuning(batch_affine_levels, min_avg_bucket, pairs_per_thread);
     return KZGB_OK;

@@ -1,0 +1,119 @@
+// Fiat-Shamir challenges on the device for BATCHES OF SMALL BLOBS (verify_blob_kzg_proof_batch):
+//   z_i = SHA-256("EIGENDA_FSBLOBVERIFY_V1_" || u64_be(n) || n x Fr_be || serialize_compressed(C_i)) mod r
+// (reference primitives/src/helpers.rs:411-472, :382-390), one thread per blob, straight from the
+// evaluations that are already resident for the barycentric evaluation.  SHA-256 is sequential per
+// message, so this only pays when there are thousands of messages (4096 x 128 KiB in config 5); a
+// single 16 MiB transcript stays on a host core with SHA-NI.
+// Also derives, per blob, the one inverse the inversion-free evaluation kernels need:
+//   tinv_i = 1 / (z_i^n - 1), or z_i / n when z_i is in the domain (see eval_quotient_launch).
+#include "kzgb_internal.hpp"
+
+namespace kzgb {
+
+__constant__ uint32_t SHA_K[64] = {
+    0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5, 0xd807aa98, 0x12835b01,
+    0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174, 0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc,
+    0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da, 0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147,
+    0x06ca6351, 0x14292967, 0x27b70a85, 0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85,
+    0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070, 0x19a4c116, 0x1e376c08,
+    0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3, 0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208,
+    0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
+
+__device__ __forceinline__ uint32_t rotr(uint32_t x, int n) { return __funnelshift_r(x, x, n); }
+
+// one compression: w[0..15] = the block as big-endian words (destroyed)
+__device__ __forceinline__ void sha256_block(uint32_t h[8], uint32_t w[16]) {
+    uint32_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
+#pragma unroll
+    for (int t = 0; t < 64; t++) {
+        if (t >= 16) {
+            uint32_t w15 = w[(t + 1) & 15], w2 = w[(t + 14) & 15];
+            uint32_t s0 = rotr(w15, 7) ^ rotr(w15, 18) ^ (w15 >> 3);
+            uint32_t s1 = rotr(w2, 17) ^ rotr(w2, 19) ^ (w2 >> 10);
+            w[t & 15] = w[t & 15] + s0 + w[(t + 9) & 15] + s1;
+        }
+        uint32_t S1 = rotr(e, 6) ^ rotr(e, 11) ^ rotr(e, 25);
+        uint32_t ch = (e & f) ^ (~e & g);
+        uint32_t t1 = hh + S1 + ch + SHA_K[t] + w[t & 15];
+        uint32_t S0 = rotr(a, 2) ^ rotr(a, 13) ^ rotr(a, 22);
+        uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
+        uint32_t t2 = S0 + mj;
+        hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+    }
+    h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
+}
+
+// canonical big-endian words of a Montgomery element: word j = limb 7-j
+__device__ __forceinline__ void fr_to_be_words(uint32_t* w, const Fr& mont) {
+    Fr c; fe_from_mont(c, mont);
+#pragma unroll
+    for (int j = 0; j < 8; j++) w[j] = c.l[7 - j];
+}
+
+__global__ void __launch_bounds__(64) k_fs_challenges(const Fr* __restrict__ evals, uint32_t n, int logn, uint32_t batch,
+                                                       const uint8_t* __restrict__ commit32, Fr ninv,
+                                                       Fr* __restrict__ z_out, Fr* __restrict__ tinv_out) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= batch) return;
+    const Fr* f = evals + (size_t)k * n;
+    uint32_t h[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+    uint32_t w[16];
+    // item 0: "EIGENDA_FSBLOBVERIFY_V1_" || u64_be(n)
+    w[0] = 0x45494745; w[1] = 0x4e44415f; w[2] = 0x4653424c; w[3] = 0x4f425645; w[4] = 0x52494659; w[5] = 0x5f56315f;
+    w[6] = 0; w[7] = n;
+    // items 1..n: evaluations; item n+1: the commitment (arkworks compressed, taken as bytes)
+    fr_to_be_words(w + 8, fe_load_ro(&f[0]));
+    sha256_block(h, w);
+    uint32_t i = 1;
+    for (; i + 1 < n; i += 2) {
+        fr_to_be_words(w, fe_load_ro(&f[i]));
+        fr_to_be_words(w + 8, fe_load_ro(&f[i + 1]));
+        sha256_block(h, w);
+    }
+    uint32_t cw[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const uint8_t* p = commit32 + (size_t)k * 32 + 4 * j;
+        cw[j] = ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3];
+    }
+    const uint64_t bits = (64ull + 32ull * n) * 8ull;
+    if (i < n) {  // n even (>= 2): evaluation n-1 and the commitment share a block, padding gets its own
+        fr_to_be_words(w, fe_load_ro(&f[i]));
+#pragma unroll
+        for (int j = 0; j < 8; j++) w[8 + j] = cw[j];
+        sha256_block(h, w);
+#pragma unroll
+        for (int j = 0; j < 16; j++) w[j] = 0;
+        w[0] = 0x80000000u;
+    } else {      // n == 1: the commitment opens the last block, padding follows it
+#pragma unroll
+        for (int j = 0; j < 8; j++) w[j] = cw[j];
+#pragma unroll
+        for (int j = 8; j < 16; j++) w[j] = 0;
+        w[8] = 0x80000000u;
+    }
+    w[14] = (uint32_t)(bits >> 32); w[15] = (uint32_t)bits;
+    sha256_block(h, w);
+    // hash_to_field_element: digest as a big-endian integer mod r, to Montgomery form
+    Fr z;
+#pragma unroll
+    for (int j = 0; j < 8; j++) z.l[7 - j] = h[j];
+    fe_to_mont(z, z);
+    fe_store(&z_out[k], z);
+    Fr zn = z, one;
+    for (int s = 0; s < logn; s++) fe_sqr(zn, zn);
+    fe_one(one);
+    Fr t;
+    if (fe_eq(zn, one)) fe_mul(t, z, ninv);
+    else { fe_sub(zn, zn, one); fe_inv_fast(t, zn); }
+    fe_store(&tinv_out[k], t);
+}
+
+void fs_challenges_launch(const Fr* evals, uint32_t n, int logn, uint32_t batch, const uint8_t* commit32_dev,
+                          const Fr* ninv_mont_host, Fr* z_out, Fr* tinv_out, cudaStream_t st) {
+    if (!batch) return;
+    k_fs_challenges<<<(batch + 63) / 64, 64, 0, st>>>(evals, n, logn, batch, commit32_dev, *ninv_mont_host, z_out, tinv_out);
+    g_launch_count++;
+}
+
+}  // namespace kzgb

@@ -111,6 +111,11 @@ void eval_quotient_launch(const Fr* evals, uint32_t n, int logn, uint32_t batch,
                           const Fr* tinv_mont_dev, const Fr* tw, int logN, const Fr* ninv_mont_host, Fr* scratch,
                           Fr* q_out, Fr* y_out, cudaStream_t st);
 size_t eval_quotient_scratch_elems(uint32_t n, uint32_t batch);
+// Fiat-Shamir challenges of `batch` blobs of n evaluations each on the device (fs.cu; reference
+// primitives/src/helpers.rs:411-472): z_out[k] (Montgomery) and tinv_out[k] = 1/(z^n - 1) (or z/n in the
+// domain).  commit32_dev: batch x 32 bytes, arkworks-compressed commitments.
+void fs_challenges_launch(const Fr* evals, uint32_t n, int logn, uint32_t batch, const uint8_t* commit32_dev,
+                          const Fr* ninv_mont_host, Fr* z_out, Fr* tinv_out, cudaStream_t st);
 // out[i] = base^(first + i) (Montgomery), i < n
 void fr_powers_launch(Fr* out, uint32_t n, const Fr* base_mont_host, cudaStream_t st, uint32_t first = 0);
 // out[i] = a[i] * b[i]

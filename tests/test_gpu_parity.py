@@ -366,3 +366,30 @@ def test_g1_ifft_closed_form_large(pkg):
     for i in (0, 1, 2, 77, n // 2, n - 1):
         den = n * ((o.SYNTH_TAU * pow(w, -i, o.R) - 1) % o.R) % o.R
         assert lag[i] == o.g1_mul(o.G1_GEN, tn * o.fr_inv(den) % o.R), i
+
+
+def test_device_fiat_shamir_matches_host_and_oracle(pkg, ref_srs, ref_srs_points):
+    """The per-blob challenges of verify_blob_kzg_proof_batch hashed on the GPU (fs.cu, one thread per
+    transcript) against the host SHA-256 pool and the oracle: polynomial lengths 1, 2, 4, 64, 256
+    (odd / even block structure of the transcript), ragged and non-canonical blobs, identity commitment."""
+    rnd = random.Random(33)
+    eng = ref_srs.engine
+    raws = [b"x", b"y" * 31, b"ab" * 20, b"cd" * 40, g.gettysburg(), g.gettysburg()[:700], bytes(31 * 200), b"z",
+            bytes(rnd.getrandbits(8) for _ in range(31 * 256 - 7)), bytes(rnd.getrandbits(8) for _ in range(31 * 250))]
+    blobs = [pkg.Blob.from_raw_data(r) for r in raws]
+    blobs.append(pkg.Blob.from_unchecked(b"\xff" * 45 + bytes(range(50))))  # non-canonical, ragged
+    blobs.sort(key=lambda b: len(b))  # equal lengths adjacent -> batched chunks
+    cs, ps = pkg.KZG.commit_and_prove_blobs(blobs, ref_srs)
+    cpts = [o.g1_deserialize_compressed(c) for c in cs]
+    ppts = [o.g1_deserialize_compressed(p) for p in ps]
+    try:
+        pkg.lib.kzgb_set_option(b"fs_device", 1)
+        dev = pkg.verify_blob_kzg_proof_batch_rlc(blobs, cpts, ppts, eng)
+        pkg.lib.kzgb_set_option(b"fs_device", 0)
+        host = pkg.verify_blob_kzg_proof_batch_rlc(blobs, cpts, ppts, eng)
+    finally:
+        pkg.lib.kzgb_set_option(b"fs_device", -1)
+    assert dev == host
+    bo = [o.Blob.from_unchecked(b.data()) for b in blobs]
+    assert dev == o.verify_blob_kzg_proof_batch_rlc(bo, cpts, ppts)
+    assert pkg.lib.kzgb_set_option(b"no_such_option", 1) != 0
