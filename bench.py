@@ -186,7 +186,7 @@ def main():
     # synthetic SRS tau^i G generated on the GPU + fixed-base window tables (one-time setup)
     t_setup = time.perf_counter()
     srs = pkg.SRS.synthetic(n, TAU, engine=eng)
-    srs.precompute(n, 0)
+    srs.precompute(n, int(os.environ.get("KZGB_WINDOW_BITS", "0")))
     setup_s = time.perf_counter() - t_setup
     cbits, cwin, ctab = C.c_int(0), C.c_int(0), C.c_size_t(0)
     lib.kzgb_msm_config(eng.h, C.byref(cbits), C.byref(cwin), C.byref(ctab))
