@@ -45,6 +45,7 @@ struct MsmWorkspace {
     XYZZ* slice_sums;   // nbuckets / slice
     XYZZ* set_sums;     // sets (device), copied to host by the caller
     uint32_t* tile_tot; // scan tile totals (<= 1024)
+    uint32_t* long_list; // [0] counter, [1..] buckets spanning many accumulate chunks (k_bucket_fix_long)
     Affine* ba_pts[2];  // level outputs, ping-pong: max_entries/2 and max_entries/4 points
     Fq* ba_prefix;      // max_entries/2
     Fq* ba_others;      // one per thread of the widest level

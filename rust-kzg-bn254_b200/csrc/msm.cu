@@ -265,8 +265,17 @@ __global__ void __launch_bounds__(128, MINB) k_accumulate_t(const uint32_t* __re
     }
 }
 
+// Buckets whose entries span more than LONG_SPAN chunks (hot buckets: equal scalars, a top window with a
+// few possible digits, adversarial blobs) are queued for k_bucket_fix_long instead of being summed by one
+// thread: with 4 waves of chunks a single bucket can own thousands of partial sums.
+static constexpr uint32_t LONG_SPAN = 48;
+static constexpr int LONG_THREADS = 128;
+static constexpr uint32_t LONG_BLOCKS = 296;
+
 __global__ void __launch_bounds__(128) k_bucket_fix(const uint32_t* __restrict__ offsets, uint32_t nbuckets, uint32_t chunk, int shift,
-                                                     XYZZ* __restrict__ buckets, const XYZZ* __restrict__ partial) {
+                                                     XYZZ* __restrict__ buckets, const XYZZ* __restrict__ partial,
+                                                     uint32_t* __restrict__ long_count, uint32_t* __restrict__ long_list,
+                                                     uint32_t long_cap) {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nbuckets) return;
     uint32_t s = offsets[b] >> shift, e = offsets[b + 1] >> shift;
@@ -277,6 +286,10 @@ __global__ void __launch_bounds__(128) k_bucket_fix(const uint32_t* __restrict__
     }
     uint32_t t_lo = s / chunk, t_hi = (e - 1) / chunk;
     if (t_lo == t_hi) return;  // written directly by k_accumulate
+    if (t_hi - t_lo >= LONG_SPAN) {
+        uint32_t slot = atomicAdd(long_count, 1u);
+        if (slot < long_cap) { long_list[slot] = b; return; }  // (cap = every possible long bucket; never exceeded)
+    }
     XYZZ acc; xyzz_set_inf(acc);
     for (uint32_t t = t_lo; t <= t_hi; t++) {
         uint32_t slot = ((uint64_t)s <= (uint64_t)t * chunk) ? 0u : 1u;
@@ -284,6 +297,40 @@ __global__ void __launch_bounds__(128) k_bucket_fix(const uint32_t* __restrict__
         xyzz_add(acc, v);
     }
     xyzz_store(&buckets[b], acc);
+}
+
+// one block per queued bucket (grid-stride over the queue): strided partial sums per thread, then a
+// shared-memory tree
+__global__ void __launch_bounds__(LONG_THREADS) k_bucket_fix_long(const uint32_t* __restrict__ offsets, uint32_t chunk, int shift,
+                                                                   XYZZ* __restrict__ buckets, const XYZZ* __restrict__ partial,
+                                                                   const uint32_t* __restrict__ long_count,
+                                                                   const uint32_t* __restrict__ long_list, uint32_t long_cap) {
+    __shared__ XYZZ sm[LONG_THREADS];
+    uint32_t count = *long_count;
+    if (count > long_cap) count = long_cap;
+    for (uint32_t q = blockIdx.x; q < count; q += gridDim.x) {
+        const uint32_t b = long_list[q];
+        const uint32_t s = offsets[b] >> shift, e = offsets[b + 1] >> shift;
+        const uint32_t t_lo = s / chunk, t_hi = (e - 1) / chunk;
+        XYZZ acc; xyzz_set_inf(acc);
+        for (uint32_t t = t_lo + threadIdx.x; t <= t_hi; t += LONG_THREADS) {
+            uint32_t slot = ((uint64_t)s <= (uint64_t)t * chunk) ? 0u : 1u;
+            XYZZ v = xyzz_load(&partial[2 * t + slot]);
+            xyzz_add(acc, v);
+        }
+        sm[threadIdx.x] = acc;
+        __syncthreads();
+        for (uint32_t w = LONG_THREADS / 2; w >= 1; w >>= 1) {
+            if (threadIdx.x < w) {
+                XYZZ x = sm[threadIdx.x], y = sm[threadIdx.x + w];
+                xyzz_add(x, y);
+                sm[threadIdx.x] = x;
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) xyzz_store(&buckets[b], sm[0]);
+        __syncthreads();
+    }
 }
 
 // ---------------------------------------------------------------------------------
@@ -687,6 +734,7 @@ size_t msm_workspace_bytes(const MsmPlan& p) {
     b += align_up((size_t)(p.nbuckets / p.slice) * sizeof(XYZZ));  // tree ping-pong
     b += align_up((size_t)p.sets * sizeof(XYZZ));
     b += align_up(1024 * 4);  // scan tile totals
+    b += align_up(((size_t)p.acc_threads / LONG_SPAN + 8) * 4);  // long-bucket queue (+ its counter)
     if (p.ba_levels) {
         uint32_t mb = ba_max_blocks(p);
         b += align_up((size_t)(p.max_entries / 2 + 1) * sizeof(Affine));
@@ -709,6 +757,7 @@ void msm_workspace_carve(const MsmPlan& p, void* base, MsmWorkspace* ws) {
     ws->slice_sums = (XYZZ*)c; c += 2 * align_up((size_t)(p.nbuckets / p.slice) * sizeof(XYZZ));
     ws->set_sums = (XYZZ*)c; c += align_up((size_t)p.sets * sizeof(XYZZ));
     ws->tile_tot = (uint32_t*)c; c += align_up(1024 * 4);
+    ws->long_list = (uint32_t*)c; c += align_up(((size_t)p.acc_threads / LONG_SPAN + 8) * 4);
     ws->ba_pts[0] = ws->ba_pts[1] = nullptr;
     ws->ba_prefix = ws->ba_others = ws->ba_blk_tot = ws->ba_blk_inv = nullptr;
     if (p.ba_levels) {
@@ -791,7 +840,16 @@ void msm_launch(const MsmPlan& p, const MsmWorkspace& ws, const Fr* scalars, boo
     }
     if (ev_acc_end) cudaEventRecord(ev_acc_end, sa);
     if (split) { cudaEventRecord(ev_join, sa); cudaStreamWaitEvent(st, ev_join, 0); }
-    k_bucket_fix<<<(p.nbuckets + 127) / 128, 128, 0, st>>>(ws.hist, p.nbuckets, p.chunk, L, ws.buckets, ws.partial);
+    {
+        const uint32_t long_cap = p.acc_threads / LONG_SPAN + 4;  // a long bucket owns >= LONG_SPAN chunks
+        uint32_t* long_count = ws.long_list;                      // [0] = counter, [1..] = queue
+        cudaMemsetAsync(long_count, 0, 4, st);
+        k_bucket_fix<<<(p.nbuckets + 127) / 128, 128, 0, st>>>(ws.hist, p.nbuckets, p.chunk, L, ws.buckets, ws.partial,
+                                                                long_count, ws.long_list + 1, long_cap);
+        k_bucket_fix_long<<<LONG_BLOCKS, LONG_THREADS, 0, st>>>(ws.hist, p.chunk, L, ws.buckets, ws.partial, long_count,
+                                                                  ws.long_list + 1, long_cap);
+        g_launch_count++;
+    }
     uint32_t nslices = p.nbuckets / p.slice;
     k_reduce_slices<<<(nslices + 127) / 128, 128, 0, st>>>(ws.buckets, p, ws.slice_sums);
     // tree-reduce each set's slice results down to one point
