@@ -502,6 +502,44 @@ void ref_proof_at(const uint64_t* evals, size_t n, const uint64_t z[4], const ui
 }
 void ref_fr_inv(const uint64_t a[4], uint64_t out[4]) { Fp x; memcpy(x.v, a, 32); Fp r = inv<FR>(x); memcpy(out, r.v, 32); }
 void ref_fq_inv(const uint64_t a[4], uint64_t out[4]) { Fp x; memcpy(x.v, a, 32); Fp r = inv<FQ>(x); memcpy(out, r.v, 32); }
+// evaluate_polynomial_in_evaluation_form (helpers.rs:475-535) and compute_challenge (helpers.rs:411-472) alone
+void ref_evaluate(const uint64_t* evals, size_t n, const uint64_t z[4], uint64_t y_out[4]) {
+    std::vector<Fp> ev((const Fp*)evals, (const Fp*)evals + n);
+    Fp zz; memcpy(zz.v, z, 32);
+    Fp y = evaluate(ev, zz);
+    memcpy(y_out, y.v, 32);
+}
+void ref_challenge(const uint8_t* blob, size_t len, const uint64_t commitment[8], uint64_t z_out[4]) {
+    std::vector<Fp> ev = to_fr_array_padded(blob, len);
+    Aff c; memcpy(&c, commitment, 64);
+    Fp z = compute_challenge(ev, c);
+    memcpy(z_out, z.v, 32);
+}
+// read_g1_point_from_bytes_be (helpers.rs:175-226) for n points, `threads` workers as prover/src/srs.rs:86-103;
+// returns 0, or 1 + the index of the first point that is not on the curve
+size_t ref_srs_decompress(const uint8_t* bytes, size_t n, int threads, uint64_t* out_xy) {
+    static const uint64_t SQRT_EXP[4] = {0x4f082305b61f3f52ull, 0x65e05aa45a1c72a3ull, 0x6e14116da0605617ull, 0x0c19139cb84c680aull};  // (p+1)/4
+    std::atomic<size_t> bad{0};
+    Aff* out = (Aff*)out_xy;
+    parallel_for(n, threads, [&](size_t i) {
+        const uint8_t* b = bytes + 32 * i;
+        uint8_t flag = b[0] & 0xC0;
+        if (flag == 0x40) { memset(&out[i], 0, 64); return; }
+        uint8_t xb[32]; memcpy(xb, b, 32); xb[0] &= 0x3F;
+        Fp xc;
+        for (int k = 0; k < 4; k++) { uint64_t w = 0; for (int j = 0; j < 8; j++) w = (w << 8) | xb[8 * (3 - k) + j]; xc.v[k] = w; }
+        Fp x = to_mont<FQ>(xc);
+        Fp three = add<FQ>(add<FQ>(one<FQ>(), one<FQ>()), one<FQ>());
+        Fp rhs = add<FQ>(mul<FQ>(sqr<FQ>(x), x), three);
+        Fp y = one<FQ>();
+        for (int k = 3; k >= 0; k--) for (int bit = 63; bit >= 0; bit--) { y = sqr<FQ>(y); if ((SQRT_EXP[k] >> bit) & 1) y = mul<FQ>(y, rhs); }
+        if (!eq(sqr<FQ>(y), rhs)) { size_t cur = bad.load(); while ((cur == 0 || i + 1 < cur) && !bad.compare_exchange_weak(cur, i + 1)) {} return; }
+        bool largest = lex_largest(y);
+        if ((flag == 0xC0) != largest && flag != 0) y = neg<FQ>(y);
+        out[i].x = x; out[i].y = y;
+    });
+    return bad.load();
+}
 int ref_hw_threads() { return (int)std::thread::hardware_concurrency(); }
 
 }  // extern "C"

@@ -101,3 +101,29 @@ def test_commit_and_proof(olib):
         olib.ref_proof_at(fr_bytes(ev), C.c_size_t(64), fr_bytes([roots[idx]]), aff_bytes(pts[:64]), 2, pf, yo)
         assert aff_from(pf.raw) == (x, y)
         assert fr_from(yo.raw)[0] == ev[idx]
+
+
+def test_srs_decompress_evaluate_challenge_exports(olib):
+    """The C++ oracle's SRS decompression (helpers.rs:175-226) against srs.g1.points.string, and its
+    stand-alone evaluate / challenge exports against the big-int oracle."""
+    olib.ref_srs_decompress.restype = C.c_size_t
+    raw = g.g1_point_bytes()
+    n = 3000
+    out = C.create_string_buffer(64 * n)
+    assert olib.ref_srs_decompress(raw, C.c_size_t(n), 4, out) == 0
+    pts = g.srs_points_string()
+    assert [aff_from(out.raw[64 * i : 64 * i + 64]) for i in range(n)] == pts
+    inf = bytes([0x40]) + bytes(31)
+    assert olib.ref_srs_decompress(inf + raw[:32], C.c_size_t(2), 1, out) == 0
+    assert aff_from(out.raw[:64]) is None and aff_from(out.raw[64:128]) == pts[0]
+    bo = o.Blob.from_raw_data(g.gettysburg())
+    po = bo.to_polynomial_eval_form()
+    rnd = random.Random(9)
+    z = rnd.randrange(o.R)
+    y = C.create_string_buffer(32)
+    olib.ref_evaluate(fr_bytes(po.evaluations), C.c_size_t(len(po.evaluations)), fr_bytes([z]), y)
+    assert fr_from(y.raw) == [o.evaluate_polynomial_in_evaluation_form(po, z)]
+    c = o.KZG().commit_blob(bo, pts[:64])
+    zc = C.create_string_buffer(32)
+    olib.ref_challenge(bo.blob_data, C.c_size_t(len(bo.blob_data)), aff_bytes([c]), zc)
+    assert fr_from(zc.raw) == [o.compute_challenge(bo, c)]
