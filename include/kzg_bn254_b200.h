@@ -75,6 +75,14 @@ int kzgb_srs_get_affine_mont(kzgb_ctx* ctx, size_t start, size_t count, uint64_t
 /* Build the fixed-base window tables (2^(c*w) * P_i) for MSMs of up to `max_n` points.  Called lazily
  * by the first commit if the caller does not; window_bits = 0 picks c from max_n. */
 int kzgb_srs_precompute(kzgb_ctx* ctx, size_t max_n, int window_bits);
+/* Build the Lagrange-basis window table for evaluation-form polynomials of exactly n = 2^k elements:
+ * L = IFFT_G1(SRS[..n]) -- the points KZG::commit_eval_form recomputes with g1_ifft on EVERY call
+ * (kzg.rs:98) -- computed once per size on the GPU and kept resident with their window shifts, so that
+ * commit_eval_form / commit_blob / compute_proof* are one MSM on the evaluations themselves with no
+ * Fr NTT on the path.  Called lazily by the first evaluation-form commit of a size if the caller does not
+ * (option "lagrange", default on); without the table those calls use Fr-IFFT + the monomial table.
+ * Same group element either way.  Err KZGB_ERR_FFT / KZGB_ERR_SRS_CAPACITY as kzgb_g1_ifft. */
+int kzgb_srs_prepare_lagrange(kzgb_ctx* ctx, size_t n);
 
 /* ---- MSM (ark-ec VariableBaseMSM::msm call sites) ---------------------------------------- */
 /* sum scalars[i] * SRS[i], i < n.  Replaces G1Projective::msm(&srs.g1[..n], coeffs) in
@@ -190,6 +198,11 @@ int kzgb_msm_tuning(int batch_affine_levels, int min_avg_bucket, int pairs_per_t
  *   "fs_device"            -1 auto (default), 0 host SHA-256 pool, 1 device kernel for the per-blob
  *                          Fiat-Shamir challenges of kzgb_verify_batch_rlc (auto: >= 256 blobs of <= 2^13 Fr)
  *   "batch_affine_levels"  as in kzgb_msm_tuning
+ *   "group"                -1 (default): kzgb_commit_and_prove_blobs processes runs of equal-size blobs of
+ *                          <= 2^17 Fr as groups (one batched launch set per phase and group, sized so a group
+ *                          holds <= 2^21 Fr and <= 64 blobs); 0: one blob at a time; k > 0: k blobs per group
+ *   "lagrange"             1 (default): evaluation-form commits/proofs build and use the Lagrange-basis
+ *                          table of their size (kzgb_srs_prepare_lagrange); 0: Fr-IFFT + monomial table
  * Unknown names return KZGB_ERR_GENERIC. */
 int kzgb_set_option(const char* name, long value);
 /* Fixed-base table in use: window bits c, windows W, points covered (0 = none). */

@@ -389,6 +389,11 @@ class SRS:
     def precompute(self, max_n: int = 0, window_bits: int = 0) -> None:
         self.engine.check(lib.kzgb_srs_precompute(self.engine.h, max_n, window_bits))
 
+    def prepare_lagrange(self, n: int) -> None:
+        """Resident Lagrange-basis window table for evaluation-form polynomials of n elements: the cached
+        equivalent of the g1_ifft that KZG::commit_eval_form runs on every call (prover/src/kzg.rs:98)."""
+        self.engine.check(lib.kzgb_srs_prepare_lagrange(self.engine.h, n))
+
 
 class KZG:
     """prover/src/kzg.rs:25-309."""

@@ -38,6 +38,7 @@ SIGNATURES = {
     "kzgb_srs_len": (C.c_size_t, [ctx_p]),
     "kzgb_srs_get_affine_mont": (C.c_int, [ctx_p, C.c_size_t, C.c_size_t, buf, buf]),
     "kzgb_srs_precompute": (C.c_int, [ctx_p, C.c_size_t, C.c_int]),
+    "kzgb_srs_prepare_lagrange": (C.c_int, [ctx_p, C.c_size_t]),
     "kzgb_msm_srs": (C.c_int, [ctx_p, buf, C.c_size_t, buf, u8p]),
     "kzgb_msm_srs_range": (C.c_int, [ctx_p, buf, C.c_size_t, C.c_size_t, buf, u8p]),
     "kzgb_msm_srs_range_dev": (C.c_int, [ctx_p, buf, C.c_size_t, C.c_size_t, buf, u8p]),

@@ -76,6 +76,9 @@ struct kzgb_ctx {
     size_t wt_n = 0;
     int wt_c = 0, wt_W = 0;
     bool auto_precompute = true;
+    // Lagrange-basis tables, one per domain size 2^k: window table over L = IFFT_G1(SRS[..2^k]) so that
+    // evaluation-form commitments are ONE MSM on the evaluations themselves (no Fr NTT on the path)
+    struct LagTable { Affine* table = nullptr; size_t n = 0; int c = 0, W = 0; } lag[29];
     DevBuf batch_bytes;  // blob bytes of the batch in flight (commit_and_prove_blobs)
     // twiddles
     Fr* tw = nullptr;
@@ -89,6 +92,10 @@ namespace {
 std::mutex g_err_mu;
 // -1: choose per call, 0: host SHA-256 pool, 1: device kernel (verify_batch_rlc challenges)
 std::atomic<int> g_fs_device{getenv("KZGB_FS_DEVICE") ? atoi(getenv("KZGB_FS_DEVICE")) : -1};
+// 1: evaluation-form commitments use a Lagrange-basis window table (built on first use per size), 0: Fr-IFFT + monomial table
+// -1: KZGB_GROUP env / auto, 0: one blob at a time, > 0: blobs per group in the small-blob batch path
+std::atomic<int> g_group{-1};
+std::atomic<int> g_lagrange{getenv("KZGB_LAGRANGE") ? atoi(getenv("KZGB_LAGRANGE")) : 1};
 int fail(kzgb_ctx* c, int code, const std::string& msg) {
     if (c) { std::lock_guard<std::mutex> lk(g_err_mu); c->err = msg; }
     return code;
@@ -270,31 +277,84 @@ int ensure_twiddles(kzgb_ctx* c, int logn) {
 }
 
 // ---------------------------------------------------------------- SRS tables
+// Window table over `points` (n affine points on the device): table[w*n + i] = 2^(c*w) * points[i].
+int build_window_table(kzgb_ctx* c, const Affine* points, size_t n, int cb, size_t reusable_bytes, Affine** out, int* W_out) {
+    if (cb < 2 || cb > 24) return fail(c, KZGB_ERR_GENERIC, "window_bits out of range");
+    int W = (255 + cb - 1) / cb;
+    size_t bytes = (size_t)W * n * sizeof(Affine);
+    size_t free_b = 0, total_b = 0;
+    CK(c, cudaMemGetInfo(&free_b, &total_b));
+    if (bytes + (2ull << 30) > free_b + reusable_bytes)
+        return fail(c, KZGB_ERR_DEVICE, "not enough device memory for the fixed-base window tables");
+    Lane& L = c->lanes[0];
+    Affine* table = nullptr;
+    CK(c, cudaMalloc((void**)&table, bytes));
+    cudaError_t e = cudaMemcpyAsync(table, points, n * sizeof(Affine), cudaMemcpyDeviceToDevice, L.st);
+    uint32_t batch = (uint32_t)std::min<size_t>(n, (size_t)1 << 18);
+    DevBuf scratch;
+    if (e == cudaSuccess) e = scratch.reserve(srs_precompute_scratch_bytes(batch, W));
+    if (e == cudaSuccess) {
+        srs_precompute_launch(table, (uint32_t)n, (uint32_t)n, cb, W, (XYZZ*)scratch.p, batch, L.st);
+        e = cudaStreamSynchronize(L.st);
+    }
+    scratch.release();
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) { cudaFree(table); CK(c, e); }
+    *out = table; *W_out = W;
+    return KZGB_OK;
+}
+
 int do_precompute(kzgb_ctx* c, size_t max_n, int window_bits) {
     if (max_n > c->srs_n) max_n = c->srs_n;
     if (max_n == 0) return KZGB_OK;
     int cb = window_bits > 0 ? window_bits : choose_c_fixed(max_n);
-    if (cb < 2 || cb > 24) return fail(c, KZGB_ERR_GENERIC, "window_bits out of range");
-    int W = (255 + cb - 1) / cb;
-    size_t bytes = (size_t)W * max_n * sizeof(Affine);
-    size_t free_b = 0, total_b = 0;
-    CK(c, cudaMemGetInfo(&free_b, &total_b));
-    if (bytes + (2ull << 30) > free_b + (c->wtable ? (size_t)c->wt_W * c->wt_n * sizeof(Affine) : 0))
-        return fail(c, KZGB_ERR_DEVICE, "not enough device memory for the fixed-base window tables");
-    Lane& L = c->lanes[0];
     for (int i = 0; i < c->n_lanes; i++) CK(c, cudaStreamSynchronize(c->lanes[i].st));
+    size_t reusable = c->wtable ? (size_t)c->wt_W * c->wt_n * sizeof(Affine) : 0;
     if (c->wtable) { cudaFree(c->wtable); c->wtable = nullptr; c->wt_n = 0; }
-    CK(c, cudaMalloc((void**)&c->wtable, bytes));
-    CK(c, cudaMemcpyAsync(c->wtable, c->srs, max_n * sizeof(Affine), cudaMemcpyDeviceToDevice, L.st));
-    uint32_t batch = (uint32_t)std::min<size_t>(max_n, (size_t)1 << 18);
-    DevBuf scratch;
-    CK(c, scratch.reserve(srs_precompute_scratch_bytes(batch, W)));
-    srs_precompute_launch(c->wtable, (uint32_t)max_n, (uint32_t)max_n, cb, W, (XYZZ*)scratch.p, batch, L.st);
+    Affine* table = nullptr;
+    int W = 0;
+    int rc = build_window_table(c, c->srs, max_n, cb, reusable, &table, &W);
+    if (rc) return rc;
+    c->wtable = table; c->wt_n = max_n; c->wt_c = cb; c->wt_W = W;
+    return KZGB_OK;
+}
+
+void lagrange_release(kzgb_ctx* c) {
+    for (auto& t : c->lag) { if (t.table) cudaFree(t.table); t = kzgb_ctx::LagTable(); }
+}
+
+// Lagrange-basis window table for the domain of size n = 2^logn: L = IFFT_G1(SRS[..n]) (the points
+// KZG::commit_eval_form recomputes on every call, kzg.rs:98), then the same window shifts as the
+// monomial table.  One G1 inverse NTT per size and context; MSM(L, evals) is the eval-form commitment.
+// Returns KZGB_OK with no table (t.table == nullptr) when the feature is off or memory is short.
+int ensure_lagrange(kzgb_ctx* c, int logn) {
+    if (logn < 1 || logn > 28) return KZGB_OK;
+    kzgb_ctx::LagTable& t = c->lag[logn];
+    if (t.table) return KZGB_OK;
+    const size_t n = (size_t)1 << logn;
+    if (!g_lagrange.load() || !c->auto_precompute || n > c->srs_n || n > ((size_t)1 << 22)) return KZGB_OK;
+    int rc = ensure_twiddles(c, logn);
+    if (rc) return rc;
+    for (int i = 0; i < c->n_lanes; i++) CK(c, cudaStreamSynchronize(c->lanes[i].st));
+    Lane& L = c->lanes[0];
+    DevBuf work, pts;
+    if (work.reserve(n * sizeof(XYZZ)) != cudaSuccess || pts.reserve(n * sizeof(Affine)) != cudaSuccess) {
+        cudaGetLastError(); work.release(); pts.release();
+        return KZGB_OK;
+    }
+    Fr ninv = ninv_mont(logn), ninv_canon;
+    fe_from_mont(ninv_canon, ninv);
+    g1_intt_launch(c->srs, logn, (XYZZ*)work.p, (Affine*)pts.p, c->tw, c->logN, &ninv_canon, L.st);
     cudaError_t e = cudaStreamSynchronize(L.st);
-    scratch.release();
-    CK(c, e);
-    CK(c, cudaGetLastError());
-    c->wt_n = max_n; c->wt_c = cb; c->wt_W = W;
+    work.release();
+    if (e != cudaSuccess) { pts.release(); CK(c, e); }
+    Affine* table = nullptr;
+    int W = 0, cb = (c->wtable && c->wt_n == n) ? c->wt_c : choose_c_fixed(n);  // an explicit window override carries over
+    rc = build_window_table(c, (const Affine*)pts.p, n, cb, 0, &table, &W);
+    pts.release();
+    if (rc == KZGB_ERR_DEVICE) { cudaGetLastError(); return KZGB_OK; }  // short of memory: stay on the monomial path
+    if (rc) return rc;
+    t.table = table; t.n = n; t.c = cb; t.W = W;
     return KZGB_OK;
 }
 
@@ -302,6 +362,7 @@ int srs_install(kzgb_ctx* c, Affine* dev_points, size_t n) {
     for (int i = 0; i < c->n_lanes; i++) cudaStreamSynchronize(c->lanes[i].st);
     if (c->srs) cudaFree(c->srs);
     if (c->wtable) { cudaFree(c->wtable); c->wtable = nullptr; c->wt_n = 0; }
+    lagrange_release(c);
     c->srs = dev_points;
     c->srs_n = n;
     return KZGB_OK;
@@ -314,12 +375,16 @@ struct MsmJob {
 };
 
 // Enqueue an MSM on lane L.  bases == nullptr: over the SRS range [first, first+n).
+// lag != nullptr: over the Lagrange-basis table of the domain of size n instead.
 int msm_enqueue(kzgb_ctx* c, Lane& L, const Fr* d_scalars, bool canonical, size_t first, size_t n,
-                const Affine* var_bases, MsmJob* job) {
+                const Affine* var_bases, MsmJob* job, const kzgb_ctx::LagTable* lag = nullptr) {
     if (n == 0) { job->active = false; return KZGB_OK; }
     MsmPlan p;
     const Affine* table;
-    if (!var_bases) {
+    if (lag) {
+        p = msm_make_plan((uint32_t)n, lag->c, true, (uint32_t)lag->n, 0);
+        table = lag->table;
+    } else if (!var_bases) {
         if (first + n > c->srs_n) return fail(c, KZGB_ERR_GENERIC, "MSM range exceeds the SRS");
         if (c->auto_precompute && (!c->wtable || first + n > c->wt_n) && c->srs_n <= ((size_t)1 << 22)) {
             size_t want = std::min(c->srs_n, next_pow2(first + n));
@@ -352,12 +417,10 @@ int msm_enqueue(kzgb_ctx* c, Lane& L, const Fr* d_scalars, bool canonical, size_
 }
 
 bool lane_wait_polls();
-// Wait for the lane and finish on the host: Horner over the window sums, then to affine.
-int msm_finish(kzgb_ctx* c, Lane& L, const MsmJob& job, Affine* out) {
-    if (!job.active) { aff_set_inf(*out); return KZGB_OK; }
-    // Spinning wait by default (a blocking-sync event costs ~0.3 ms per MSM in wake-up latency).  When the
-    // ranks on this host have more lane threads than spare cores, spinning lanes starve the SHA-256
-    // pool (8 GPUs x 4 lanes on 32 cores): poll with short sleeps instead.
+// Wait for everything queued on the lane.  Spinning by default (a blocking-sync event costs ~0.3 ms per
+// MSM in wake-up latency).  When the ranks on this host have more lane threads than spare cores, spinning
+// lanes starve the SHA-256 pool (8 GPUs x 4 lanes on 32 cores): poll with short sleeps instead.
+int lane_wait(kzgb_ctx* c, Lane& L) {
     if (lane_wait_polls()) {
         CK(c, cudaEventRecord(L.ev_done, L.st));
         for (;;) {
@@ -371,6 +434,12 @@ int msm_finish(kzgb_ctx* c, Lane& L, const MsmJob& job, Affine* out) {
         CK(c, cudaStreamSynchronize(L.st));
     }
     CK(c, cudaGetLastError());
+    return KZGB_OK;
+}
+// Wait for the lane and finish on the host: Horner over the window sums, then to affine.
+int msm_finish(kzgb_ctx* c, Lane& L, const MsmJob& job, Affine* out) {
+    if (!job.active) { aff_set_inf(*out); return KZGB_OK; }
+    { int rc = lane_wait(c, L); if (rc) return rc; }
     lane_collect_acc(L);
     const MsmPlan& p = job.plan;
     XYZZ acc = L.h_sets[p.sets - 1];
@@ -390,10 +459,52 @@ int msm_blocking(kzgb_ctx* c, Lane& L, const Fr* d_scalars, bool canonical, size
     return msm_finish(c, L, job, out);
 }
 
+// `batch` independent fixed-base MSMs of n_per scalars each in ONE set of launches (one bucket set per
+// MSM): d_scalars holds batch * n_per scalars back to back.  Over the Lagrange-basis table `lag`, or the
+// monomial window table when lag == nullptr.  Small polynomials are latency-bound one at a time (bucket
+// reduction tail, host hand-off per MSM); batched they fill the GPU.
+int msm_enqueue_batched(kzgb_ctx* c, Lane& L, const Fr* d_scalars, size_t n_per, size_t batch,
+                        const kzgb_ctx::LagTable* lag, MsmJob* job) {
+    if (n_per == 0 || batch == 0) { job->active = false; return KZGB_OK; }
+    if (batch > (size_t)MAX_SETS) return fail(c, KZGB_ERR_GENERIC, "too many MSMs in one batch");
+    const Affine* table;
+    MsmPlan p;
+    if (lag) {
+        p = msm_make_plan((uint32_t)(n_per * batch), lag->c, true, (uint32_t)lag->n, 0, (uint32_t)batch);
+        table = lag->table;
+    } else {
+        if (!c->wtable || n_per > c->wt_n) return fail(c, KZGB_ERR_GENERIC, "batched MSM needs a fixed-base table");
+        p = msm_make_plan((uint32_t)(n_per * batch), c->wt_c, true, (uint32_t)c->wt_n, 0, (uint32_t)batch);
+        table = c->wtable;
+    }
+    if ((uint64_t)n_per * batch * p.W >= 0xfff00000ull) return fail(c, KZGB_ERR_GENERIC, "MSM too large for one launch");
+    CK(c, L.msm_ws.reserve(msm_workspace_bytes(p)));
+    MsmWorkspace ws;
+    msm_workspace_carve(p, L.msm_ws.p, &ws);
+    lane_collect_acc(L);
+    msm_launch(p, ws, d_scalars, false, table, L.st, L.ev0, L.ev1, L.st_acc, L.ev_fork, L.ev_join);
+    L.ev_pending = true;
+    L.acc_adds += (uint64_t)n_per * batch * p.W;
+    CK(c, cudaMemcpyAsync(L.h_sets, ws.set_sums, sizeof(XYZZ) * p.sets, cudaMemcpyDeviceToHost, L.st));
+    job->plan = p;
+    job->active = true;
+    return KZGB_OK;
+}
+int msm_finish_batched(kzgb_ctx* c, Lane& L, const MsmJob& job, size_t batch, Affine* outs) {
+    if (!job.active) { for (size_t k = 0; k < batch; k++) aff_set_inf(outs[k]); return KZGB_OK; }
+    int rc = lane_wait(c, L);
+    if (rc) return rc;
+    lane_collect_acc(L);
+    for (size_t k = 0; k < batch; k++) xyzz_to_affine(outs[k], L.h_sets[k]);
+    return KZGB_OK;
+}
+
 // ---------------------------------------------------------------- polynomial pipeline pieces
 // d_evals (n Fr, Montgomery) -> commitment.  Uses L.work / L.ntt_scratch.
 int commit_evals_enqueue(kzgb_ctx* c, Lane& L, const Fr* d_evals, size_t n, MsmJob* job) {
     int logn = log2_exact(n);
+    if (logn <= 28 && c->lag[logn].table && g_lagrange.load())  // Lagrange-basis table resident: the evaluations ARE the scalars
+        return msm_enqueue(c, L, d_evals, false, 0, n, nullptr, job, &c->lag[logn]);
     int rc = ensure_twiddles(c, logn);
     if (rc) return rc;
     CK(c, L.work.reserve(n * sizeof(Fr)));
@@ -422,6 +533,8 @@ int proof_enqueue(kzgb_ctx* c, Lane& L, const Fr* d_evals, size_t n, const Fr& z
     Fr ninv = ninv_mont(logn);
     eval_quotient_launch(d_evals, (uint32_t)n, logn, 1, d_z, d_z + 1, c->tw, c->logN, &ninv, (Fr*)L.eval_scratch.p,
                          (Fr*)L.work.p, d_y, L.st);
+    if (c->lag[logn].table && g_lagrange.load())  // quotient in evaluation form against the Lagrange-basis table
+        return msm_enqueue(c, L, (Fr*)L.work.p, false, 0, n, nullptr, job, &c->lag[logn]);
     ntt_launch((Fr*)L.work.p, logn, 1, true, c->tw, c->logN, &ninv, (Fr*)L.ntt_scratch.p, L.st);
     return msm_enqueue(c, L, (Fr*)L.work.p, false, 0, n, nullptr, job);
 }
@@ -560,6 +673,7 @@ void kzgb_ctx_destroy(kzgb_ctx* c) {
     for (int i = 0; i < c->n_lanes; i++) { cudaStreamSynchronize(c->lanes[i].st); lane_destroy(c->lanes[i]); }
     if (c->srs) cudaFree(c->srs);
     if (c->wtable) cudaFree(c->wtable);
+    lagrange_release(c);
     if (c->tw) cudaFree(c->tw);
     c->batch_bytes.release();
     if (c->t0) cudaEventDestroy(c->t0);
@@ -669,10 +783,26 @@ int kzgb_srs_precompute(kzgb_ctx* c, size_t max_n, int window_bits) {
         c->auto_precompute = false;
         for (int i = 0; i < c->n_lanes; i++) cudaStreamSynchronize(c->lanes[i].st);
         if (c->wtable) { cudaFree(c->wtable); c->wtable = nullptr; c->wt_n = 0; }
+        lagrange_release(c);
         return KZGB_OK;
     }
     if (!c->srs_n) return fail(c, KZGB_ERR_GENERIC, "no SRS loaded");
     return do_precompute(c, max_n ? max_n : c->srs_n, window_bits);
+}
+
+int kzgb_srs_prepare_lagrange(kzgb_ctx* c, size_t n) {
+    Guard g(c);
+    if (n == 0 || (n & (n - 1))) return fail(c, KZGB_ERR_FFT, "length provided is not a power of 2");
+    if (n > c->srs_n) {
+        char msg[160];
+        snprintf(msg, sizeof msg, "SRS capacity exceeded: polynomial_len=%zu srs_len=%zu", n, c->srs_n);
+        return fail(c, KZGB_ERR_SRS_CAPACITY, msg);
+    }
+    int logn = log2_exact(n);
+    int rc = ensure_lagrange(c, logn);
+    if (rc) return rc;
+    if (logn >= 1 && !c->lag[logn].table) return fail(c, KZGB_ERR_DEVICE, "Lagrange-basis table not built (disabled, or not enough device memory)");
+    return KZGB_OK;
 }
 
 // ------------------------------------------------------------------------------- MSM
@@ -816,6 +946,8 @@ int kzgb_commit_eval(kzgb_ctx* c, const uint64_t* evals, size_t n, uint64_t out_
         return fail(c, KZGB_ERR_SRS_CAPACITY, msg);
     }
     if (n == 0 || (n & (n - 1))) return fail(c, KZGB_ERR_FFT, "length provided is not a power of 2");  // kzg.rs:265-269
+    int rc = ensure_lagrange(c, log2_exact(n));
+    if (rc) return rc;
     return commit_evals_host(c, evals, n, out_xy, out_inf);
 }
 
@@ -834,7 +966,9 @@ int kzgb_commit_blob(kzgb_ctx* c, const uint8_t* blob, size_t len, uint64_t out_
         snprintf(msg, sizeof msg, "SRS capacity exceeded: polynomial_len=%zu srs_len=%zu", n, c->srs_n);
         return fail(c, KZGB_ERR_SRS_CAPACITY, msg);
     }
-    int rc = blob_to_evals(c, L, blob, nullptr, len, n);
+    int rc = ensure_lagrange(c, log2_exact(n));
+    if (rc) return rc;
+    rc = blob_to_evals(c, L, blob, nullptr, len, n);
     if (rc) return rc;
     MsmJob job;
     rc = commit_evals_enqueue(c, L, (Fr*)L.evals.p, n, &job);
@@ -885,12 +1019,14 @@ int kzgb_compute_proof(kzgb_ctx* c, const uint64_t* evals, size_t n, const uint6
         snprintf(msg, sizeof msg, "SRS capacity exceeded: polynomial_len=%zu srs_len=%zu", n, c->srs_n);
         return fail(c, KZGB_ERR_SRS_CAPACITY, msg);
     }
+    int rc = ensure_lagrange(c, log2_exact(n));
+    if (rc) return rc;
     CK(c, L.evals.reserve(n * sizeof(Fr)));
     CK(c, cudaMemcpyAsync(L.evals.p, evals, n * sizeof(Fr), cudaMemcpyHostToDevice, L.st));
     Fr z;
     memcpy(z.l, z_mont, 32);
     MsmJob job;
-    int rc = proof_enqueue(c, L, (Fr*)L.evals.p, n, z, &job);
+    rc = proof_enqueue(c, L, (Fr*)L.evals.p, n, z, &job);
     if (rc) return rc;
     if (y_out) CK(c, cudaMemcpyAsync(&L.h_fr[3], (Fr*)L.small.p + 2, sizeof(Fr), cudaMemcpyDeviceToHost, L.st));
     Affine r;
@@ -951,7 +1087,9 @@ int kzgb_compute_blob_proof(kzgb_ctx* c, const uint8_t* blob, size_t len, const 
         snprintf(msg, sizeof msg, "SRS capacity exceeded: polynomial_len=%zu srs_len=%zu", n, c->srs_n);
         return fail(c, KZGB_ERR_SRS_CAPACITY, msg);
     }
-    int rc = blob_to_evals(c, L, blob, nullptr, len, n);  // H2D + conversion run while the host hashes
+    int rc = ensure_lagrange(c, log2_exact(n));
+    if (rc) return rc;
+    rc = blob_to_evals(c, L, blob, nullptr, len, n);  // H2D + conversion run while the host hashes
     if (rc) return rc;
     Sha256 sh;
     challenge_midstate(sh, blob, len, n);
@@ -981,18 +1119,49 @@ static int batch_impl(kzgb_ctx* c, const uint8_t* const* blobs_dev, const uint8_
         }
         max_n = std::max(max_n, n);
     }
+    // Small blobs (<= 2^17 Fr): runs of equal-size blobs are processed as groups, every kernel of a phase
+    // launched ONCE for the whole group (batched conversion, evaluation/quotient and MSM with one bucket set
+    // per blob) -- one blob at a time they are latency-bound (bucket-reduction tail, host hand-off per MSM).
+    static const int group_env = getenv("KZGB_GROUP") ? atoi(getenv("KZGB_GROUP")) : -1;
+    const int group_opt = g_group.load() >= 0 ? g_group.load() : group_env;
+    std::vector<std::pair<size_t, size_t>> groups;  // (first blob, blobs)
+    if (group_opt != 0 && count >= 2 && max_n <= ((size_t)1 << 17) && c->auto_precompute && c->srs_n <= ((size_t)1 << 22)) {
+        for (size_t i = 0; i < count;) {
+            size_t n = blob_poly_len(lens[i]);
+            size_t cap = group_opt > 0 ? (size_t)group_opt : std::max<size_t>(1, ((size_t)1 << 21) / n);
+            cap = std::min<size_t>(cap, 64);
+            size_t j = i + 1;
+            while (j < count && j - i < cap && blob_poly_len(lens[j]) == n) j++;
+            groups.emplace_back(i, j - i);
+            i = j;
+        }
+    }
     // lanes in flight: 3 keep the GPU full on 16 MiB blobs; small blobs are latency-bound per lane
     // (bucket reduction, host hand-offs), so they get more
     static const int lanes_env = getenv("KZGB_LANES") ? atoi(getenv("KZGB_LANES")) : 0;
     int want_lanes = lanes_env > 0 ? lanes_env : ((max_n >= ((size_t)1 << 18) && !lane_wait_polls()) ? 4 : 6);
-    int n_lanes = (int)std::min<size_t>(count, (size_t)std::min(want_lanes, MAX_LANES));
+    if (!groups.empty() && lanes_env <= 0) want_lanes = 3;
+    int n_lanes = (int)std::min<size_t>(groups.empty() ? count : groups.size(), (size_t)std::min(want_lanes, MAX_LANES));
     int rc = ensure_lanes(c, n_lanes);
     if (rc) return rc;
     rc = ensure_twiddles(c, log2_exact(max_n));
     if (rc) return rc;
-    if (c->auto_precompute && (!c->wtable || max_n > c->wt_n) && c->srs_n <= ((size_t)1 << 22)) {
+    bool all_lagrange = true;
+    for (size_t i = 0; i < count; i++) {
+        int logn = log2_exact(blob_poly_len(lens[i]));
+        rc = ensure_lagrange(c, logn);
+        if (rc) return rc;
+        if (!c->lag[logn].table) all_lagrange = false;
+    }
+    if (!all_lagrange && c->auto_precompute && (!c->wtable || max_n > c->wt_n) && c->srs_n <= ((size_t)1 << 22)) {
         rc = do_precompute(c, std::min(c->srs_n, next_pow2(max_n)), 0);
         if (rc && rc != KZGB_ERR_DEVICE) return rc;
+    }
+    for (size_t gi = 0; gi < groups.size(); gi++) {  // the batched MSM needs a window table for every size
+        size_t n = blob_poly_len(lens[groups[gi].first]);
+        int logn = log2_exact(n);
+        bool lag_ok = c->lag[logn].table && g_lagrange.load();
+        if (!lag_ok && !(c->wtable && n <= c->wt_n)) { groups.clear(); break; }
     }
 
     // host hashing pool: transcript midstates (everything but the commitment)
@@ -1015,6 +1184,103 @@ static int batch_impl(kzgb_ctx* c, const uint8_t* const* blobs_dev, const uint8_
         });
     }
 
+    std::vector<int> lane_rc(n_lanes, KZGB_OK);
+    bool failed = false;
+    if (!groups.empty()) {
+        // ---- small blobs: groups of equal-size blobs, each phase of a group is ONE batched launch set ----
+        std::atomic<size_t> next_group{0};
+        auto group_main = [&](int li) {
+            cudaSetDevice(c->device);
+            Lane& L = c->lanes[li];
+            std::vector<Affine> pts;
+            std::vector<Fr> zt;
+            for (;;) {
+                size_t gi = next_group.fetch_add(1);
+                if (gi >= groups.size()) return;
+                { std::lock_guard<std::mutex> lk(mu); if (failed) return; }
+                const size_t i0 = groups[gi].first, b = groups[gi].second;
+                const size_t n = blob_poly_len(lens[i0]);
+                const int logn = log2_exact(n);
+                const kzgb_ctx::LagTable* lag = (c->lag[logn].table && g_lagrange.load()) ? &c->lag[logn] : nullptr;
+                Fr ninv = ninv_mont(logn);
+                int r = KZGB_OK;
+                auto ck = [&](cudaError_t e, const char* what) {
+                    if (!r && e != cudaSuccess) r = fail(c, KZGB_ERR_DEVICE, std::string("CUDA error: ") + cudaGetErrorString(e) + " at " + what);
+                };
+                ck(L.evals.reserve(b * n * sizeof(Fr)), "evals");
+                ck(L.work.reserve(b * n * sizeof(Fr)), "work");
+                ck(L.small.reserve((3 * b + 8) * sizeof(Fr)), "small");
+                ck(L.eval_scratch.reserve(eval_quotient_scratch_elems((uint32_t)n, (uint32_t)b) * sizeof(Fr)), "eval scratch");
+                if (!lag) ck(L.ntt_scratch.reserve(b * n * sizeof(Fr)), "ntt scratch");
+                if (!blobs_dev) ck(L.bytes.reserve(b * n * 32), "bytes");
+                bool full = true;  // every blob fills its polynomial: one conversion launch for the group
+                for (size_t k = 0; k < b; k++) full = full && lens[i0 + k] == n * 32;
+                bool dev_run = blobs_dev && full;  // device blobs back to back: one conversion launch too
+                for (size_t k = 0; k < b && dev_run; k++) dev_run = blobs_dev[i0 + k] == blobs_dev[i0] + k * n * 32;
+                if (dev_run) bytes_to_fr_launch(blobs_dev[i0], (uint64_t)b * n * 32, (Fr*)L.evals.p, (uint32_t)(b * n), L.st);
+                for (size_t k = 0; k < b && !r && !dev_run; k++) {
+                    const uint8_t* src = blobs_dev ? blobs_dev[i0 + k] : nullptr;
+                    if (!src) {
+                        uint8_t* dst = (uint8_t*)L.bytes.p + k * n * 32;
+                        ck(cudaMemcpyAsync(dst, blobs_host[i0 + k], lens[i0 + k], cudaMemcpyHostToDevice, L.st), "H2D copy of a blob");
+                        src = dst;
+                    }
+                    if (!full || blobs_dev) bytes_to_fr_launch(src, lens[i0 + k], (Fr*)L.evals.p + k * n, (uint32_t)n, L.st);
+                }
+                if (!r && full && !blobs_dev) bytes_to_fr_launch((const uint8_t*)L.bytes.p, (uint64_t)b * n * 32, (Fr*)L.evals.p, (uint32_t)(b * n), L.st);
+                // commitments
+                MsmJob job;
+                pts.resize(b);
+                if (!r) {
+                    const Fr* sc = (const Fr*)L.evals.p;
+                    if (!lag) {
+                        ck(cudaMemcpyAsync(L.work.p, L.evals.p, b * n * sizeof(Fr), cudaMemcpyDeviceToDevice, L.st), "copy");
+                        ntt_launch((Fr*)L.work.p, logn, (uint32_t)b, true, c->tw, c->logN, &ninv, (Fr*)L.ntt_scratch.p, L.st);
+                        sc = (const Fr*)L.work.p;
+                    }
+                    if (!r) r = msm_enqueue_batched(c, L, sc, n, b, lag, &job);
+                }
+                if (!r) r = msm_finish_batched(c, L, job, b, pts.data());
+                if (!r) {
+                    for (size_t k = 0; k < b; k++) serialize_compressed(pts[k], commitments32 + 32 * (i0 + k));
+                    // challenges: the transcript midstates come from the hashing pool
+                    zt.resize(2 * b);
+                    {
+                        std::unique_lock<std::mutex> lk(mu);
+                        for (size_t k = 0; k < b; k++) cv.wait(lk, [&] { return ready[i0 + k] != 0 || failed; });
+                        if (failed) return;
+                    }
+                    for (size_t k = 0; k < b; k++) {
+                        zt[k] = challenge_finish(mid[i0 + k], pts[k]);
+                        zt[b + k] = eval_tinv(zt[k], logn);
+                    }
+                    Fr* d_z = (Fr*)L.small.p;  // [z x b | tinv x b | y x b]
+                    ck(cudaMemcpyAsync(d_z, zt.data(), 2 * b * sizeof(Fr), cudaMemcpyHostToDevice, L.st), "H2D of the challenges");
+                    eval_quotient_launch((Fr*)L.evals.p, (uint32_t)n, logn, (uint32_t)b, d_z, d_z + b, c->tw, c->logN, &ninv,
+                                         (Fr*)L.eval_scratch.p, (Fr*)L.work.p, d_z + 2 * b, L.st);
+                    if (!lag) ntt_launch((Fr*)L.work.p, logn, (uint32_t)b, true, c->tw, c->logN, &ninv, (Fr*)L.ntt_scratch.p, L.st);
+                    if (!r) r = msm_enqueue_batched(c, L, (const Fr*)L.work.p, n, b, lag, &job);
+                    if (!r) r = msm_finish_batched(c, L, job, b, pts.data());
+                }
+                if (r) {
+                    std::lock_guard<std::mutex> lk(mu);
+                    lane_rc[li] = r; failed = true;
+                    cv.notify_all();
+                    return;
+                }
+                for (size_t k = 0; k < b; k++) serialize_compressed(pts[k], proofs32 + 32 * (i0 + k));
+            }
+        };
+        std::vector<std::thread> lane_threads;
+        for (int li = 1; li < n_lanes; li++) lane_threads.emplace_back(group_main, li);
+        group_main(0);
+        for (auto& t : lane_threads) t.join();
+        next_hash.store(count);
+        for (auto& t : hashers) t.join();
+        for (int li = 0; li < n_lanes; li++) if (lane_rc[li]) return lane_rc[li];
+        return KZGB_OK;
+    }
+
     // Blob bytes stay resident on the device between a blob's commit and its proof (one H2D per blob).
     std::vector<size_t> byte_off(count, 0);
     bool resident = false;
@@ -1028,11 +1294,9 @@ static int batch_impl(kzgb_ctx* c, const uint8_t* const* blobs_dev, const uint8_
     // Task scheduler.  commit(i) needs nothing; proof(i) needs commit(i) and the transcript midstate of
     // blob i (host SHA-256, ~9 ms for 16 MiB).  A lane takes the lowest ready proof, else the next
     // commit, so the GPU never idles behind the hashing pool.
-    std::vector<int> lane_rc(n_lanes, KZGB_OK);
     std::vector<uint8_t> commit_done(count, 0), proof_taken(count, 0);
     std::vector<Affine> commits(count);
     size_t next_commit = 0, proofs_taken = 0, proof_scan = 0;
-    bool failed = false;
     auto lane_main = [&](int li) {
         cudaSetDevice(c->device);
         Lane& L = c->lanes[li];
@@ -1419,6 +1683,8 @@ int kzgb_stats(kzgb_ctx* c, double* acc_ms, uint64_t* acc_launches, uint64_t* ac
 int kzgb_set_option(const char* name, long value) {
     if (!name) return KZGB_ERR_GENERIC;
     if (!strcmp(name, "fs_device")) { g_fs_device.store((int)value); return KZGB_OK; }
+    if (!strcmp(name, "group")) { g_group.store((int)value); return KZGB_OK; }
+    if (!strcmp(name, "lagrange")) { g_lagrange.store(value != 0); return KZGB_OK; }
     if (!strcmp(name, "batch_affine_levels")) { msm_set_tuning((int)value, -1, -1); return KZGB_OK; }
     return KZGB_ERR_GENERIC;
 }

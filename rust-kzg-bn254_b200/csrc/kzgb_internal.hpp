@@ -20,7 +20,8 @@ extern std::atomic<uint64_t> g_launch_count;
 struct MsmPlan {
     int c;             // window bits
     int W;             // number of windows
-    int sets;          // 1 (fixed-base table) or W (variable base)
+    int sets;          // 1 (fixed-base table), W (variable base) or the number of batched fixed-base MSMs
+    uint32_t batch_n;  // batched fixed-base MSMs: scalars per MSM (scalar i belongs to MSM i / batch_n); 0 = not batched
     uint32_t nbuckets; // sets * 2^(c-1)
     uint32_t n;        // points in this launch
     uint32_t table_stride;  // points per window in the table (0 when sets == W)
@@ -55,7 +56,9 @@ struct MsmWorkspace {
 
 size_t msm_workspace_bytes(const MsmPlan& p);
 void msm_workspace_carve(const MsmPlan& p, void* base, MsmWorkspace* ws);
-MsmPlan msm_make_plan(uint32_t n, int c, bool fixed_base, uint32_t table_stride, uint32_t base_offset);
+// batch > 0 (fixed base only): n = batch * (n / batch) scalars of `batch` independent MSMs over the same
+// table points [base_offset, base_offset + n / batch); set_sums[k] is the result of MSM k.
+MsmPlan msm_make_plan(uint32_t n, int c, bool fixed_base, uint32_t table_stride, uint32_t base_offset, uint32_t batch = 0);
 // Batch-affine tuning: levels (default 0 = off), minimum average bucket occupancy for it to be
 // used (default 64), pairs per thread at level 0 (0 = default: one wave per level).  Negative values keep
 // the current setting.

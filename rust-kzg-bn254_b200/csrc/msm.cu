@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(256) k_digits_hist(const Fr* __restrict__ scal
         bool neg;
         uint32_t mag = signed_digit(s.l, w, p.c, carry, neg);
         if (mag) {
-            uint32_t key = (p.sets == 1 ? 0u : (uint32_t)w * half) + mag - 1u;
+            uint32_t key = (p.batch_n ? (i / p.batch_n) * half : (p.sets == 1 ? 0u : (uint32_t)w * half)) + mag - 1u;
             atomicAdd(&hist[key], 1u);
         }
     }
@@ -160,9 +160,10 @@ __global__ void __launch_bounds__(256) k_scatter(const Fr* __restrict__ canon, M
         bool neg;
         uint32_t mag = signed_digit(s.l, w, p.c, carry, neg);
         if (mag) {
-            uint32_t key = (p.sets == 1 ? 0u : (uint32_t)w * half) + mag - 1u;
+            uint32_t key = (p.batch_n ? (i / p.batch_n) * half : (p.sets == 1 ? 0u : (uint32_t)w * half)) + mag - 1u;
             uint32_t pos = atomicAdd(&cursor[key], 1u);
-            uint32_t ref = (p.sets == 1) ? ((uint32_t)w * p.table_stride + p.base_offset + i) : i;
+            uint32_t ref = p.batch_n ? ((uint32_t)w * p.table_stride + p.base_offset + i % p.batch_n)
+                                     : (p.sets == 1) ? ((uint32_t)w * p.table_stride + p.base_offset + i) : i;
             sorted[pos] = ref | (neg ? 0x80000000u : 0u);
         }
     }
@@ -666,12 +667,13 @@ static void tuning_from_env() {
     if ((e = getenv("KZGB_BA_K0")) && atoi(e) >= 0) g_ba_k0 = atoi(e);
 }
 
-MsmPlan msm_make_plan(uint32_t n, int c, bool fixed_base, uint32_t table_stride, uint32_t base_offset) {
+MsmPlan msm_make_plan(uint32_t n, int c, bool fixed_base, uint32_t table_stride, uint32_t base_offset, uint32_t batch) {
     tuning_from_env();
     MsmPlan p;
     p.c = c;
     p.W = (255 + c - 1) / c;
-    p.sets = fixed_base ? 1 : p.W;
+    p.batch_n = (fixed_base && batch > 0) ? n / batch : 0;  // `batch` independent MSMs over the same table, one bucket set each
+    p.sets = fixed_base ? (p.batch_n ? (int)batch : 1) : p.W;
     p.nbuckets = (uint32_t)p.sets << (c - 1);
     p.n = n;
     p.table_stride = fixed_base ? table_stride : 0;

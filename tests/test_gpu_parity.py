@@ -276,6 +276,39 @@ def test_batch_commit_and_prove(pkg, ref_srs, ref_srs_points):
         assert pb == o.g1_serialize_compressed(ko.compute_blob_proof(bo, c, ref_srs_points))
 
 
+def test_batch_groups_of_equal_size_blobs(pkg, ref_srs, ref_srs_points):
+    """Small blobs go through the grouped path (one batched MSM / evaluation launch set per group): same
+    bytes as one blob at a time, with and without the Lagrange-basis table, and as the oracle."""
+    rnd = random.Random(16)
+    raws = [bytes(rnd.getrandbits(8) for _ in range(31 * 64 - k)) for k in (0, 1, 40, 0, 7)]          # n = 64, ragged lengths
+    raws += [bytes(rnd.getrandbits(8) for _ in range(31 * 256 - 3 * k)) for k in range(4)]            # n = 256
+    raws += [bytes(31 * 64), raws[0], raws[0]]                                                        # zero blob, duplicates
+    raws += [b"q"]                                                                                    # n = 1
+    blobs = [pkg.Blob.from_raw_data(r) for r in raws]
+    lib = pkg.lib
+    outs = {}
+    try:
+        for lag in (1, 0):
+            for group in (-1, 0, 3):
+                lib.kzgb_set_option(b"lagrange", lag)
+                lib.kzgb_set_option(b"group", group)
+                srs = pkg.SRS.from_gnark_bytes(g.g1_point_bytes(), engine=pkg.Engine(0))
+                outs[(lag, group)] = pkg.KZG.commit_and_prove_blobs(blobs, srs)
+    finally:
+        lib.kzgb_set_option(b"lagrange", 1)
+        lib.kzgb_set_option(b"group", -1)
+    first = outs[(1, -1)]
+    for k, v in outs.items():
+        assert v == first, k
+    for i in (1, 5, 9, 12):
+        bo = o.Blob.from_raw_data(raws[i])
+        ko = o.KZG()
+        ko.calculate_and_store_roots_of_unity(len(bo))
+        c = ko.commit_blob(bo, ref_srs_points)
+        assert first[0][i] == o.g1_serialize_compressed(c)
+        assert first[1][i] == o.g1_serialize_compressed(ko.compute_blob_proof(bo, c, ref_srs_points))
+
+
 def test_verify_batch_rlc(pkg, ref_srs, ref_srs_points):
     """verifier/src/batch.rs:16-249 up to the pairing: both G1 outputs equal the oracle's."""
     rnd = random.Random(8)
@@ -332,6 +365,82 @@ def test_batch_affine_levels_exact(pkg, eng, ref_srs, ref_srs_points, levels, k0
         assert kzg.commit_coeff_form(pkg.PolynomialCoeffForm([0] * 64), ref_srs) is None
     finally:
         pkg.lib.kzgb_msm_tuning(0, 64, 0)
+
+
+def test_lagrange_table_and_monomial_paths_agree(pkg, ref_srs_points):
+    """Evaluation-form commits/proofs through the resident Lagrange-basis table (one MSM on the evaluations,
+    the cached form of kzg.rs:98) and through Fr-IFFT + monomial table give the oracle's group element."""
+    rnd = random.Random(21)
+    lib = pkg.lib
+    try:
+        results = {}
+        for mode in (0, 1):
+            assert lib.kzgb_set_option(b"lagrange", mode) == 0
+            srs = pkg.SRS.from_gnark_bytes(g.g1_point_bytes(), engine=pkg.Engine(0))  # fresh context: no tables yet
+            kzg = pkg.KZG()
+            out = []
+            for n in (2, 8, 64, 512, 2048):
+                rr = random.Random(100 + n)
+                ev = [rr.randrange(o.R) for _ in range(n)]
+                if n == 8:
+                    ev = [0] * n  # zero polynomial -> identity
+                if n == 512:
+                    ev = [ev[0]] * n  # constant polynomial: every evaluation in the same buckets
+                poly = pkg.PolynomialEvalForm(ev)
+                kzg.calculate_and_store_roots_of_unity(32 * n)
+                out.append(kzg.commit_eval_form(poly, srs))
+                out.append(kzg.compute_proof(poly, rr.randrange(o.R), srs))
+                out.append(kzg.compute_proof_with_known_z_fr_index(poly, n // 3, srs))
+            results[mode] = out
+        assert results[0] == results[1]
+        # oracle check of the Lagrange path at the sizes the big-int oracle finishes quickly
+        lib.kzgb_set_option(b"lagrange", 1)
+        srs = pkg.SRS.from_gnark_bytes(g.g1_point_bytes(), engine=pkg.Engine(0))
+        srs.prepare_lagrange(64)
+        ev = [rnd.randrange(o.R) for _ in range(64)]
+        ko = o.KZG()
+        ko.calculate_and_store_roots_of_unity(32 * 64)
+        po = o.PolynomialEvalForm(ev)
+        kzg = pkg.KZG()
+        kzg.calculate_and_store_roots_of_unity(32 * 64)
+        z = rnd.randrange(o.R)
+        assert kzg.commit_eval_form(pkg.PolynomialEvalForm(ev), srs) == ko.commit_eval_form(po, ref_srs_points)
+        assert kzg.compute_proof(pkg.PolynomialEvalForm(ev), z, srs) == ko.compute_proof(po, z, ref_srs_points)
+        with pytest.raises(pkg.KzgError) as e:
+            srs.prepare_lagrange(48)
+        assert e.value.variant == "FFTError"
+        with pytest.raises(pkg.KzgError) as e:
+            srs.prepare_lagrange(4096)  # 3000-point SRS
+        assert e.value.variant == "SrsCapacityExceeded"
+    finally:
+        lib.kzgb_set_option(b"lagrange", 1)
+
+
+def test_lagrange_table_tau_trick_large(pkg):
+    """n = 2^16 on the synthetic SRS: commitment through the Lagrange table == p(tau) G, proof == ((p(tau)-y)/(tau-z)) G."""
+    n = 1 << 16
+    srs = pkg.SRS.synthetic(n, o.SYNTH_TAU)
+    srs.prepare_lagrange(n)
+    rnd = random.Random(22)
+    ev = [rnd.randrange(o.R) for _ in range(n)]
+    kzg = pkg.KZG()
+    kzg.calculate_and_store_roots_of_unity(32 * n)
+    poly = pkg.PolynomialEvalForm(ev)
+    c = kzg.commit_eval_form(poly, srs)
+    coeffs = poly.to_coeff_form(srs.engine).coeffs
+    ptau = 0
+    for cf in reversed(coeffs):
+        ptau = (ptau * o.SYNTH_TAU + cf) % o.R
+    assert c == o.g1_mul(o.G1_GEN, ptau)
+    z = rnd.randrange(o.R)
+    y = pkg.evaluate_polynomial_in_evaluation_form(poly, z, srs.engine)
+    expect = o.g1_mul(o.G1_GEN, (ptau - y) * o.fr_inv((o.SYNTH_TAU - z) % o.R) % o.R)
+    assert kzg.compute_proof(poly, z, srs) == expect
+    pkg.lib.kzgb_set_option(b"lagrange", 0)
+    try:
+        assert kzg.commit_eval_form(poly, srs) == c
+    finally:
+        pkg.lib.kzgb_set_option(b"lagrange", 1)
 
 
 def test_g1_ifft_kernel_sizes_and_identities(pkg, eng, ref_srs, ref_srs_points):
