@@ -57,8 +57,16 @@ int kzgb_sync(kzgb_ctx* ctx);
 
 /* ---- SRS (prover/src/srs.rs:11-49 `SRS`, `SRS::new`) ------------------------------------ */
 /* Load the first `points_to_load` points of a g1.point file (32 B gnark-BE each).  Replaces
- * SRS::new(path, order, points_to_load) (srs.rs:35-49) incl. its `points_to_load > order` error. */
+ * SRS::new(path, order, points_to_load) (srs.rs:35-49) incl. its `points_to_load > order` error.
+ * Streamed: chunks of 2^22 points are read into pinned memory while the previous chunk is copied and
+ * decompressed on the GPU (the reference reads 32 bytes per syscall, srs.rs:154-188). */
 int kzgb_srs_load_file(kzgb_ctx* ctx, const char* path, uint32_t order, uint32_t points_to_load);
+/* On-disk cache of the DECOMPRESSED points (64-byte header + 64 B x||y Montgomery per point): written
+ * from the resident SRS, loaded without the per-point square root (each point is still checked to be on
+ * the curve on the GPU).  points_to_load = 0 loads the whole cache; more than the cache holds is the
+ * same error as SRS::new's order check. */
+int kzgb_srs_save_cache(kzgb_ctx* ctx, const char* path);
+int kzgb_srs_load_cache(kzgb_ctx* ctx, const char* path, uint32_t points_to_load);
 /* Same from memory (replaces parallel_read_g1_points + read_g1_point_from_bytes_be, srs.rs:81-138). */
 int kzgb_srs_load_gnark_be(kzgb_ctx* ctx, const uint8_t* bytes, size_t n_points);
 /* From an existing `SRS.g1` slice: n x (x||y) Montgomery words; inf[i] != 0 marks the identity (may be NULL). */
@@ -198,6 +206,7 @@ int kzgb_msm_tuning(int batch_affine_levels, int min_avg_bucket, int pairs_per_t
  *   "fs_device"            -1 auto (default), 0 host SHA-256 pool, 1 device kernel for the per-blob
  *                          Fiat-Shamir challenges of kzgb_verify_batch_rlc (auto: >= 256 blobs of <= 2^13 Fr)
  *   "batch_affine_levels"  as in kzgb_msm_tuning
+ *   "srs_chunk_points"     points per chunk of the streamed SRS ingest (0 = default 2^22)
  *   "group"                -1 (default): kzgb_commit_and_prove_blobs processes runs of equal-size blobs of
  *                          <= 2^17 Fr as groups (one batched launch set per phase and group, sized so a group
  *                          holds <= 2^21 Fr and <= 64 blobs); 0: one blob at a time; k > 0: k blobs per group

@@ -358,6 +358,17 @@ class SRS:
         return s
 
     @classmethod
+    def from_cache(cls, path: str, points_to_load: int = 0, engine: Optional[Engine] = None) -> "SRS":
+        """Decompressed-point cache written by :meth:`save_cache` (no square roots; on-curve check on the GPU)."""
+        s = cls._blank(engine, points_to_load)
+        s.engine.check(lib.kzgb_srs_load_cache(s.engine.h, path.encode(), points_to_load))
+        s.order = len(s)
+        return s
+
+    def save_cache(self, path: str) -> None:
+        self.engine.check(lib.kzgb_srs_save_cache(self.engine.h, path.encode()))
+
+    @classmethod
     def from_points(cls, pts: Sequence[Affine], engine: Optional[Engine] = None) -> "SRS":
         s = cls._blank(engine, len(pts))
         xy, inf = g1_to_abi(pts)

@@ -31,6 +31,8 @@ SIGNATURES = {
     "kzgb_last_error": (C.c_char_p, [ctx_p]),
     "kzgb_sync": (C.c_int, [ctx_p]),
     "kzgb_srs_load_file": (C.c_int, [ctx_p, C.c_char_p, C.c_uint32, C.c_uint32]),
+    "kzgb_srs_save_cache": (C.c_int, [ctx_p, C.c_char_p]),
+    "kzgb_srs_load_cache": (C.c_int, [ctx_p, C.c_char_p, C.c_uint32]),
     "kzgb_srs_load_gnark_be": (C.c_int, [ctx_p, buf, C.c_size_t]),
     "kzgb_srs_load_affine_mont": (C.c_int, [ctx_p, buf, buf, C.c_size_t]),
     "kzgb_srs_load_synthetic": (C.c_int, [ctx_p, buf, C.c_size_t]),

@@ -95,6 +95,8 @@ std::atomic<int> g_fs_device{getenv("KZGB_FS_DEVICE") ? atoi(getenv("KZGB_FS_DEV
 // 1: evaluation-form commitments use a Lagrange-basis window table (built on first use per size), 0: Fr-IFFT + monomial table
 // -1: KZGB_GROUP env / auto, 0: one blob at a time, > 0: blobs per group in the small-blob batch path
 std::atomic<int> g_group{-1};
+// points per chunk of the streamed SRS ingest (0 = 2^22); tests shrink it to cross chunk boundaries
+std::atomic<long> g_srs_chunk{0};
 std::atomic<int> g_lagrange{getenv("KZGB_LAGRANGE") ? atoi(getenv("KZGB_LAGRANGE")) : 1};
 int fail(kzgb_ctx* c, int code, const std::string& msg) {
     if (c) { std::lock_guard<std::mutex> lk(g_err_mu); c->err = msg; }
@@ -638,6 +640,80 @@ struct Guard {
     ~Guard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
+// Streamed ingest of `n` compressed points: `read(dst, first, count)` fills a pinned staging buffer with
+// points [first, first+count); the read of chunk k+1 overlaps the H2D copy and the decompression kernel of
+// chunk k (two staging buffers).  The reference does one 32-byte read + one channel send per point
+// (srs.rs:154-188) and a sqrt per point on CPU threads ("a few minutes" for the 2^28-point mainnet SRS).
+// raw = true: the source already holds 64-byte affine Montgomery points (the table cache); they are only
+// checked to be on the curve.
+template <class Reader>
+int srs_ingest_stream(kzgb_ctx* c, size_t n, bool raw, Reader read) {
+    if (n == 0 || n > ((size_t)1 << 28)) return fail(c, KZGB_ERR_GENERIC, "invalid number of SRS points");
+    Lane& L = c->lanes[0];
+    const size_t unit = raw ? sizeof(Affine) : 32;
+    size_t chunk = (size_t)g_srs_chunk.load();
+    if (chunk == 0) chunk = (size_t)1 << 22;
+    chunk = std::min(chunk, n);
+    uint8_t* pin[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    DevBuf stage[2], errb;
+    Affine* pts = nullptr;
+    int rc = KZGB_OK;
+    auto cleanup = [&]() {
+        for (int k = 0; k < 2; k++) { if (pin[k]) cudaFreeHost(pin[k]); if (ev[k]) cudaEventDestroy(ev[k]); stage[k].release(); }
+        errb.release();
+    };
+    auto ck = [&](cudaError_t e, const char* what) {
+        if (!rc && e != cudaSuccess) rc = fail(c, KZGB_ERR_DEVICE, std::string("CUDA error: ") + cudaGetErrorString(e) + " at " + what);
+    };
+    const size_t n_chunks = (n + chunk - 1) / chunk;
+    ck(cudaMalloc((void**)&pts, n * sizeof(Affine)), "cudaMalloc(SRS points)");
+    ck(errb.reserve(4 * n_chunks), "cudaMalloc");
+    for (int k = 0; k < 2 && !rc; k++) {
+        ck(cudaMallocHost((void**)&pin[k], chunk * unit), "cudaMallocHost(staging)");
+        ck(cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming), "cudaEventCreate");
+        if (!raw) ck(stage[k].reserve(chunk * unit), "cudaMalloc(staging)");
+    }
+    std::vector<uint32_t> herr(n_chunks, 0xffffffffu);
+    uint32_t* d_err = (uint32_t*)errb.p;  // one slot per chunk
+    if (!rc) ck(cudaMemsetAsync(d_err, 0xff, 4 * n_chunks, L.st), "memset");
+    for (size_t k = 0; k < n_chunks && !rc; k++) {
+        const size_t first = k * chunk, count = std::min(chunk, n - first);
+        const int b = (int)(k & 1);
+        if (k >= 2) ck(cudaEventSynchronize(ev[b]), "cudaEventSynchronize");  // staging buffer free again
+        if (rc) break;
+        if (!read(pin[b], first, count)) { rc = fail(c, KZGB_ERR_GENERIC, "Failed to read G1 points: file shorter than points_to_load"); break; }
+        if (raw) {
+            ck(cudaMemcpyAsync(pts + first, pin[b], count * unit, cudaMemcpyHostToDevice, L.st), "H2D copy of SRS points");
+            g1_validate_launch(pts + first, (uint32_t)count, d_err + k, L.st);
+        } else {
+            ck(cudaMemcpyAsync(stage[b].p, pin[b], count * unit, cudaMemcpyHostToDevice, L.st), "H2D copy of SRS points");
+            srs_decompress_launch((const uint8_t*)stage[b].p, (uint32_t)count, pts + first, d_err + k, L.st);
+        }
+        ck(cudaEventRecord(ev[b], L.st), "cudaEventRecord");
+    }
+    if (!rc) ck(cudaMemcpyAsync(herr.data(), d_err, 4 * n_chunks, cudaMemcpyDeviceToHost, L.st), "D2H");
+    ck(cudaStreamSynchronize(L.st), "sync");
+    if (!rc) ck(cudaGetLastError(), "SRS ingest kernels");
+    for (size_t k = 0; k < n_chunks && !rc; k++) {
+        if (herr[k] == 0xffffffffu) continue;
+        char msg[128];
+        if (raw) {
+            snprintf(msg, sizeof msg, "G1 point not on curve (cached point %zu)", k * chunk + herr[k] - 1);
+            rc = fail(c, KZGB_ERR_NOT_ON_CURVE, msg);
+        } else if ((herr[k] & 3u) == 2u) {
+            snprintf(msg, sizeof msg, "point at infinity not coded properly for g1 (point %zu)", k * chunk + (herr[k] >> 2) - 1);
+            rc = fail(c, KZGB_ERR_DESERIALIZATION, msg);
+        } else {
+            snprintf(msg, sizeof msg, "compressed g1 point not on curve (point %zu)", k * chunk + (herr[k] >> 2) - 1);
+            rc = fail(c, KZGB_ERR_NOT_ON_CURVE, msg);
+        }
+    }
+    cleanup();
+    if (rc) { if (pts) cudaFree(pts); return rc; }
+    return srs_install(c, pts, n);
+}
+
 }  // namespace
 
 // =====================================================================================
@@ -695,43 +771,75 @@ uint64_t kzgb_launch_count(const kzgb_ctx*) { return g_launch_count.load(); }
 // ------------------------------------------------------------------------------- SRS
 int kzgb_srs_load_gnark_be(kzgb_ctx* c, const uint8_t* bytes, size_t n) {
     Guard g(c);
-    if (n == 0 || n > ((size_t)1 << 28)) return fail(c, KZGB_ERR_GENERIC, "invalid number of SRS points");
-    Lane& L = c->lanes[0];
-    DevBuf raw, errb;
-    CK(c, raw.reserve(n * 32));
-    CK(c, errb.reserve(64));
-    Affine* pts = nullptr;
-    CK(c, cudaMalloc((void**)&pts, n * sizeof(Affine)));
-    CK(c, cudaMemcpyAsync(raw.p, bytes, n * 32, cudaMemcpyHostToDevice, L.st));
-    CK(c, cudaMemsetAsync(errb.p, 0xff, 64, L.st));
-    srs_decompress_launch((const uint8_t*)raw.p, (uint32_t)n, pts, (uint32_t*)errb.p, L.st);
-    uint32_t herr[2] = {0, 0};
-    CK(c, cudaMemcpyAsync(herr, errb.p, 8, cudaMemcpyDeviceToHost, L.st));
-    cudaError_t e = cudaStreamSynchronize(L.st);
-    raw.release(); errb.release();
-    if (e != cudaSuccess) { cudaFree(pts); CK(c, e); }
-    if (herr[0] != 0xffffffffu) {
-        cudaFree(pts);
-        char msg[128];
-        if (herr[1] == 2) {
-            snprintf(msg, sizeof msg, "point at infinity not coded properly for g1 (point %u)", herr[0] - 1);
-            return fail(c, KZGB_ERR_DESERIALIZATION, msg);
-        }
-        snprintf(msg, sizeof msg, "compressed g1 point not on curve (point %u)", herr[0] - 1);
-        return fail(c, KZGB_ERR_NOT_ON_CURVE, msg);
-    }
-    return srs_install(c, pts, n);
+    return srs_ingest_stream(c, n, false, [&](uint8_t* dst, size_t first, size_t count) {
+        memcpy(dst, bytes + first * 32, count * 32);
+        return true;
+    });
 }
 
 int kzgb_srs_load_file(kzgb_ctx* c, const char* path, uint32_t order, uint32_t points_to_load) {
     if (points_to_load > order) return fail(c, KZGB_ERR_GENERIC, "Number of points to load exceeds SRS order.");  // srs.rs:36-40
     FILE* f = fopen(path, "rb");
     if (!f) return fail(c, KZGB_ERR_GENERIC, std::string("Failed to read G1 points: cannot open ") + path);
-    std::vector<uint8_t> buf((size_t)points_to_load * 32);
-    size_t got = fread(buf.data(), 1, buf.size(), f);  // one bulk read instead of one 32-byte read per point (srs.rs:173)
+    Guard g(c);
+    // bulk sequential reads of whole chunks instead of one 32-byte read per point (srs.rs:173)
+    int rc = srs_ingest_stream(c, points_to_load, false, [&](uint8_t* dst, size_t, size_t count) {
+        return fread(dst, 32, count, f) == count;
+    });
     fclose(f);
-    if (got != buf.size()) return fail(c, KZGB_ERR_GENERIC, "Failed to read G1 points: file shorter than points_to_load");
-    return kzgb_srs_load_gnark_be(c, buf.data(), points_to_load);
+    return rc;
+}
+
+// ---- on-disk cache of the decompressed points ---------------------------------------------------
+// Header (64 bytes): "KZGBSRS1", u64 point count, zero padding; then count x 64 bytes x || y Montgomery
+// (identity = all zero).  Loading it skips the per-point square root; every point is still checked to be
+// on the curve on the GPU, so a damaged cache fails instead of giving wrong commitments.
+static const char SRS_CACHE_MAGIC[8] = {'K', 'Z', 'G', 'B', 'S', 'R', 'S', '1'};
+
+int kzgb_srs_save_cache(kzgb_ctx* c, const char* path) {
+    Guard g(c);
+    if (!c->srs_n) return fail(c, KZGB_ERR_GENERIC, "no SRS loaded");
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(c, KZGB_ERR_GENERIC, std::string("cannot create ") + path);
+    uint8_t hdr[64] = {0};
+    memcpy(hdr, SRS_CACHE_MAGIC, 8);
+    uint64_t n64 = c->srs_n;
+    memcpy(hdr + 8, &n64, 8);
+    bool ok = fwrite(hdr, 1, 64, f) == 64;
+    const size_t chunk = (size_t)1 << 20;
+    std::vector<Affine> buf(std::min(chunk, c->srs_n));
+    for (size_t first = 0; first < c->srs_n && ok; first += chunk) {
+        size_t count = std::min(chunk, c->srs_n - first);
+        cudaError_t e = cudaMemcpy(buf.data(), c->srs + first, count * sizeof(Affine), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { fclose(f); remove(path); CK(c, e); }
+        ok = fwrite(buf.data(), sizeof(Affine), count, f) == count;
+    }
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) { remove(path); return fail(c, KZGB_ERR_GENERIC, std::string("short write to ") + path); }
+    return KZGB_OK;
+}
+
+int kzgb_srs_load_cache(kzgb_ctx* c, const char* path, uint32_t points_to_load) {
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(c, KZGB_ERR_GENERIC, std::string("Failed to read G1 points: cannot open ") + path);
+    uint8_t hdr[64];
+    uint64_t n64 = 0;
+    if (fread(hdr, 1, 64, f) != 64 || memcmp(hdr, SRS_CACHE_MAGIC, 8) != 0) {
+        fclose(f);
+        return fail(c, KZGB_ERR_DESERIALIZATION, "not an SRS point cache (bad header)");
+    }
+    memcpy(&n64, hdr + 8, 8);
+    if (points_to_load == 0) points_to_load = (uint32_t)std::min<uint64_t>(n64, 0xffffffffu);
+    if (points_to_load > n64) {
+        fclose(f);
+        return fail(c, KZGB_ERR_GENERIC, "Number of points to load exceeds SRS order.");
+    }
+    Guard g(c);
+    int rc = srs_ingest_stream(c, points_to_load, true, [&](uint8_t* dst, size_t, size_t count) {
+        return fread(dst, sizeof(Affine), count, f) == count;
+    });
+    fclose(f);
+    return rc;
 }
 
 int kzgb_srs_load_affine_mont(kzgb_ctx* c, const uint64_t* xy, const uint8_t* inf, size_t n) {
@@ -1683,6 +1791,7 @@ int kzgb_stats(kzgb_ctx* c, double* acc_ms, uint64_t* acc_launches, uint64_t* ac
 int kzgb_set_option(const char* name, long value) {
     if (!name) return KZGB_ERR_GENERIC;
     if (!strcmp(name, "fs_device")) { g_fs_device.store((int)value); return KZGB_OK; }
+    if (!strcmp(name, "srs_chunk_points")) { g_srs_chunk.store(value < 0 ? 0 : value); return KZGB_OK; }
     if (!strcmp(name, "group")) { g_group.store((int)value); return KZGB_OK; }
     if (!strcmp(name, "lagrange")) { g_lagrange.store(value != 0); return KZGB_OK; }
     if (!strcmp(name, "batch_affine_levels")) { msm_set_tuning((int)value, -1, -1); return KZGB_OK; }

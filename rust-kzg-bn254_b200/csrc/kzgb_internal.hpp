@@ -74,8 +74,9 @@ void msm_launch(const MsmPlan& p, const MsmWorkspace& ws, const Fr* scalars, boo
 // with ev_fork / ev_join.
 
 // ---- SRS ------------------------------------------------------------------------
-// gnark big-endian compressed points -> affine Montgomery.  err[] must be preset to 0xffffffff;
-// afterwards err[0] = 1 + index of the lowest bad point (0xffffffff = none), err[1] = kind.
+// gnark big-endian compressed points -> affine Montgomery (n < 2^30 per launch).  err[0] must be preset to
+// 0xffffffff; afterwards err[0] = ((1 + index of the lowest bad point) << 2) | kind (0xffffffff = none),
+// kind 1 = not on curve, 2 = infinity not coded properly.
 void srs_decompress_launch(const uint8_t* in_be, uint32_t n, Affine* out, uint32_t* err, cudaStream_t st);
 // table[w * stride + i] = 2^(c*w) * table[i] for w = 1..W-1 (window 0 must already be there)
 void srs_precompute_launch(Affine* table, uint32_t n, uint32_t stride, int c, int W, XYZZ* scratch,

@@ -9,7 +9,7 @@ namespace kzgb {
 
 __device__ __forceinline__ uint32_t bswap32s(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
 
-// err[0]: 0 = ok, else 1 + index of the lowest bad point; err[1]: kind (1 = not on curve, 2 = bad infinity)
+// err[0] (preset 0xffffffff): ((1 + index of the lowest bad point) << 2) | kind, kind 1 = not on curve, 2 = bad infinity
 __global__ void __launch_bounds__(128) k_decompress(const uint8_t* __restrict__ in, uint32_t n, Affine* __restrict__ out,
                                                      uint32_t* __restrict__ err) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(128) k_decompress(const uint8_t* __restrict__ 
     x.l[7] &= 0x3fffffffu;
     Affine P;
     if (flag == 1u) {  // 0b01: infinity, remaining bits must be zero (helpers.rs:188-196)
-        if (!fe_is_zero(x)) { atomicMin(&err[0], i + 1); err[1] = 2; }
+        if (!fe_is_zero(x)) atomicMin(&err[0], ((i + 1) << 2) | 2u);
         aff_set_inf(P);
         aff_store(&out[i], P);
         return;
@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(128) k_decompress(const uint8_t* __restrict__ 
     fe_pow(y, y2, e);  // p = 3 mod 4
     fe_sqr(t, y);
     if (!fe_eq(t, y2)) {
-        atomicMin(&err[0], i + 1); err[1] = 1;
+        atomicMin(&err[0], ((i + 1) << 2) | 1u);
         aff_set_inf(P);
         aff_store(&out[i], P);
         return;

@@ -77,6 +77,60 @@ def test_srs_new_order_error(pkg, tmp_path):
     assert s.points() == g.srs_points_string()[:100]
 
 
+def test_streamed_ingest_and_point_cache(pkg, ref_srs_points, tmp_path):
+    """SRS::new through the chunked loader (chunks of 257 points: 12 chunks for the 3000-point fixture), a bad
+    point in a late chunk, and the decompressed-point cache round trip incl. a damaged cache."""
+    lib = pkg.lib
+    raw = g.g1_point_bytes()
+    path = tmp_path / "g1.point"
+    path.write_bytes(raw)
+    try:
+        assert lib.kzgb_set_option(b"srs_chunk_points", 257) == 0
+        srs = pkg.SRS(str(path), 3000, 3000, engine=pkg.Engine(0))
+        assert srs.points() == ref_srs_points
+        assert pkg.SRS(str(path), 3000, 1000, engine=pkg.Engine(0)).points() == ref_srs_points[:1000]
+        with pytest.raises(pkg.KzgError) as e:
+            pkg.SRS(str(path), 3001, 3001, engine=pkg.Engine(0))  # file shorter than points_to_load
+        assert "Failed to read G1 points" in e.value.msg
+        x = 2
+        while o.fq_sqrt((x**3 + 3) % o.P) is not None:
+            x += 1
+        bad = bytearray(raw)
+        bad[32 * 2345 : 32 * 2346] = bytes([0x80]) + x.to_bytes(31, "big")
+        with pytest.raises(pkg.KzgError) as e:
+            pkg.SRS.from_gnark_bytes(bytes(bad), engine=pkg.Engine(0))
+        assert e.value.variant == "NotOnCurveError" and "point 2345" in e.value.msg
+        bad[32 * 700 : 32 * 701] = bytes([0x40, 1]) + bytes(30)  # infinity flag with stray bits, in an earlier chunk
+        with pytest.raises(pkg.KzgError) as e:
+            pkg.SRS.from_gnark_bytes(bytes(bad), engine=pkg.Engine(0))
+        assert e.value.variant == "DeserializationError" and "point 700" in e.value.msg
+        cache = tmp_path / "g1.cache"
+        srs.save_cache(str(cache))
+        assert cache.stat().st_size == 64 + 64 * 3000
+        assert pkg.SRS.from_cache(str(cache), engine=pkg.Engine(0)).points() == ref_srs_points
+        part = pkg.SRS.from_cache(str(cache), 1500, engine=pkg.Engine(0))
+        assert len(part) == 1500 and part.points() == ref_srs_points[:1500]
+        with pytest.raises(pkg.KzgError) as e:
+            pkg.SRS.from_cache(str(cache), 3001, engine=pkg.Engine(0))
+        assert e.value.msg == "Number of points to load exceeds SRS order."
+        blob = bytearray(cache.read_bytes())
+        blob[64 + 64 * 2000 + 5] ^= 0x10  # one flipped bit in point 2000
+        dmg = tmp_path / "damaged.cache"
+        dmg.write_bytes(bytes(blob))
+        with pytest.raises(pkg.KzgError) as e:
+            pkg.SRS.from_cache(str(dmg), engine=pkg.Engine(0))
+        assert e.value.variant == "NotOnCurveError" and "2000" in e.value.msg
+        dmg.write_bytes(bytes(blob[: 64 + 64 * 100]))  # truncated
+        with pytest.raises(pkg.KzgError):
+            pkg.SRS.from_cache(str(dmg), 3000, engine=pkg.Engine(0))
+        dmg.write_bytes(raw)
+        with pytest.raises(pkg.KzgError) as e:
+            pkg.SRS.from_cache(str(dmg), engine=pkg.Engine(0))
+        assert e.value.variant == "DeserializationError"
+    finally:
+        lib.kzgb_set_option(b"srs_chunk_points", 0)
+
+
 def test_to_fr_array_kat(pkg, eng):
     assert pkg.to_fr_array(g.blobs_txt(), eng) == g.blobs_from_fr()
     for raw in (b"", b"\x01", bytes(range(33)), b"\xff" * 95, g.gettysburg()):
