@@ -78,7 +78,18 @@ def run_c4(args):
     a = 0x1D5F3C29A7B4E6081122334455667788990AABBCCDDEEFF0123456789ABCDEF1 % R_MOD  # scalar base
     t0 = time.perf_counter()
     srs = pkg.SRS.synthetic(count, TAU, engine=eng, first=first)
-    srs.precompute(0, -1)  # no window tables: variable-base mode over this rank's range
+    # fixed-base window tables over this rank's point range (W x count x 64 B: 51.5 GB for 2^26 points on one
+    # GPU, 6.9 GB per GPU at 8); KZGB_C4_TABLES=0 or a failed allocation -> variable-base mode (one bucket set per window)
+    tables = os.environ.get("KZGB_C4_TABLES", "1") != "0"
+    if tables:
+        try:
+            srs.precompute(count, int(os.environ.get("KZGB_WINDOW_BITS", "0")))
+        except pkg.KzgError:
+            tables = False
+    if not tables:
+        srs.precompute(0, -1)
+    cbits, cwin, ctab = C.c_int(0), C.c_int(0), C.c_size_t(0)
+    lib.kzgb_msm_config(eng.h, C.byref(cbits), C.byref(cwin), C.byref(ctab))
     scal = torch.empty(count * 32, dtype=torch.uint8, device="cuda")
     eng.check(lib.kzgb_fr_powers_dev(eng.h, _fr_mont(a), first, count, scal.data_ptr()))
     host_scal = scal.cpu().pin_memory()
@@ -142,7 +153,8 @@ def run_c4(args):
             "dtype": "u32 (8x32-bit Montgomery limbs, BN254 Fq/Fr)", "data": "synthetic",
             "config": {"workload": "standalone 2^%d-point G1 MSM over SRS_i = tau^i G, scalars a^i, sharded by point range; "
                                    "partial sums exchanged with one all_gather (65 B/rank) and added on every rank" % logn,
-                       "points_per_rank": count, "l2": "inputs larger than L2: %d MiB of points + %d MiB of scalars per rank" % (count * 64 >> 20, count * 32 >> 20)},
+                       "points_per_rank": count, "fixed_base_tables": bool(ctab.value), "msm_window_bits": cbits.value,
+                       "msm_windows": cwin.value, "table_GiB_per_rank": cwin.value * ctab.value * 64 / 2**30, "l2": "inputs larger than L2: %d MiB of points + %d MiB of scalars per rank" % (count * 64 >> 20, count * 32 >> 20)},
             "e2e": {"value": N * args.steps / (e2e_ms * 1e-3) / 1e6, "unit": "Mpts/s", "h2d_bytes_per_step": count * 32,
                     "d2h_bytes_per_step": 128 * 16, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": launches, "clocks": sampler.summary(),

@@ -56,6 +56,7 @@ struct Lane {
     Fr* h_fr = nullptr;       // pinned, 16 elements
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_done = nullptr;
     bool ev_pending = false;
+    bool throughput = false;  // driven by a batch pipeline: plans trade MSM latency for less work
     double acc_ms = 0;        // summed duration of bucket-accumulation kernels
     uint64_t acc_launches = 0;
     uint64_t acc_adds = 0;    // point additions those kernels performed (n * W upper bound)
@@ -201,7 +202,11 @@ int choose_c_var(size_t n) {
 }
 int choose_c_fixed(size_t n) {
     int best = 4; double bc = 1e300;
-    for (int c = 4; c <= 17; c++) {  // measured at n = 2^19: c = 17 beats 16 (1.99 vs 2.08 ms); 18+ lose to the bucket tail
+    // measured at n = 2^19: c = 17 beats 16 (1.99 vs 2.08 ms); 18+ lose to the bucket tail.  Point-range shards
+    // of a very large MSM (2^22 .. 2^26 points per GPU) amortise a longer tail: up to c = 22 (W = 12, a
+    // 51.5 GB table at 2^26 points -- what 180 GB of HBM is for).
+    const int c_max = n > ((size_t)1 << 20) ? 22 : 17;
+    for (int c = 4; c <= c_max; c++) {
         int W = (255 + c - 1) / c;
         double cost = (double)n * W * 10.0 + (double)(1u << (c - 1)) * 140.0;  // the bucket tail is latency-bound
         if (cost < bc) { bc = cost; best = c; }
@@ -384,7 +389,7 @@ int msm_enqueue(kzgb_ctx* c, Lane& L, const Fr* d_scalars, bool canonical, size_
     MsmPlan p;
     const Affine* table;
     if (lag) {
-        p = msm_make_plan((uint32_t)n, lag->c, true, (uint32_t)lag->n, 0);
+        p = msm_make_plan((uint32_t)n, lag->c, true, (uint32_t)lag->n, 0, 0, L.throughput);
         table = lag->table;
     } else if (!var_bases) {
         if (first + n > c->srs_n) return fail(c, KZGB_ERR_GENERIC, "MSM range exceeds the SRS");
@@ -394,7 +399,7 @@ int msm_enqueue(kzgb_ctx* c, Lane& L, const Fr* d_scalars, bool canonical, size_
             if (rc && rc != KZGB_ERR_DEVICE) return rc;
         }
         if (c->wtable && first + n <= c->wt_n) {
-            p = msm_make_plan((uint32_t)n, c->wt_c, true, (uint32_t)c->wt_n, (uint32_t)first);
+            p = msm_make_plan((uint32_t)n, c->wt_c, true, (uint32_t)c->wt_n, (uint32_t)first, 0, L.throughput);
             table = c->wtable;
         } else {
             p = msm_make_plan((uint32_t)n, choose_c_var(n), false, 0, 0);
@@ -472,11 +477,11 @@ int msm_enqueue_batched(kzgb_ctx* c, Lane& L, const Fr* d_scalars, size_t n_per,
     const Affine* table;
     MsmPlan p;
     if (lag) {
-        p = msm_make_plan((uint32_t)(n_per * batch), lag->c, true, (uint32_t)lag->n, 0, (uint32_t)batch);
+        p = msm_make_plan((uint32_t)(n_per * batch), lag->c, true, (uint32_t)lag->n, 0, (uint32_t)batch, L.throughput);
         table = lag->table;
     } else {
         if (!c->wtable || n_per > c->wt_n) return fail(c, KZGB_ERR_GENERIC, "batched MSM needs a fixed-base table");
-        p = msm_make_plan((uint32_t)(n_per * batch), c->wt_c, true, (uint32_t)c->wt_n, 0, (uint32_t)batch);
+        p = msm_make_plan((uint32_t)(n_per * batch), c->wt_c, true, (uint32_t)c->wt_n, 0, (uint32_t)batch, L.throughput);
         table = c->wtable;
     }
     if ((uint64_t)n_per * batch * p.W >= 0xfff00000ull) return fail(c, KZGB_ERR_GENERIC, "MSM too large for one launch");
@@ -1300,6 +1305,8 @@ static int batch_impl(kzgb_ctx* c, const uint8_t* const* blobs_dev, const uint8_
         auto group_main = [&](int li) {
             cudaSetDevice(c->device);
             Lane& L = c->lanes[li];
+            L.throughput = true;
+            struct Reset { Lane& l; ~Reset() { l.throughput = false; } } reset{L};
             std::vector<Affine> pts;
             std::vector<Fr> zt;
             for (;;) {
@@ -1408,6 +1415,8 @@ static int batch_impl(kzgb_ctx* c, const uint8_t* const* blobs_dev, const uint8_
     auto lane_main = [&](int li) {
         cudaSetDevice(c->device);
         Lane& L = c->lanes[li];
+        L.throughput = count > 1;
+        struct Reset { Lane& l; ~Reset() { l.throughput = false; } } reset{L};
         for (;;) {
             size_t i = 0;
             bool is_proof = false;

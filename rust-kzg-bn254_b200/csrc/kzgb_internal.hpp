@@ -58,7 +58,9 @@ size_t msm_workspace_bytes(const MsmPlan& p);
 void msm_workspace_carve(const MsmPlan& p, void* base, MsmWorkspace* ws);
 // batch > 0 (fixed base only): n = batch * (n / batch) scalars of `batch` independent MSMs over the same
 // table points [base_offset, base_offset + n / batch); set_sums[k] is the result of MSM k.
-MsmPlan msm_make_plan(uint32_t n, int c, bool fixed_base, uint32_t table_stride, uint32_t base_offset, uint32_t batch = 0);
+// throughput: the MSM runs inside a pipeline of several lanes (longer bucket-reduce slices: less work, more latency).
+MsmPlan msm_make_plan(uint32_t n, int c, bool fixed_base, uint32_t table_stride, uint32_t base_offset, uint32_t batch = 0,
+                      bool throughput = false);
 // Batch-affine tuning: levels (default 0 = off), minimum average bucket occupancy for it to be
 // used (default 64), pairs per thread at level 0 (0 = default: one wave per level).  Negative values keep
 // the current setting.

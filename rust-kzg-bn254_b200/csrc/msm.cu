@@ -667,7 +667,7 @@ static void tuning_from_env() {
     if ((e = getenv("KZGB_BA_K0")) && atoi(e) >= 0) g_ba_k0 = atoi(e);
 }
 
-MsmPlan msm_make_plan(uint32_t n, int c, bool fixed_base, uint32_t table_stride, uint32_t base_offset, uint32_t batch) {
+MsmPlan msm_make_plan(uint32_t n, int c, bool fixed_base, uint32_t table_stride, uint32_t base_offset, uint32_t batch, bool throughput) {
     tuning_from_env();
     MsmPlan p;
     p.c = c;
@@ -707,7 +707,19 @@ MsmPlan msm_make_plan(uint32_t n, int c, bool fixed_base, uint32_t table_stride,
     p.chunk = (uint32_t)((tail + p.acc_threads - 1) / p.acc_threads);
     if (p.chunk == 0) p.chunk = 1;
     uint32_t half = 1u << (c - 1);
+    // Buckets per bucket-reduce thread.  A thread does 2 XYZZ additions per bucket plus one small scalar
+    // multiplication per slice, so longer slices mean less work but a longer serial chain.  Measured on the
+    // 2^19 pipeline (profiles/r01_sweep_slice.txt): 4 -> 283, 8 -> 299, 16 -> 304, 32 -> 306 blobs/s (the
+    // fat, latency-bound reduce blocks displace accumulation blocks while they are resident); alone, one
+    // MSM is fastest at 8 (1.975 ms) and 0.3 ms slower at 32.  So: 32 for pipelines (throughput), 8 for single calls.
     p.slice = half >= 1024 ? 4 : (half >= 4 ? 2 : 1);
+    if (half >= 2048) p.slice = 8;
+    if (throughput && half >= 8192) p.slice = 32;
+    {  // KZGB_SLICE overrides (power of two)
+        static int slice_env = -1;
+        if (slice_env < 0) { const char* e = getenv("KZGB_SLICE"); slice_env = e ? atoi(e) : 0; }
+        if (slice_env > 0 && (slice_env & (slice_env - 1)) == 0 && (uint32_t)slice_env * 256u <= half) p.slice = (uint32_t)slice_env;
+    }
     return p;
 }
 
