@@ -216,11 +216,11 @@ __device__ __forceinline__ void xyzz_madd_call(XYZZ& acc, const Affine& q) {
 // Source of the entries: SRC_REFS = sorted refs into the table (gather), SRC_POINTS = the affine
 // points left by the batch-affine levels (entry `pos` is points[pos]; bucket offsets are the level-0
 // offsets >> shift).
-template <int MINB, bool CALL, bool PREFETCH, bool DIRECT>
-__global__ void __launch_bounds__(128, MINB) k_accumulate_t(const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ offsets,
-                                                              const Affine* __restrict__ table, uint32_t nb, uint32_t acc_threads,
-                                                              uint32_t chunk, int shift,
-                                                              XYZZ* __restrict__ buckets, XYZZ* __restrict__ partial) {
+template <bool CALL, bool PREFETCH, bool DIRECT>
+__device__ __forceinline__ void accumulate_body(const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ offsets,
+                                                const Affine* __restrict__ table, uint32_t nb, uint32_t acc_threads,
+                                                uint32_t chunk, int shift,
+                                                XYZZ* __restrict__ buckets, XYZZ* __restrict__ partial) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= acc_threads) return;
     const uint32_t M = offsets[nb] >> shift;
@@ -264,6 +264,24 @@ __global__ void __launch_bounds__(128, MINB) k_accumulate_t(const uint32_t* __re
         else if (run_begin <= start) xyzz_store(&partial[2 * t], acc);
         else xyzz_store(&partial[2 * t + 1], acc);
     }
+}
+
+template <int MINB, bool CALL, bool PREFETCH, bool DIRECT>
+__global__ void __launch_bounds__(128, MINB) k_accumulate_t(const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ offsets,
+                                                              const Affine* __restrict__ table, uint32_t nb, uint32_t acc_threads,
+                                                              uint32_t chunk, int shift,
+                                                              XYZZ* __restrict__ buckets, XYZZ* __restrict__ partial) {
+    accumulate_body<CALL, PREFETCH, DIRECT>(sorted, offsets, table, nb, acc_threads, chunk, shift, buckets, partial);
+}
+// Same body under a hard register cap instead of a blocks-per-SM hint: at 112 registers four blocks leave
+// 8 K registers of every SM free, so the small blocks of the other lanes' sort kernels can be resident
+// NEXT TO the accumulation instead of displacing it (ptxas: 112 registers, no spills; 96: 28 B of spills).
+template <int MAXR>
+__global__ void __maxnreg__(MAXR) k_accumulate_r(const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ offsets,
+                                                  const Affine* __restrict__ table, uint32_t nb, uint32_t acc_threads,
+                                                  uint32_t chunk, int shift,
+                                                  XYZZ* __restrict__ buckets, XYZZ* __restrict__ partial) {
+    accumulate_body<false, false, false>(sorted, offsets, table, nb, acc_threads, chunk, shift, buckets, partial);
 }
 
 // Buckets whose entries span more than LONG_SPAN chunks (hot buckets: equal scalars, a top window with a
@@ -847,6 +865,10 @@ void msm_launch(const MsmPlan& p, const MsmWorkspace& ws, const Fr* scalars, boo
                 case 1: KZ_ACC(3, false, true, false); break;
                 case 3: KZ_ACC(4, true, true, false); break;
                 case 9: KZ_ACC(5, false, true, false); break;
+                case 11: k_accumulate_r<112><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, L, ws.buckets, ws.partial); break;
+                case 12: k_accumulate_r<96><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, L, ws.buckets, ws.partial); break;
+                case 13: k_accumulate_r<104><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, L, ws.buckets, ws.partial); break;
+                case 14: k_accumulate_r<80><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, L, ws.buckets, ws.partial); break;
                 default: KZ_ACC(4, false, false, false); break;
             }
         }
