@@ -664,18 +664,25 @@ int srs_ingest_stream(kzgb_ctx* c, size_t n, bool raw, Reader read) {
     DevBuf stage[2], errb;
     Affine* pts = nullptr;
     int rc = KZGB_OK;
+    bool pinned = true;
     auto cleanup = [&]() {
-        for (int k = 0; k < 2; k++) { if (pin[k]) cudaFreeHost(pin[k]); if (ev[k]) cudaEventDestroy(ev[k]); stage[k].release(); }
+        for (int k = 0; k < 2; k++) {
+            if (pin[k]) { if (pinned) cudaFreeHost(pin[k]); else free(pin[k]); }
+            if (ev[k]) cudaEventDestroy(ev[k]);
+            stage[k].release();
+        }
         errb.release();
     };
     auto ck = [&](cudaError_t e, const char* what) {
         if (!rc && e != cudaSuccess) rc = fail(c, KZGB_ERR_DEVICE, std::string("CUDA error: ") + cudaGetErrorString(e) + " at " + what);
     };
     const size_t n_chunks = (n + chunk - 1) / chunk;
+    pinned = n_chunks > 1;  // a single chunk has nothing to overlap with: skip the (slow) pinned allocation
     ck(cudaMalloc((void**)&pts, n * sizeof(Affine)), "cudaMalloc(SRS points)");
     ck(errb.reserve(4 * n_chunks), "cudaMalloc");
-    for (int k = 0; k < 2 && !rc; k++) {
-        ck(cudaMallocHost((void**)&pin[k], chunk * unit), "cudaMallocHost(staging)");
+    for (int k = 0; k < (pinned ? 2 : 1) && !rc; k++) {
+        if (pinned) ck(cudaMallocHost((void**)&pin[k], chunk * unit), "cudaMallocHost(staging)");
+        else if (!(pin[k] = (uint8_t*)malloc(chunk * unit))) rc = fail(c, KZGB_ERR_GENERIC, "out of host memory");
         ck(cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming), "cudaEventCreate");
         if (!raw) ck(stage[k].reserve(chunk * unit), "cudaMalloc(staging)");
     }

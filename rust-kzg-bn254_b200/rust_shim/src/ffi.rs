@@ -24,6 +24,10 @@ extern "C" {
     pub fn kzgb_ctx_destroy(ctx: *mut kzgb_ctx);
     pub fn kzgb_last_error(ctx: *const kzgb_ctx) -> *const c_char;
     pub fn kzgb_srs_load_file(ctx: *mut kzgb_ctx, path: *const c_char, order: u32, points_to_load: u32) -> c_int;
+    pub fn kzgb_srs_save_cache(ctx: *mut kzgb_ctx, path: *const c_char) -> c_int;
+    pub fn kzgb_srs_load_cache(ctx: *mut kzgb_ctx, path: *const c_char, points_to_load: u32) -> c_int;
+    pub fn kzgb_srs_precompute(ctx: *mut kzgb_ctx, max_n: usize, window_bits: c_int) -> c_int;
+    pub fn kzgb_srs_prepare_lagrange(ctx: *mut kzgb_ctx, n: usize) -> c_int;
     pub fn kzgb_srs_load_affine_mont(ctx: *mut kzgb_ctx, xy: *const u64, inf: *const u8, n: usize) -> c_int;
     pub fn kzgb_srs_len(ctx: *const kzgb_ctx) -> usize;
     pub fn kzgb_srs_get_affine_mont(ctx: *mut kzgb_ctx, start: usize, count: usize, out_xy: *mut u64, out_inf: *mut u8) -> c_int;
