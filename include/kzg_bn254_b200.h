@@ -206,6 +206,8 @@ int kzgb_msm_tuning(int batch_affine_levels, int min_avg_bucket, int pairs_per_t
  *   "fs_device"            -1 auto (default), 0 host SHA-256 pool, 1 device kernel for the per-blob
  *                          Fiat-Shamir challenges of kzgb_verify_batch_rlc (auto: >= 256 blobs of <= 2^13 Fr)
  *   "batch_affine_levels"  as in kzgb_msm_tuning
+ *   "eval_structured"      1 (default): for z outside the domain the barycentric denominators 1/(z - w_i) come from
+ *                          the factorisation of z^n - 1 (~3 multiplications each); 0: generic prefix/suffix products
  *   "srs_chunk_points"     points per chunk of the streamed SRS ingest (0 = default 2^22)
  *   "group"                -1 (default): kzgb_commit_and_prove_blobs processes runs of equal-size blobs of
  *                          <= 2^17 Fr as groups (one batched launch set per phase and group, sized so a group

@@ -133,11 +133,11 @@ Fr ninv_mont(int logn) {
     return r;
 }
 // 1 / prod_i (z - w_i) with the zero factor (z = w_m) replaced by 1: prod = z^n - 1, or n / z in the domain
-Fr eval_tinv(const Fr& z, int logn) {
+Fr eval_tinv(const Fr& z, int logn, bool* in_domain = nullptr) {
     Fr zn = z, one, r;
     for (int k = 0; k < logn; k++) fe_sqr(zn, zn);
     fe_one(one);
-    if (fe_eq(zn, one)) { Fr ni = ninv_mont(logn); fe_mul(r, z, ni); return r; }
+    if (fe_eq(zn, one)) { if (in_domain) *in_domain = true; Fr ni = ninv_mont(logn); fe_mul(r, z, ni); return r; }
     fe_sub(zn, zn, one);
     fe_inv(r, zn);
     return r;
@@ -535,11 +535,12 @@ int proof_enqueue(kzgb_ctx* c, Lane& L, const Fr* d_evals, size_t n, const Fr& z
     Fr* d_z = (Fr*)L.small.p;  // [z, tinv, y]
     Fr* d_y = d_z + 2;
     L.h_fr[0] = z_mont;
-    L.h_fr[1] = eval_tinv(z_mont, logn);
+    bool in_domain = false;
+    L.h_fr[1] = eval_tinv(z_mont, logn, &in_domain);
     CK(c, cudaMemcpyAsync(d_z, &L.h_fr[0], 2 * sizeof(Fr), cudaMemcpyHostToDevice, L.st));
     Fr ninv = ninv_mont(logn);
     eval_quotient_launch(d_evals, (uint32_t)n, logn, 1, d_z, d_z + 1, c->tw, c->logN, &ninv, (Fr*)L.eval_scratch.p,
-                         (Fr*)L.work.p, d_y, L.st);
+                         (Fr*)L.work.p, d_y, L.st, !in_domain);
     if (c->lag[logn].table && g_lagrange.load())  // quotient in evaluation form against the Lagrange-basis table
         return msm_enqueue(c, L, (Fr*)L.work.p, false, 0, n, nullptr, job, &c->lag[logn]);
     ntt_launch((Fr*)L.work.p, logn, 1, true, c->tw, c->logN, &ninv, (Fr*)L.ntt_scratch.p, L.st);
@@ -1169,12 +1170,13 @@ int kzgb_evaluate_polynomial(kzgb_ctx* c, const uint64_t* evals, size_t n, const
     CK(c, L.small.reserve(64 * sizeof(Fr)));
     CK(c, cudaMemcpyAsync(L.evals.p, evals, n * sizeof(Fr), cudaMemcpyHostToDevice, L.st));
     memcpy(L.h_fr[0].l, z_mont, 32);
-    L.h_fr[1] = eval_tinv(L.h_fr[0], logn);
+    bool in_domain = false;
+    L.h_fr[1] = eval_tinv(L.h_fr[0], logn, &in_domain);
     Fr* d_z = (Fr*)L.small.p;
     CK(c, cudaMemcpyAsync(d_z, &L.h_fr[0], 2 * sizeof(Fr), cudaMemcpyHostToDevice, L.st));
     Fr ninv = ninv_mont(logn);
     eval_quotient_launch((Fr*)L.evals.p, (uint32_t)n, logn, 1, d_z, d_z + 1, c->tw, c->logN, &ninv,
-                         (Fr*)L.eval_scratch.p, nullptr, d_z + 2, L.st);
+                         (Fr*)L.eval_scratch.p, nullptr, d_z + 2, L.st, !in_domain);
     CK(c, cudaMemcpyAsync(&L.h_fr[3], d_z + 2, sizeof(Fr), cudaMemcpyDeviceToHost, L.st));
     CK(c, cudaStreamSynchronize(L.st));
     CK(c, cudaGetLastError());
@@ -1372,14 +1374,15 @@ static int batch_impl(kzgb_ctx* c, const uint8_t* const* blobs_dev, const uint8_
                         for (size_t k = 0; k < b; k++) cv.wait(lk, [&] { return ready[i0 + k] != 0 || failed; });
                         if (failed) return;
                     }
+                    bool any_in_domain = false;
                     for (size_t k = 0; k < b; k++) {
                         zt[k] = challenge_finish(mid[i0 + k], pts[k]);
-                        zt[b + k] = eval_tinv(zt[k], logn);
+                        zt[b + k] = eval_tinv(zt[k], logn, &any_in_domain);
                     }
                     Fr* d_z = (Fr*)L.small.p;  // [z x b | tinv x b | y x b]
                     ck(cudaMemcpyAsync(d_z, zt.data(), 2 * b * sizeof(Fr), cudaMemcpyHostToDevice, L.st), "H2D of the challenges");
                     eval_quotient_launch((Fr*)L.evals.p, (uint32_t)n, logn, (uint32_t)b, d_z, d_z + b, c->tw, c->logN, &ninv,
-                                         (Fr*)L.eval_scratch.p, (Fr*)L.work.p, d_z + 2 * b, L.st);
+                                         (Fr*)L.eval_scratch.p, (Fr*)L.work.p, d_z + 2 * b, L.st, !any_in_domain);
                     if (!lag) ntt_launch((Fr*)L.work.p, logn, (uint32_t)b, true, c->tw, c->logN, &ninv, (Fr*)L.ntt_scratch.p, L.st);
                     if (!r) r = msm_enqueue_batched(c, L, (const Fr*)L.work.p, n, b, lag, &job);
                     if (!r) r = msm_finish_batched(c, L, job, b, pts.data());
@@ -1599,6 +1602,7 @@ int kzgb_verify_batch_rlc(kzgb_ctx* c, const uint8_t* const* blobs, const size_t
         Fr ninv = ninv_mont(logn);
         std::vector<Fr> tinvs;
         std::vector<uint8_t> cbytes;
+        bool any_in_domain = false;  // (challenges hashed on the device are not known here: generic inverses)
         if (fs_device) {
             uint8_t* d_c32 = (uint8_t*)(d_y + b);
             cbytes.resize(b * 32);
@@ -1608,12 +1612,12 @@ int kzgb_verify_batch_rlc(kzgb_ctx* c, const uint8_t* const* blobs, const size_t
             CK(c, cudaMemcpyAsync(&zs[i0], d_z, b * sizeof(Fr), cudaMemcpyDeviceToHost, L.st));
         } else {
             tinvs.resize(b);
-            for (size_t k = 0; k < b; k++) tinvs[k] = eval_tinv(zs[i0 + k], logn);
+            for (size_t k = 0; k < b; k++) tinvs[k] = eval_tinv(zs[i0 + k], logn, &any_in_domain);
             CK(c, cudaMemcpyAsync(d_z, &zs[i0], b * sizeof(Fr), cudaMemcpyHostToDevice, L.st));
             CK(c, cudaMemcpyAsync(d_t, tinvs.data(), b * sizeof(Fr), cudaMemcpyHostToDevice, L.st));
         }
         eval_quotient_launch((Fr*)L.evals.p, (uint32_t)n, logn, (uint32_t)b, d_z, d_t, c->tw, c->logN, &ninv,
-                             (Fr*)L.eval_scratch.p, nullptr, d_y, L.st);
+                             (Fr*)L.eval_scratch.p, nullptr, d_y, L.st, !fs_device && !any_in_domain);
         CK(c, cudaMemcpyAsync(&ys[i0], d_y, b * sizeof(Fr), cudaMemcpyDeviceToHost, L.st));
         CK(c, cudaStreamSynchronize(L.st));
         CK(c, cudaGetLastError());
@@ -1808,6 +1812,7 @@ int kzgb_set_option(const char* name, long value) {
     if (!name) return KZGB_ERR_GENERIC;
     if (!strcmp(name, "fs_device")) { g_fs_device.store((int)value); return KZGB_OK; }
     if (!strcmp(name, "srs_chunk_points")) { g_srs_chunk.store(value < 0 ? 0 : value); return KZGB_OK; }
+    if (!strcmp(name, "eval_structured")) { eval_set_structured((int)value); return KZGB_OK; }
     if (!strcmp(name, "group")) { g_group.store((int)value); return KZGB_OK; }
     if (!strcmp(name, "lagrange")) { g_lagrange.store(value != 0); return KZGB_OK; }
     if (!strcmp(name, "batch_affine_levels")) { msm_set_tuning((int)value, -1, -1); return KZGB_OK; }

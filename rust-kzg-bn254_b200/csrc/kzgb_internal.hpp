@@ -116,8 +116,12 @@ void fr_to_bytes_launch(const Fr* in, uint8_t* out, uint32_t n, cudaStream_t st)
 // tinv_mont_dev[batch]: 1/(z^n - 1), or z/n when z^n == 1 (one host inversion per polynomial).
 void eval_quotient_launch(const Fr* evals, uint32_t n, int logn, uint32_t batch, const Fr* z_mont_dev,
                           const Fr* tinv_mont_dev, const Fr* tw, int logN, const Fr* ninv_mont_host, Fr* scratch,
-                          Fr* q_out, Fr* y_out, cudaStream_t st);
+                          Fr* q_out, Fr* y_out, cudaStream_t st, bool z_outside_domain = false);
+// z_outside_domain: the caller knows that no z of the batch is a root of the domain (z^n != 1); the
+// inverses then come from the factorisation of z^n - 1 (~3 instead of ~10 multiplications per element).
 size_t eval_quotient_scratch_elems(uint32_t n, uint32_t batch);
+// 0: always the generic prefix/suffix-product inverses (tests compare the two forms)
+void eval_set_structured(int on);
 // Fiat-Shamir challenges of `batch` blobs of n evaluations each on the device (fs.cu; reference
 // primitives/src/helpers.rs:411-472): z_out[k] (Montgomery) and tinv_out[k] = 1/(z^n - 1) (or z/n in the
 // domain).  commit32_dev: batch x 32 bytes, arkworks-compressed commitments.

@@ -7,6 +7,7 @@
 // The reference does n separate field inversions (twice); here the n denominators z - w_i are
 // inverted with Montgomery's trick: 8 per thread in registers, a product scan across the warp
 // with shuffles, ONE Fermat inversion per warp.
+#include <cstdlib>
 #include "kzgb_internal.hpp"
 
 namespace kzgb {
@@ -95,7 +96,7 @@ __device__ __forceinline__ void block_sum_fr(Fr v, Fr* out) {
     __syncthreads();
     if (threadIdx.x == 0) {
         Fr acc = v;
-        for (int w = 1; w < EVAL_THREADS / 32; w++) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); w++) {  // blockDim.x <= EVAL_THREADS
             Fr o;
 #pragma unroll
             for (int k = 0; k < 8; k++) o.l[k] = red[k][w];
@@ -292,6 +293,87 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_eval_inverses(const Fr* __rest
     block_sum_fr(sum, &partial[blockIdx.x]);
 }
 
+// ---- the same inverses from the STRUCTURE of the domain, for z outside it (the generic case: z is a hash) ----
+//     (z - w_i) * prod_{j < k} (z^(2^j) + w_i^(2^j)) = z^n - 1        (n = 2^k)
+// so 1/(z - w_i) = T^-1 * prod_j (Z_j + w^((i << j) mod n)), Z_j = z^(2^j), and the factor of level j only
+// depends on i mod (n >> j): a thread that owns the 16 elements i = r + t * n/16 shares the k - 4 top factors
+// among all of them and the lower ones pairwise -> (k - 3) + 30 multiplications per 16 inverses (2.8 per
+// element instead of ~10 for the prefix/suffix products), no block or grid level products at all.
+static constexpr int EV2_THREADS = 128;
+static std::atomic<int> g_eval_structured{getenv("KZGB_EVAL_STRUCTURED") ? atoi(getenv("KZGB_EVAL_STRUCTURED")) : 1};
+void eval_set_structured(int on) { g_eval_structured.store(on != 0); }
+static constexpr int ZP_STRIDE = 32;  // Z_j slots per polynomial
+
+__global__ void __launch_bounds__(64) k_eval_zpowers(const Fr* __restrict__ z_all, int logn, uint32_t batch, Fr* __restrict__ zp_all) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    Fr z = fe_load(&z_all[b]);
+    for (int j = 0; j < logn; j++) {
+        fe_store(&zp_all[(size_t)b * ZP_STRIDE + j], z);
+        fe_sqr(z, z);
+    }
+}
+
+__global__ void __launch_bounds__(EV2_THREADS) k_eval_inverses2(const Fr* __restrict__ evals_all, uint32_t n, int logn,
+                                                                 const Fr* __restrict__ tw, int logN,
+                                                                 const Fr* __restrict__ tinv_all, const Fr* __restrict__ zp_all,
+                                                                 Fr* __restrict__ inv_all, Fr* __restrict__ partial_all,
+                                                                 uint32_t nparts) {
+    __shared__ Fr zs[ZP_STRIDE];
+    const uint32_t bi = blockIdx.y;
+    if ((int)threadIdx.x < logn) zs[threadIdx.x] = fe_load(&zp_all[(size_t)bi * ZP_STRIDE + threadIdx.x]);
+    __syncthreads();
+    const Fr* evals = evals_all + (size_t)bi * n;
+    Fr* inv = inv_all + (size_t)bi * n;
+    const uint32_t q = n >> 4, mask = n - 1;
+    const uint32_t r = blockIdx.x * EV2_THREADS + threadIdx.x;
+    Fr sum; fe_zero(sum);
+    if (r < q) {
+        Fr P4 = fe_load(&tinv_all[bi]);  // 1 / (z^n - 1)
+#pragma unroll 1
+        for (int m = logn - 1; m >= 4; m--) {
+            Fr t = domain_root(tw, (r << m) & mask, logn, logN);
+            fe_add(t, t, zs[m]);
+            fe_mul(P4, P4, t);
+        }
+#pragma unroll 1
+        for (uint32_t a = 0; a < 2; a++) {
+            const uint32_t i3 = r + a * q;
+            Fr P3 = domain_root(tw, (i3 << 3) & mask, logn, logN);
+            fe_add(P3, P3, zs[3]);
+            fe_mul(P3, P3, P4);
+#pragma unroll 1
+            for (uint32_t b = 0; b < 2; b++) {
+                const uint32_t i2 = i3 + 2 * b * q;
+                Fr P2 = domain_root(tw, (i2 << 2) & mask, logn, logN);
+                fe_add(P2, P2, zs[2]);
+                fe_mul(P2, P2, P3);
+#pragma unroll 1
+                for (uint32_t cc = 0; cc < 2; cc++) {
+                    const uint32_t i1 = i2 + 4 * cc * q;
+                    Fr P1 = domain_root(tw, (i1 << 1) & mask, logn, logN);
+                    fe_add(P1, P1, zs[1]);
+                    fe_mul(P1, P1, P2);
+#pragma unroll 1
+                    for (uint32_t d = 0; d < 2; d++) {
+                        const uint32_t i0 = i1 + 8 * d * q;
+                        Fr w = domain_root(tw, i0, logn, logN);
+                        Fr iv;
+                        fe_add(iv, w, zs[0]);
+                        fe_mul(iv, iv, P1);  // 1 / (z - w_i)
+                        fe_store(&inv[i0], iv);
+                        Fr f = fe_load_ro(&evals[i0]);
+                        fe_mul(f, f, w);
+                        fe_mul(f, f, iv);
+                        fe_add(sum, sum, f);
+                    }
+                }
+            }
+        }
+    }
+    block_sum_fr(sum, &partial_all[(size_t)bi * nparts + blockIdx.x]);
+}
+
 // y = (z^n - 1)/n * sum   or   f_m when z = w_m          (one block per batch entry)
 __global__ void __launch_bounds__(EVAL_THREADS) k_eval_finish(const Fr* __restrict__ evals_all, uint32_t n, int logn,
                                                               const Fr* __restrict__ z_all, Fr ninv,
@@ -427,12 +509,12 @@ size_t eval_quotient_scratch_elems(uint32_t n, uint32_t batch) {
     uint32_t parts1 = (n + EVAL_TILE - 1) / EVAL_TILE;
     uint32_t parts2 = (n + EVAL_THREADS - 1) / EVAL_THREADS;
     // inverses, block products, block factors, partial sums (both kernels), zidx words (whole Fr slots)
-    return (size_t)batch * ((size_t)n + 3 * (size_t)parts1 + parts2) + ((size_t)batch * 4 + 31) / 32 + 1;
+    return (size_t)batch * ((size_t)n + 3 * (size_t)parts1 + parts2 + ZP_STRIDE) + ((size_t)batch * 4 + 31) / 32 + 1;
 }
 
 void eval_quotient_launch(const Fr* evals, uint32_t n, int logn, uint32_t batch, const Fr* z_mont_dev,
                           const Fr* tinv_mont_dev, const Fr* tw, int logN, const Fr* ninv_mont_host, Fr* scratch,
-                          Fr* q_out, Fr* y_out, cudaStream_t st) {
+                          Fr* q_out, Fr* y_out, cudaStream_t st, bool z_outside_domain) {
     if (!batch) return;
     uint32_t parts1 = (n + EVAL_TILE - 1) / EVAL_TILE;
     uint32_t parts2 = (n + EVAL_THREADS - 1) / EVAL_THREADS;
@@ -442,13 +524,24 @@ void eval_quotient_launch(const Fr* evals, uint32_t n, int logn, uint32_t batch,
     Fr* partial1 = fac + (size_t)batch * parts1;
     Fr* partial2 = partial1 + (size_t)batch * parts1;
     uint32_t* zidx = reinterpret_cast<uint32_t*>(partial2 + (size_t)batch * parts2);
+    Fr* zp = partial2 + (size_t)batch * parts2 + (((size_t)batch * 4 + 31) / 32 + 1);
     cudaMemsetAsync(zidx, 0, (size_t)batch * 4, st);
-    k_eval_block_products<<<dim3(parts1, batch), EVAL_THREADS, 0, st>>>(n, logn, z_mont_dev, tw, logN, bprod, parts1, zidx);
-    k_eval_block_factors<<<batch, EVAL_THREADS, 0, st>>>(bprod, parts1, tinv_mont_dev, fac);
-    k_eval_inverses<<<dim3(parts1, batch), EVAL_THREADS, 0, st>>>(evals, n, logn, z_mont_dev, tw, logN, fac, inv, partial1,
-                                                                  parts1);
+    if (z_outside_domain && g_eval_structured.load() && logn >= 6 && logn <= 28) {
+        // every z is outside the domain: inverses from the factorisation of z^n - 1 (EVAL_TILE = 16 * EV2_THREADS,
+        // so the per-block partial sums land exactly where k_eval_finish expects them)
+        static_assert(16 * EV2_THREADS == EVAL_TILE, "partial-sum layout");
+        k_eval_zpowers<<<(batch + 63) / 64, 64, 0, st>>>(z_mont_dev, logn, batch, zp);
+        k_eval_inverses2<<<dim3(parts1, batch), EV2_THREADS, 0, st>>>(evals, n, logn, tw, logN, tinv_mont_dev, zp, inv, partial1, parts1);
+        g_launch_count += 2;
+    } else {
+        k_eval_block_products<<<dim3(parts1, batch), EVAL_THREADS, 0, st>>>(n, logn, z_mont_dev, tw, logN, bprod, parts1, zidx);
+        k_eval_block_factors<<<batch, EVAL_THREADS, 0, st>>>(bprod, parts1, tinv_mont_dev, fac);
+        k_eval_inverses<<<dim3(parts1, batch), EVAL_THREADS, 0, st>>>(evals, n, logn, z_mont_dev, tw, logN, fac, inv, partial1,
+                                                                      parts1);
+        g_launch_count += 3;
+    }
     k_eval_finish<<<batch, EVAL_THREADS, 0, st>>>(evals, n, logn, z_mont_dev, *ninv_mont_host, partial1, parts1, zidx, y_out);
-    g_launch_count += 4;
+    g_launch_count += 1;
     if (q_out) {
         k_quotient<<<dim3(parts2, batch), EVAL_THREADS, 0, st>>>(evals, n, logn, tw, logN, inv, y_out, zidx, q_out,
                                                                  partial2, parts2);

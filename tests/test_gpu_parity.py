@@ -246,6 +246,34 @@ def test_evaluate_polynomial(pkg, eng):
             assert pkg.evaluate_polynomial_in_evaluation_form(pg, z, eng) == o.evaluate_polynomial_in_evaluation_form(po, z)
 
 
+@pytest.mark.parametrize("logn", [6, 7, 9, 12, 16])
+def test_structured_and_generic_denominators_agree(pkg, logn):
+    """1/(z - w_i) from the factorisation of z^n - 1 (z outside the domain) vs the generic prefix/suffix
+    products: same evaluation y and same proof, also for z = 0, z = 1 + r - 1 (= 0), z = 2 and a root (generic path)."""
+    n = 1 << logn
+    eng = pkg.Engine(0)
+    srs = pkg.SRS.synthetic(n, o.SYNTH_TAU, engine=eng)
+    rnd = random.Random(300 + logn)
+    ev = [rnd.randrange(o.R) for _ in range(n)]
+    poly = pkg.PolynomialEvalForm(ev)
+    kzg = pkg.KZG()
+    kzg.calculate_and_store_roots_of_unity(32 * n)
+    w = o.PRIMITIVE_ROOTS_OF_UNITY[logn]
+    zs = [rnd.randrange(o.R), 0, 2, o.R - 1 if logn == 0 else pow(w, 3, o.R), rnd.randrange(o.R)]
+    got = {}
+    try:
+        for mode in (1, 0):
+            assert pkg.lib.kzgb_set_option(b"eval_structured", mode) == 0
+            got[mode] = [(pkg.evaluate_polynomial_in_evaluation_form(poly, z, eng), kzg.compute_proof(poly, z, srs)) for z in zs]
+    finally:
+        pkg.lib.kzgb_set_option(b"eval_structured", 1)
+    assert got[0] == got[1]
+    if logn <= 9:
+        po = o.PolynomialEvalForm(ev)
+        for z, (y, _) in zip(zs, got[1]):
+            assert y == o.evaluate_polynomial_in_evaluation_form(po, z)
+
+
 def test_blob_proof_matches_oracle(pkg, ref_srs, ref_srs_points):
     rnd = random.Random(4)
     for raw in (g.gettysburg(), b"a", bytes(rnd.getrandbits(8) for _ in range(31 * 100 + 5))):
