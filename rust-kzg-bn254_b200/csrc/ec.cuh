@@ -42,9 +42,7 @@ KZ_HD void xyzz_dbl_affine(XYZZ& r, const Affine& p) {
     fe_sqr(r.x, M);
     fe_sub(r.x, r.x, S); fe_sub(r.x, r.x, S);
     fe_sub(t, S, r.x);
-    fe_mul(t, M, t);
-    fe_mul(U, W, p.y);
-    fe_sub(r.y, t, U);
+    fe_mul2sub(r.y, M, t, W, p.y);  // M (S - X3) - W y, one reduction
     r.zz = V;
     r.zzz = W;
 }
@@ -62,16 +60,18 @@ KZ_HD void xyzz_dbl(XYZZ& r, const XYZZ& p) {
     fe_sqr(X3, M);
     fe_sub(X3, X3, S); fe_sub(X3, X3, S);
     fe_sub(t, S, X3);
-    fe_mul(t, M, t);
-    fe_mul(U, W, p.y);
-    fe_sub(r.y, t, U);
+    {
+        Fq y1 = p.y;  // r may alias p
+        fe_mul2sub(r.y, M, t, W, y1);  // M (S - X3) - W Y1, one reduction
+    }
     r.x = X3;
     fe_mul(r.zz, V, p.zz);
     fe_mul(r.zzz, W, p.zzz);
 }
 
-// acc += affine q             (EFD madd-2008-s: 8M + 2S), exact on all inputs
-KZ_HD void xyzz_madd(XYZZ& acc, const Affine& q) {
+// acc += affine q             (EFD madd-2008-s: 8M + 2S), exact on all inputs; every product reduced on its
+// own (10 Montgomery reductions) -- kept for the kernel variant sweep, xyzz_madd below is the one in use
+KZ_HD void xyzz_madd_classic(XYZZ& acc, const Affine& q) {
     if (aff_is_inf(q)) return;
     if (xyzz_is_inf(acc)) { acc.x = q.x; acc.y = q.y; fe_one(acc.zz); fe_one(acc.zzz); return; }
     Fq U2, S2, Pp, Rr, PP, PPP, Q, t;
@@ -98,6 +98,34 @@ KZ_HD void xyzz_madd(XYZZ& acc, const Affine& q) {
     fe_mul(acc.zzz, acc.zzz, PPP);
 }
 
+// The same addition with the difference of products  Y3 = R*(Q - X3) - Y1*PPP  reduced ONCE
+// (fe_mul2sub): 9 Montgomery reductions instead of 10, bit-identical results
+// (1.245 -> 1.195 ms for the 2^19 accumulation, profiles/r01_sweep_slice.txt).
+KZ_HD void xyzz_madd(XYZZ& acc, const Affine& q) {
+    if (aff_is_inf(q)) return;
+    if (xyzz_is_inf(acc)) { acc.x = q.x; acc.y = q.y; fe_one(acc.zz); fe_one(acc.zzz); return; }
+    Fq U2, S2, Pp, Rr, PP, PPP, Q, t;
+    fe_mul(U2, q.x, acc.zz);
+    fe_mul(S2, q.y, acc.zzz);
+    fe_sub(Pp, U2, acc.x);
+    fe_sub(Rr, S2, acc.y);
+    if (fe_is_zero(Pp)) {
+        if (fe_is_zero(Rr)) xyzz_dbl_affine(acc, q);
+        else xyzz_set_inf(acc);
+        return;
+    }
+    fe_sqr(PP, Pp);
+    fe_mul(PPP, Pp, PP);
+    fe_mul(Q, acc.x, PP);
+    fe_mul(acc.zz, acc.zz, PP);
+    fe_mul(acc.zzz, acc.zzz, PPP);
+    fe_sqr(t, Rr);
+    fe_sub(t, t, PPP); fe_sub(t, t, Q); fe_sub(t, t, Q);  // X3
+    fe_sub(Q, Q, t);
+    fe_mul2sub(acc.y, Rr, Q, acc.y, PPP);
+    acc.x = t;
+}
+
 // acc += q                    (EFD add-2008-s: 12M + 2S), exact on all inputs
 KZ_HD void xyzz_add(XYZZ& acc, const XYZZ& q) {
     if (xyzz_is_inf(q)) return;
@@ -120,9 +148,7 @@ KZ_HD void xyzz_add(XYZZ& acc, const XYZZ& q) {
     fe_sqr(t, Rr);
     fe_sub(t, t, PPP); fe_sub(t, t, Q); fe_sub(t, t, Q);  // X3
     fe_sub(Q, Q, t);
-    fe_mul(Q, Rr, Q);
-    fe_mul(S1, S1, PPP);
-    fe_sub(acc.y, Q, S1);
+    fe_mul2sub(acc.y, Rr, Q, S1, PPP);  // R (Q - X3) - S1 PPP, one reduction
     acc.x = t;
     fe_mul(acc.zz, acc.zz, q.zz);
     fe_mul(acc.zz, acc.zz, PP);

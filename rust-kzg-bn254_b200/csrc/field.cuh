@@ -140,6 +140,17 @@ template <int F> KZ_HD void fe_sub(Fe<F>& r, const Fe<F>& a, const Fe<F>& b) {
     hostimpl::sub<F>(r.l, a.l, b.l);
 #endif
 }
+// r = a*b - c*d with ONE Montgomery reduction on the device (gen_field.py gen_mul2sub; Fq only)
+KZ_HD void fe_mul2sub(Fe<FQ>& r, const Fe<FQ>& a, const Fe<FQ>& b, const Fe<FQ>& c, const Fe<FQ>& d) {
+#ifdef __CUDA_ARCH__
+    fq_mul2sub_ptx(r.l, a.l, b.l, c.l, d.l);
+#else
+    Fe<FQ> t, u;
+    fe_mul(t, a, b);
+    fe_mul(u, c, d);
+    fe_sub(r, t, u);
+#endif
+}
 // r = a mod p for a < 2p
 template <int F> KZ_HD void fe_reduce_once(Fe<F>& r, const Fe<F>& a) {
 #ifdef __CUDA_ARCH__
