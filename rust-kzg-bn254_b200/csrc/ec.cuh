@@ -126,6 +126,53 @@ KZ_HD void xyzz_madd(XYZZ& acc, const Affine& q) {
     acc.x = t;
 }
 
+#ifdef __CUDACC__
+// ---- the same addition on RELAXED coordinates: every coordinate of acc lives in [0, 2p) instead of
+// [0, p).  4p < 2^256, so a Montgomery product of operands below 2p is again below 2p without its final
+// conditional subtraction (gen_field.py "mulnr"/"mul2subnr", ranges asserted by the emulator), and
+// a - b + 2p (if negative) stays in [0, 2p) ("sub2p").  Nine conditional subtractions less per
+// addition; the caller normalises with xyzz_relaxed_normalise before the accumulator leaves the loop.
+// q is canonical.  Zero tests are "congruent to 0": the value 0 or p.
+KZ_D bool fq_is_zero_mod(const Fq& a) {
+    const uint32_t pm[8] = FQ_MOD_LIMBS;
+    uint32_t z = 0, e = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { z |= a.l[i]; e |= a.l[i] ^ pm[i]; }
+    return z == 0 || e == 0;
+}
+KZ_D void xyzz_madd_relaxed(XYZZ& acc, const Affine& q) {
+    if (aff_is_inf(q)) return;
+    if (xyzz_is_inf(acc)) { acc.x = q.x; acc.y = q.y; fe_one(acc.zz); fe_one(acc.zzz); return; }
+    Fq U2, S2, Pp, Rr, PP, PPP, Q, t;
+    fq_mulnr_ptx(U2.l, q.x.l, acc.zz.l);
+    fq_mulnr_ptx(S2.l, q.y.l, acc.zzz.l);
+    fq_sub2p_ptx(Pp.l, U2.l, acc.x.l);
+    fq_sub2p_ptx(Rr.l, S2.l, acc.y.l);
+    if (fq_is_zero_mod(Pp)) {
+        if (fq_is_zero_mod(Rr)) xyzz_dbl_affine(acc, q);  // canonical result from the canonical q
+        else xyzz_set_inf(acc);
+        return;
+    }
+    fq_mulnr_ptx(PP.l, Pp.l, Pp.l);
+    fq_mulnr_ptx(PPP.l, Pp.l, PP.l);
+    fq_mulnr_ptx(Q.l, acc.x.l, PP.l);
+    fq_mulnr_ptx(acc.zz.l, acc.zz.l, PP.l);
+    fq_mulnr_ptx(acc.zzz.l, acc.zzz.l, PPP.l);
+    fq_mulnr_ptx(t.l, Rr.l, Rr.l);
+    fq_sub2p_ptx(t.l, t.l, PPP.l); fq_sub2p_ptx(t.l, t.l, Q.l); fq_sub2p_ptx(t.l, t.l, Q.l);  // X3
+    fq_sub2p_ptx(Q.l, Q.l, t.l);
+    fq_mul2subnr_ptx(acc.y.l, Rr.l, Q.l, acc.y.l, PPP.l);
+    acc.x = t;
+}
+// back to canonical coordinates (identity stays all-zero: zz == 0 exactly)
+KZ_D void xyzz_relaxed_normalise(XYZZ& acc) {
+    fq_reduce_once_ptx(acc.x.l, acc.x.l);
+    fq_reduce_once_ptx(acc.y.l, acc.y.l);
+    fq_reduce_once_ptx(acc.zz.l, acc.zz.l);
+    fq_reduce_once_ptx(acc.zzz.l, acc.zzz.l);
+}
+#endif
+
 // acc += q                    (EFD add-2008-s: 12M + 2S), exact on all inputs
 KZ_HD void xyzz_add(XYZZ& acc, const XYZZ& q) {
     if (xyzz_is_inf(q)) return;

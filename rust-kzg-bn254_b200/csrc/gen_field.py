@@ -151,14 +151,14 @@ def cond_sub(pr: Prog, src, mod, out, tag):
         pr.op("selp.u32", out[i], src[i], d[i], p)
 
 
-def gen_mul(field: str, sqr: bool = False) -> Prog:
+def gen_mul(field: str, sqr: bool = False, nr: bool = False) -> Prog:
     mod = FIELDS[field]
     pl = limbs(mod)
     np0 = (-pow(mod, -1, 1 << 32)) & MASK
     a = [f"a{i}" for i in range(8)]
     b = a if sqr else [f"b{i}" for i in range(8)]
     r = [f"r{i}" for i in range(8)]
-    pr = Prog(f"{field}_{'sqr' if sqr else 'mul'}", a + ([] if sqr else b), r)
+    pr = Prog(f"{field}_{'sqr' if sqr else 'mul'}{'nr' if nr else ''}", a + ([] if sqr else b), r)
     X = [pr.tmp(f"x{i}") for i in range(8)]  # two accumulators; roles swap every round
     Y = [pr.tmp(f"y{i}") for i in range(8)]
     m = pr.tmp("m")
@@ -214,7 +214,11 @@ def gen_mul(field: str, sqr: bool = False) -> Prog:
     for j in range(1, 7):
         pr.op("addc.cc.u32", s[j], A[j + 1], B[j])
     pr.op("addc.u32", s[7], B[7], 0)
-    cond_sub(pr, s, mod, r, "c")
+    if nr:  # "not reduced": operands and result in [0, 2p) (4p < 2^256), no final subtraction
+        for i in range(8):
+            pr.op("mov.u32", r[i], s[i])
+    else:
+        cond_sub(pr, s, mod, r, "c")
     return pr
 
 
@@ -340,7 +344,7 @@ def emit_karatsuba8(pr: Prog, nm: Namer, a, b):
     return T
 
 
-def emit_redc(pr: Prog, nm: Namer, T, mod, out, tag):
+def emit_redc(pr: Prog, nm: Namer, T, mod, out, tag, nr: bool = False):
     """Montgomery reduction of a 16-limb T < mod * 2^256: out = T / 2^256 mod p (fully reduced).
     Word-serial on the low half with the two shifting accumulators of gen_mul, then + T_hi."""
     pl = limbs(mod)
@@ -390,7 +394,11 @@ def emit_redc(pr: Prog, nm: Namer, T, mod, out, tag):
     for j in range(1, 7):
         pr.op("addc.cc.u32", u[j], s[j], T[8 + j])
     pr.op("addc.u32", u[7], s[7], T[15])
-    cond_sub(pr, u, mod, out, tag)
+    if nr:
+        for i in range(8):
+            pr.op("mov.u32", out[i], u[i])
+    else:
+        cond_sub(pr, u, mod, out, tag)
 
 
 def gen_mulk(field: str) -> Prog:
@@ -405,7 +413,7 @@ def gen_mulk(field: str) -> Prog:
     return pr
 
 
-def gen_mul2sub(field: str) -> Prog:
+def gen_mul2sub(field: str, nr: bool = False) -> Prog:
     """r = (a*b - c*d) / 2^256 mod p with ONE Montgomery reduction (lazy reduction of a difference of
     products: Y3 = R*(Q - X3) - Y1*PPP in XYZZ += affine).  Two plain 8x8 products (64 wide multiplies
     each), a 16-limb subtraction, + p*2^256 when it borrowed (so the value is in [0, p*2^256)), then the
@@ -417,7 +425,7 @@ def gen_mul2sub(field: str) -> Prog:
     c = [f"c{i}" for i in range(8)]
     d = [f"d{i}" for i in range(8)]
     r = [f"r{i}" for i in range(8)]
-    pr = Prog(f"{field}_mul2sub", a + b + c + d, r)
+    pr = Prog(f"{field}_mul2sub{'nr' if nr else ''}", a + b + c + d, r)
     nm = Namer(pr, "t")
     T1 = emit_mulw(pr, nm, a, b, 8)
     T2 = emit_mulw(pr, nm, c, d, 8)
@@ -435,7 +443,7 @@ def gen_mul2sub(field: str) -> Prog:
     for i in range(1, 7):
         pr.op("addc.cc.u32", E[i], D[8 + i], q[i])
     pr.op("addc.u32", E[7], D[15], q[7])  # the carry out cancels the borrow
-    emit_redc(pr, nm, D[0:8] + E, mod, r, "c")
+    emit_redc(pr, nm, D[0:8] + E, mod, r, "c", nr)
     return pr
 
 
@@ -477,6 +485,30 @@ def gen_sub(field: str) -> Prog:
     return pr
 
 
+def gen_sub2p(field: str) -> Prog:
+    """r = a - b (+ 2p if negative) for a, b in [0, 2p): result in [0, 2p), congruent to a - b."""
+    mod = FIELDS[field]
+    pl = limbs(2 * mod)
+    a = [f"a{i}" for i in range(8)]
+    b = [f"b{i}" for i in range(8)]
+    r = [f"r{i}" for i in range(8)]
+    pr = Prog(f"{field}_sub2p", a + b, r)
+    d = [pr.tmp(f"d{i}") for i in range(8)]
+    brw = pr.tmp("brw")
+    pr.op("sub.cc.u32", d[0], a[0], b[0])
+    for i in range(1, 8):
+        pr.op("subc.cc.u32", d[i], a[i], b[i])
+    pr.op("subc.u32", brw, 0, 0)
+    q = [pr.tmp(f"q{i}") for i in range(8)]
+    for i in range(8):
+        pr.op("and.b32", q[i], brw, pl[i])
+    pr.op("add.cc.u32", r[0], d[0], q[0])
+    for i in range(1, 7):
+        pr.op("addc.cc.u32", r[i], d[i], q[i])
+    pr.op("addc.u32", r[7], d[7], q[7])
+    return pr
+
+
 def gen_reduce_once(field: str) -> Prog:
     """r = a - p if a >= p else a  (for a < 2p)."""
     mod = FIELDS[field]
@@ -494,6 +526,9 @@ ROUTINES = {
     "mul": gen_mul,
     "mulk": gen_mulk,
     "mul2sub": gen_mul2sub,
+    "mulnr": lambda f: gen_mul(f, nr=True),
+    "mul2subnr": lambda f: gen_mul2sub(f, nr=True),
+    "sub2p": gen_sub2p,
     "add": gen_add,
     "sub": gen_sub,
     "reduce_once": gen_reduce_once,
@@ -545,10 +580,15 @@ def emit_header() -> str:
             outs = [f"r[{i}]" for i in range(8)]
             ins = [f"a[{i}]" for i in range(8)] + ([f"b[{i}]" for i in range(8)] if two else [])
             out.append(pr.emit(sig, outs, ins))
-    pr = ROUTINES["mul2sub"]("fq")
-    out.append(pr.emit("fq_mul2sub_ptx(uint32_t* r, const uint32_t* a, const uint32_t* b, const uint32_t* c, const uint32_t* d)",
-                       [f"r[{i}]" for i in range(8)],
-                       [f"{v}[{i}]" for v in "abcd" for i in range(8)]))
+    for what in ("mul2sub", "mul2subnr"):
+        pr = ROUTINES[what]("fq")
+        out.append(pr.emit(f"fq_{what}_ptx(uint32_t* r, const uint32_t* a, const uint32_t* b, const uint32_t* c, const uint32_t* d)",
+                           [f"r[{i}]" for i in range(8)],
+                           [f"{v}[{i}]" for v in "abcd" for i in range(8)]))
+    for what in ("mulnr", "sub2p"):  # the [0, 2p) forms used inside the bucket accumulation
+        pr = ROUTINES[what]("fq")
+        out.append(pr.emit(f"fq_{what}_ptx(uint32_t* r, const uint32_t* a, const uint32_t* b)",
+                           [f"r[{i}]" for i in range(8)], [f"a[{i}]" for i in range(8)] + [f"b[{i}]" for i in range(8)]))
     out.append("#endif  // __CUDACC__")
     return "\n".join(out) + "\n"
 
@@ -569,6 +609,19 @@ def selftest(iters: int = 300) -> None:
         quad += [tuple(rnd.randrange(mod) for _ in range(4)) for _ in range(iters)]
         for w, x, y, z in quad:
             assert emulate(field, "mul2sub", w, x, y, z) == (w * x - y * z) * rinv % mod, (field, "mul2sub", w, x, y, z)
+        # the [0, 2p) forms: congruent results that stay below 2p for ANY operands below 2p
+        edge2 = [0, 1, mod - 1, mod, mod + 1, 2 * mod - 1, 2 * mod - 2, (1 << 254), (1 << 254) + 12345]
+        pairs2 = [(x, y) for x in edge2 for y in edge2] + [(rnd.randrange(2 * mod), rnd.randrange(2 * mod)) for _ in range(iters)]
+        for x, y in pairs2:
+            v = emulate(field, "mulnr", x, y)
+            assert v < 2 * mod and v % mod == x * y * rinv % mod, (field, "mulnr", x, y)
+            v = emulate(field, "sub2p", x, y)
+            assert v < 2 * mod and v % mod == (x - y) % mod, (field, "sub2p", x, y)
+        quad2 = [(w, x, y, z) for w in edge2[2:7] for x in edge2[2:7] for y in (0, mod, 2 * mod - 1) for z in (0, 2 * mod - 1, mod + 1)]
+        quad2 += [tuple(rnd.randrange(2 * mod) for _ in range(4)) for _ in range(iters)]
+        for w, x, y, z in quad2:
+            v = emulate(field, "mul2subnr", w, x, y, z)
+            assert v < 2 * mod and v % mod == (w * x - y * z) * rinv % mod, (field, "mul2subnr", w, x, y, z)
         # multiplicand a < p, word operand b ANY 256-bit value (used for bytes -> Fr)
         for _ in range(iters):
             x, y = rnd.randrange(mod), rnd.randrange(1 << 256)

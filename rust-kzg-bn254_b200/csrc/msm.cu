@@ -216,7 +216,7 @@ __device__ __forceinline__ void xyzz_madd_call(XYZZ& acc, const Affine& q) {
 // Source of the entries: SRC_REFS = sorted refs into the table (gather), SRC_POINTS = the affine
 // points left by the batch-affine levels (entry `pos` is points[pos]; bucket offsets are the level-0
 // offsets >> shift).
-template <bool CALL, bool PREFETCH, bool DIRECT, bool LAZY = false>
+template <bool CALL, bool PREFETCH, bool DIRECT, bool LAZY = false, bool RELAXED = false>
 __device__ __forceinline__ void accumulate_body(const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ offsets,
                                                 const Affine* __restrict__ table, uint32_t nb, uint32_t acc_threads,
                                                 uint32_t chunk, int shift,
@@ -249,17 +249,19 @@ __device__ __forceinline__ void accumulate_body(const uint32_t* __restrict__ sor
         else q = fetch(pos);
         if (pos >= next) {
             bool complete = (run_begin >= start);  // its end (`next`) is <= pos < end
+            if (RELAXED) xyzz_relaxed_normalise(acc);
             if (complete) xyzz_store(&buckets[b], acc);
             else xyzz_store(&partial[2 * t], acc);
             xyzz_set_inf(acc);
             do { b++; } while ((offsets[b + 1] >> shift) <= pos);
             run_begin = offsets[b] >> shift; next = offsets[b + 1] >> shift;
         }
-        if (LAZY) xyzz_madd(acc, q); else if (CALL) xyzz_madd_call(acc, q); else xyzz_madd_classic(acc, q);
+        if (RELAXED) xyzz_madd_relaxed(acc, q); else if (LAZY) xyzz_madd(acc, q); else if (CALL) xyzz_madd_call(acc, q); else xyzz_madd_classic(acc, q);
         if (PREFETCH) { if (pos + 1 < end) q = qn; }
     }
     {
         bool complete = (run_begin >= start) && (next <= end);
+        if (RELAXED) xyzz_relaxed_normalise(acc);
         if (complete) xyzz_store(&buckets[b], acc);
         else if (run_begin <= start) xyzz_store(&partial[2 * t], acc);
         else xyzz_store(&partial[2 * t + 1], acc);
@@ -280,6 +282,15 @@ __global__ void __launch_bounds__(128, MINB) k_accumulate_lazy(const uint32_t* _
                                                                  uint32_t chunk, int shift,
                                                                  XYZZ* __restrict__ buckets, XYZZ* __restrict__ partial) {
     accumulate_body<false, false, false, true>(sorted, offsets, table, nb, acc_threads, chunk, shift, buckets, partial);
+}
+// ... and with the accumulator kept in [0, 2p) (no conditional subtraction after any product; normalised when
+// it leaves the loop)
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_accumulate_relaxed(const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ offsets,
+                                                                    const Affine* __restrict__ table, uint32_t nb, uint32_t acc_threads,
+                                                                    uint32_t chunk, int shift,
+                                                                    XYZZ* __restrict__ buckets, XYZZ* __restrict__ partial) {
+    accumulate_body<false, false, false, true, true>(sorted, offsets, table, nb, acc_threads, chunk, shift, buckets, partial);
 }
 // Same body under a hard register cap instead of a blocks-per-SM hint: at 112 registers four blocks leave
 // 8 K registers of every SM free, so the small blocks of the other lanes' sort kernels can be resident
@@ -874,12 +885,14 @@ void msm_launch(const MsmPlan& p, const MsmWorkspace& ws, const Fr* scalars, boo
                 case 3: KZ_ACC(4, true, true, false); break;
                 case 9: KZ_ACC(5, false, true, false); break;
                 case 15: k_accumulate_lazy<4><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, L, ws.buckets, ws.partial); break;
+                case 17: k_accumulate_relaxed<3><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, L, ws.buckets, ws.partial); break;
                 case 11: k_accumulate_r<112><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, L, ws.buckets, ws.partial); break;
                 case 12: k_accumulate_r<96><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, L, ws.buckets, ws.partial); break;
                 case 13: k_accumulate_r<104><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, L, ws.buckets, ws.partial); break;
                 case 14: k_accumulate_r<80><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, L, ws.buckets, ws.partial); break;
                 case 20: KZ_ACC(4, false, false, false); break;  // every product reduced on its own (the default until the lazy Y3)
-                default: k_accumulate_lazy<3><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, L, ws.buckets, ws.partial); break;
+                case 16: k_accumulate_lazy<3><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, L, ws.buckets, ws.partial); break;
+                default: k_accumulate_relaxed<4><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, L, ws.buckets, ws.partial); break;
             }
         }
 #undef KZ_ACC
