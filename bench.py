@@ -317,12 +317,13 @@ def main():
         "single_2p19_butterfly_fr_mul_per_s": (1 << LOG_N) * LOG_N / 2.0 / (ntt1_ms.value * 1e-3),
     }
     roofline = {
-        "kernel": "k_accumulate_t (MSM bucket accumulation, XYZZ += affine)", "bound": "integer-pipe (IMAD)",
+        "kernel": "k_accumulate_relaxed (MSM bucket accumulation, XYZZ += affine)", "bound": "integer-pipe (IMAD)",
         "achieved": achieved_iso, "peak": peak, "unit": "GFqmul/s", "frac": achieved_iso / peak if peak else None,
         "traffic": traffic,
         "achieved_in_pipeline": achieved, "frac_in_pipeline": achieved / peak if peak else None,
         "launch_ms_isolated": iso_acc.value, "launch_ms_in_pipeline": avg_acc_ms, "msm_total_ms_isolated": iso_total.value,
         "algorithmic_fqmul_per_launch": FQMUL_PER_MADD * adds_per_launch, "point_adds_per_launch": adds_per_launch,
+        "executed_note": "algorithmic count (SURVEY 8d): 10 Fq-mul per XYZZ += affine; the kernel executes 10 products and 9 Montgomery reductions (Y3 is one reduction of a difference of two products)",
         "peak_source": "measured live: dependency-free IMAD chains / 136 IMAD per 8x32-bit Montgomery multiplication (SURVEY.md 8d model)",
         "peak_wide_multiply": imadw.value / 132.0 / 1e9, "frac_of_wide_multiply_peak": achieved_iso / (imadw.value / 132.0 / 1e9) if imadw.value else None,
         "peak_wide_multiply_source": "measured live: IMAD.WIDE.U32 issues at half the IMAD rate on sm_100; a multiplication is 128 wide + 8 narrow multiplies",
@@ -360,10 +361,12 @@ def main():
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u32 (8x32-bit Montgomery limbs, BN254 Fq/Fr)", "data": "synthetic",
         "config": {"workload": "single 16 MiB blob (2^19 Fr): eval-form IFFT + 2^19-point G1 MSM commitment and blob proof",
+                   "path": "commit_blob + compute_blob_proof; the eval-form IFFT is the G1 IFFT of the SRS (kzg.rs:98) computed once and kept "
+                           "resident as a Lagrange-basis window table, so each commitment / proof is one 2^19-point MSM on the evaluations",
                    "blobs_per_step_per_gpu": B, "log_n": LOG_N, "srs": "tau^i*G, 2^19 points, generated on GPU",
                    "blob_distribution": "D1 payload (byte 0 of each element = 0)", "sharding": "by blob, no collective",
                    "msm_window_bits": cbits.value, "msm_windows": cwin.value,
-                   "l2": f"inputs larger than L2: {B * n * 32 >> 20} MiB of blobs + {cwin.value * n * 64 >> 20} MiB window table per step"},
+                   "l2": f"inputs larger than L2: {B * n * 32 >> 20} MiB of blobs + {cwin.value * n * 64 >> 20} MiB Lagrange window table per step"},
         "e2e": {"value": e2e_value, "unit": "blobs/s", "h2d_bytes_per_step": B * n * 32, "d2h_bytes_per_step": B * 2 * 128,
                 "ms_per_step": e2e_ms / args.steps, "wall_ms_per_step": e2e_wall / args.steps},
         "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "roofline_ntt": roofline_ntt,
