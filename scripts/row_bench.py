@@ -105,7 +105,7 @@ def main():
     eng.check(lib.kzgb_commit_eval(eng.h, evals_b, n, out, C.byref(inf)))
     g = best(lambda: eng.check(lib.kzgb_commit_eval(eng.h, evals_b, n, out, C.byref(inf))), args.reps)
     c = once(lambda: olib.ref_msm(srs_xy, cbuf.raw, C.c_size_t(n), th, cout)) + c
-    emit("a1", "KZG::commit_eval_form (Fr-IFFT + MSM form)", g, c, out.raw == cout.raw,
+    emit("a1", "KZG::commit_eval_form (one MSM over the resident Lagrange table; CPU: Fr-IFFT + MSM)", g, c, out.raw == cout.raw,
          "CPU = oracle NTT + MSM; the reference's literal G1-IFFT form is ~200x more (bench.py cpu_baseline)")
 
     # a11 to_fr_array / a4 commit_blob / a8 challenge / a5 blob proof
