@@ -130,7 +130,7 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 (4x64-bit Montgomery, BN254 Fq/Fr)",
         "data": "synthetic",
-        "config": {"workload": "single 16 MiB blob (2^19 Fr): commit_blob + compute_blob_proof", "blobs_per_step": 1,
+        "config": {"workload": "single 16 MiB blob (2^19 Fr): eval-form IFFT + 2^19-point G1 MSM commitment and blob proof", "blobs_per_step": 1,
                    "log_n": LOG_N, "algorithm": "Fr-IFFT + MSM (the cheaper form; the reference's literal G1-IFFT-per-commit path is ~180x slower, see BASELINE.md)"},
         "cpu_baseline": {"value": value, "unit": "blobs/s", "cores": threads, "kind": "port",
                          "sample": "1 blob (2^19 Fr) commit+proof per step; C++ restatement of the arkworks algorithm (oracle/cpu_ref.cpp), "
