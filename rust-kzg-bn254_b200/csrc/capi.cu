@@ -1102,7 +1102,8 @@ int kzgb_commit_blob(kzgb_ctx* c, const uint8_t* blob, size_t len, uint64_t out_
 }
 
 // KZG::g1_ifft (kzg.rs:263-285): the Lagrange-basis SRS, a G1-point inverse NTT on the GPU (g1ntt.cu).
-// Only a public API here -- commitments use the Fr-IFFT + monomial MSM identity instead.
+// The same transform builds the resident Lagrange window tables (ensure_lagrange); this entry point returns
+// the points themselves to the caller.
 int kzgb_g1_ifft(kzgb_ctx* c, size_t n, uint64_t* out_xy, uint8_t* out_inf) {
     if (n == 0 || (n & (n - 1))) return fail(c, KZGB_ERR_FFT, "length provided is not a power of 2");
     Guard g(c);

@@ -13,6 +13,8 @@
 //   6. k_reduce_slices per-slice running sums  sum (k+1) * B_k  + small scalar fix-up
 //   7. k_tree_reduce   tree sum of the slice results -> one XYZZ point per bucket set
 // The caller copies `sets` XYZZ points (128 B each) back and finishes on the host.
+// One launch set can also carry `batch` independent fixed-base MSMs over the same table (MsmPlan.batch_n):
+// scalar i belongs to MSM i / batch_n, which owns bucket set i / batch_n -- how runs of small blobs are committed.
 #include <cstdlib>
 #include "kzgb_internal.hpp"
 
