@@ -12,6 +12,11 @@ Parity status: pinned against the reference's own fixtures (copied under
 fixture ("parity unpinned"): the arkworks ``serialize_compressed`` byte layout
 that feeds the Fiat-Shamir transcripts (restated from the published arkworks 0.5
 format), hence the challenge ``z`` of ``compute_blob_proof`` and the RLC scalar
-``r``.  The reference itself (Rust + un-vendored arkworks 0.5) cannot be built
+``r``.  The verifier's pairing (``verify_proof`` / ``verify_blob_kzg_proof`` / the
+final check of the batch verifier) is restated here too -- only so the tests can run
+BASELINE config 1 end to end and check GPU-made proofs against the pairing equation
+with an injected [tau]G2; it is anchored on the reference's ``G2_TAU`` constant lying
+on the twist with order r and on bilinearity, and the product never computes a pairing.
+The reference itself (Rust + un-vendored arkworks 0.5) cannot be built
 in this image, so there is no ``oracle/_ref``.
 """

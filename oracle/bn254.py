@@ -870,3 +870,256 @@ def tau_trick_msm(scalars: Sequence[int], tau: int = SYNTH_TAU) -> Affine:
     for s in reversed(scalars):
         acc = (acc * tau + s) % R
     return g1_mul(G1_GEN, acc)
+
+
+# ----------------------------------------------------------------------------
+# Pairing (TEST ORACLE ONLY; the product leaves the pairing in the reference's code).
+# ark-bn254's optimal ate pairing restated on the polynomial tower
+#   Fq2 = Fq[i]/(i^2 + 1),  Fq12 = Fq[w]/(w^12 - 18 w^6 + 82)   (w^6 = 9 + i),
+# G2 on the sextic twist y^2 = x^3 + 3/(9 + i), mapped into Fq12 by (x, y) -> (x w^2, y w^3).
+# Used by verify_proof / verify_blob_kzg_proof / verify_blob_kzg_proof_batch
+# (verifier/src/verify.rs:10-115, verifier/src/batch.rs:16-69, helpers.rs:392-398) with an
+# INJECTABLE [tau]G2 so config 1 verifies against the synthetic SRS; the default is the
+# reference's mainnet constant G2_TAU (primitives/src/consts.rs:55-64).
+# Anchors: G2_TAU and the generator lie on the twist and have order r; bilinearity in both
+# arguments (tests/test_oracle.py).
+# ----------------------------------------------------------------------------
+Fq2 = Tuple[int, int]
+G2Affine = Optional[Tuple[Fq2, Fq2]]
+
+G2_GEN: G2Affine = (
+    (10857046999023057135944570762232829481370756359578518086990519993285655852781,
+     11559732032986387107991004021392285783925812861821192530917403151452391805634),
+    (8495653923123431417604973247489272438418190587263600148770280649306958101930,
+     4082367875863433681332203403145435568316851327593401208105741076214120093531),
+)
+G2_TAU: G2Affine = (  # consts.rs:55-64
+    (19394299006376106554626551996044114846855237028623244664226757033024550999552,
+     10478571113809844268398751534081669357808742555529167819607714577862447855483),
+    (9205262336805673656533560220225620941045451042642528799409071118332922267006,
+     10552783866161062341197740743287753408530108186218052255509661543860392060676),
+)
+ATE_LOOP_COUNT = 29793968203157093288  # 6x + 2, x = 4965661367192848881
+
+
+def fq2_add(a: Fq2, b: Fq2) -> Fq2:
+    return ((a[0] + b[0]) % P, (a[1] + b[1]) % P)
+
+
+def fq2_sub(a: Fq2, b: Fq2) -> Fq2:
+    return ((a[0] - b[0]) % P, (a[1] - b[1]) % P)
+
+
+def fq2_mul(a: Fq2, b: Fq2) -> Fq2:
+    return ((a[0] * b[0] - a[1] * b[1]) % P, (a[0] * b[1] + a[1] * b[0]) % P)
+
+
+def fq2_inv(a: Fq2) -> Fq2:
+    d = fq_inv((a[0] * a[0] + a[1] * a[1]) % P)
+    return (a[0] * d % P, -a[1] * d % P)
+
+
+_TWIST_B: Fq2 = fq2_mul((3, 0), fq2_inv((9, 1)))  # 3 / (9 + i)
+
+
+def g2_is_on_curve(q: G2Affine) -> bool:
+    if q is None:
+        return True
+    x, y = q
+    return fq2_mul(y, y) == fq2_add(fq2_mul(fq2_mul(x, x), x), _TWIST_B)
+
+
+def g2_neg(q: G2Affine) -> G2Affine:
+    return None if q is None else (q[0], (-q[1][0] % P, -q[1][1] % P))
+
+
+def g2_add(a: G2Affine, b: G2Affine) -> G2Affine:
+    if a is None:
+        return b
+    if b is None:
+        return a
+    (x1, y1), (x2, y2) = a, b
+    if x1 == x2:
+        if y1 != y2 or y1 == (0, 0):
+            return None
+        x1x1 = fq2_mul(x1, x1)
+        lam = fq2_mul(fq2_add(fq2_add(x1x1, x1x1), x1x1), fq2_inv(fq2_add(y1, y1)))
+    else:
+        lam = fq2_mul(fq2_sub(y2, y1), fq2_inv(fq2_sub(x2, x1)))
+    x3 = fq2_sub(fq2_sub(fq2_mul(lam, lam), x1), x2)
+    return (x3, fq2_sub(fq2_mul(lam, fq2_sub(x1, x3)), y1))
+
+
+def g2_mul(q: G2Affine, k: int) -> G2Affine:
+    k %= R
+    acc: G2Affine = None
+    for bit in bin(k)[2:] if k else "":
+        acc = g2_add(acc, acc)
+        if bit == "1":
+            acc = g2_add(acc, q)
+    return acc
+
+
+# ---- Fq12 as coefficient lists of length 12 over Fq, modulus w^12 - 18 w^6 + 82
+def _f12_mul(a: List[int], b: List[int]) -> List[int]:
+    t = [0] * 23
+    for i, ai in enumerate(a):
+        if ai:
+            for j, bj in enumerate(b):
+                t[i + j] += ai * bj
+    for k in range(22, 11, -1):  # w^k = 18 w^(k-6) - 82 w^(k-12)
+        c = t[k]
+        if c:
+            t[k - 6] += 18 * c
+            t[k - 12] -= 82 * c
+    return [x % P for x in t[:12]]
+
+
+_F12_ONE = [1] + [0] * 11
+
+
+def _f12_pow(a: List[int], e: int) -> List[int]:
+    out = _F12_ONE
+    for bit in bin(e)[2:]:
+        out = _f12_mul(out, out)
+        if bit == "1":
+            out = _f12_mul(out, a)
+    return out
+
+
+def _poly_deg(p: List[int]) -> int:
+    d = len(p) - 1
+    while d and p[d] == 0:
+        d -= 1
+    return d
+
+
+def _f12_inv(a: List[int]) -> List[int]:
+    """Extended Euclid in Fq[w] against the modulus polynomial."""
+    lm, hm = [1] + [0] * 12, [0] * 13
+    low, high = list(a) + [0], [82, 0, 0, 0, 0, 0, -18 % P, 0, 0, 0, 0, 0, 1]
+    while _poly_deg(low):
+        # r = high // low (polynomial quotient)
+        dl, dh = _poly_deg(low), _poly_deg(high)
+        temp = list(high)
+        q = [0] * 13
+        inv_lead = fq_inv(low[dl])
+        for i in range(dh - dl, -1, -1):
+            q[i] = temp[dl + i] * inv_lead % P
+            for c in range(dl + 1):
+                temp[c + i] = (temp[c + i] - q[i] * low[c]) % P
+        nm, new = list(hm), list(high)
+        for i in range(13):
+            for j in range(13 - i):
+                nm[i + j] = (nm[i + j] - lm[i] * q[j]) % P
+                new[i + j] = (new[i + j] - low[i] * q[j]) % P
+        lm, low, hm, high = nm, new, lm, low
+    inv0 = fq_inv(low[0])
+    return [x * inv0 % P for x in lm[:12]]
+
+
+def _twist(q: Tuple[Fq2, Fq2]) -> Tuple[List[int], List[int]]:
+    """G2 (on the twist, over Fq2) -> E(Fq12): a + b i  ->  (a - 9 b) + b w^6, then (x w^2, y w^3)."""
+    (x0, x1), (y0, y1) = q
+    nx = [0] * 12
+    ny = [0] * 12
+    nx[2], nx[8] = (x0 - 9 * x1) % P, x1
+    ny[3], ny[9] = (y0 - 9 * y1) % P, y1
+    return nx, ny
+
+
+def _f12_sub(a, b):
+    return [(x - y) % P for x, y in zip(a, b)]
+
+
+def _f12_add(a, b):
+    return [(x + y) % P for x, y in zip(a, b)]
+
+
+def _line(p1, p2, t):
+    """Line through p1, p2 (points of E(Fq12)) evaluated at t."""
+    (x1, y1), (x2, y2), (xt, yt) = p1, p2, t
+    if x1 != x2:
+        m = _f12_mul(_f12_sub(y2, y1), _f12_inv(_f12_sub(x2, x1)))
+    elif y1 == y2:
+        x1x1 = _f12_mul(x1, x1)
+        m = _f12_mul([3 * c % P for c in x1x1], _f12_inv([2 * c % P for c in y1]))
+    else:
+        return _f12_sub(xt, x1)
+    return _f12_sub(_f12_mul(m, _f12_sub(xt, x1)), _f12_sub(yt, y1))
+
+
+def _e12_add(p1, p2):
+    (x1, y1), (x2, y2) = p1, p2
+    if x1 == x2 and y1 == y2:
+        x1x1 = _f12_mul(x1, x1)
+        m = _f12_mul([3 * c % P for c in x1x1], _f12_inv([2 * c % P for c in y1]))
+    else:
+        m = _f12_mul(_f12_sub(y2, y1), _f12_inv(_f12_sub(x2, x1)))
+    x3 = _f12_sub(_f12_sub(_f12_mul(m, m), x1), x2)
+    return x3, _f12_sub(_f12_mul(m, _f12_sub(x1, x3)), y1)
+
+
+def miller_loop(q: G2Affine, p: Affine) -> List[int]:
+    """Optimal ate Miller loop f_{6x+2,Q}(P) with the two Frobenius lines; no final exponentiation."""
+    if q is None or p is None:
+        return _F12_ONE
+    Q = _twist(q)
+    Pt = ([p[0]] + [0] * 11, [p[1]] + [0] * 11)
+    Rp = Q
+    f = _F12_ONE
+    for i in range(ATE_LOOP_COUNT.bit_length() - 2, -1, -1):
+        f = _f12_mul(_f12_mul(f, f), _line(Rp, Rp, Pt))
+        Rp = _e12_add(Rp, Rp)
+        if (ATE_LOOP_COUNT >> i) & 1:
+            f = _f12_mul(f, _line(Rp, Q, Pt))
+            Rp = _e12_add(Rp, Q)
+    Q1 = (_f12_pow(Q[0], P), _f12_pow(Q[1], P))
+    nQ2 = (_f12_pow(Q1[0], P), [-c % P for c in _f12_pow(Q1[1], P)])
+    f = _f12_mul(f, _line(Rp, Q1, Pt))
+    Rp = _e12_add(Rp, Q1)
+    f = _f12_mul(f, _line(Rp, nQ2, Pt))
+    return f
+
+
+def final_exponentiation(f: List[int]) -> List[int]:
+    return _f12_pow(f, (P**12 - 1) // R)
+
+
+def pairing(q: G2Affine, p: Affine) -> List[int]:
+    return final_exponentiation(miller_loop(q, p))
+
+
+def pairings_verify(a1: Affine, a2: G2Affine, b1: Affine, b2: G2Affine) -> bool:
+    """helpers.rs:392-398: e(a1, a2) == e(b1, b2), as one product e(a1, a2) * e(-b1, b2) == 1."""
+    f = _f12_mul(miller_loop(a2, a1), miller_loop(b2, g1_neg(b1)))
+    return final_exponentiation(f) == _F12_ONE
+
+
+def verify_proof(commitment: Affine, proof: Affine, value_fr: int, z_fr: int, g2_tau: G2Affine = G2_TAU) -> bool:
+    """verifier/src/verify.rs:10-73: e(C - y G1, G2) == e(proof, [tau - z] G2)."""
+    validate_g1_point(commitment)
+    validate_g1_point(proof)
+    if not g2_is_on_curve(g2_tau):
+        raise KzgError("NotOnCurveError", "Invalid trusted setup: G2_TAU not on curve")
+    commit_minus_value = g1_add(commitment, g1_neg(g1_mul(G1_GEN, value_fr % R)))
+    x_minus_z = g2_add(g2_tau, g2_neg(g2_mul(G2_GEN, z_fr % R)))
+    if x_minus_z is None:
+        raise KzgError("GenericError", "Evaluation point equals trusted setup secret")
+    return pairings_verify(commit_minus_value, G2_GEN, proof, x_minus_z)
+
+
+def verify_blob_kzg_proof(blob: Blob, commitment: Affine, proof: Affine, g2_tau: G2Affine = G2_TAU) -> bool:
+    """verifier/src/verify.rs:77-115: challenge, evaluation, then verify_proof."""
+    validate_g1_point(commitment)
+    validate_g1_point(proof)
+    poly = blob.to_polynomial_eval_form()
+    z = compute_challenge(blob, commitment)
+    y = evaluate_polynomial_in_evaluation_form(poly, z)
+    return verify_proof(commitment, proof, y, z, g2_tau)
+
+
+def verify_blob_kzg_proof_batch(blobs: Sequence[Blob], commitments, proofs, g2_tau: G2Affine = G2_TAU) -> bool:
+    """verifier/src/batch.rs:16-69,170-255: the RLC front half, then e(lhs, [tau]G2) == e(rhs, G2)."""
+    lhs, rhs = verify_blob_kzg_proof_batch_rlc(blobs, commitments, proofs)
+    return pairings_verify(lhs, g2_tau, rhs, G2_GEN)

@@ -69,6 +69,37 @@ def test_commit_and_proof_closed_form_at_bench_sizes(pkg, logn):
     assert kzg.compute_blob_proof(blob, c, srs) == pi
 
 
+def test_config1_gpu_prover_verified_by_the_pairing(pkg):
+    """BASELINE configs[0]: one 128 KiB blob (4096 Fr, the reference's blobs.txt) on a synthetic 2^12-point SRS.
+    commit_blob + compute_blob_proof run on the GPU; verify_blob_kzg_proof (verifier/src/verify.rs:77-115: challenge,
+    evaluation, e(C - y G1, G2) == e(proof, [tau - z] G2)) runs on the CPU oracle with [tau]G2 injected.  A proof for
+    another blob fails, and the GPU's batch RLC outputs satisfy the final pairing of batch.rs:253-254."""
+    n = 1 << 12
+    eng = pkg.Engine(0)
+    srs = pkg.SRS.synthetic(n, TAU, engine=eng)
+    g2_tau = o.g2_mul(o.G2_GEN, TAU)
+    data = g.blobs_txt()
+    blob = pkg.Blob.new(data)
+    kzg = pkg.KZG()
+    kzg.calculate_and_store_roots_of_unity(len(blob))
+    c = kzg.commit_blob(blob, srs)
+    pi = kzg.compute_blob_proof(blob, c, srs)
+    bo = o.Blob(data)
+    assert o.verify_blob_kzg_proof(bo, c, pi, g2_tau)
+    rnd = random.Random(41)
+    other = b"".join(rnd.randrange(o.R).to_bytes(32, "big") for _ in range(n))
+    blob2 = pkg.Blob.new(other)
+    c2 = kzg.commit_blob(blob2, srs)
+    pi2 = kzg.compute_blob_proof(blob2, c2, srs)
+    assert o.verify_blob_kzg_proof(o.Blob(other), c2, pi2, g2_tau)
+    assert not o.verify_blob_kzg_proof(bo, c, pi2, g2_tau)
+    assert not o.verify_blob_kzg_proof(bo, c2, pi, g2_tau)
+    lhs, rhs = pkg.verify_blob_kzg_proof_batch_rlc([blob, blob2], [c, c2], [pi, pi2], eng)
+    assert o.pairings_verify(lhs, g2_tau, rhs, o.G2_GEN)
+    lhs_bad, rhs_bad = pkg.verify_blob_kzg_proof_batch_rlc([blob, blob2], [c, c2], [pi2, pi], eng)
+    assert not o.pairings_verify(lhs_bad, g2_tau, rhs_bad, o.G2_GEN)
+
+
 def test_point_range_sharded_msm_closed_form(pkg):
     """config 4 at 2^20 on one GPU in variable-base mode, as 1 range and as 3 ranges added on the host:
     scalars a^i => MSM = ((a tau)^N - 1)/(a tau - 1) G."""

@@ -134,3 +134,58 @@ def test_rlc_transcript_layout():
     r = int.from_bytes(hashlib.sha256(buf).digest(), "big") % o.R
     assert o.compute_r_powers([c, c], zs * 2, ys * 2, [pi, pi], [1, 1])[0] == 1
     assert r != 0
+
+
+def test_pairing_constants_and_bilinearity():
+    """The oracle's pairing (test infrastructure for config 1): the reference's G2_TAU (consts.rs:55-64) and
+    the generator lie on the twist with order r; e is bilinear in both arguments and has order r."""
+    for q in (o.G2_GEN, o.G2_TAU):
+        assert o.g2_is_on_curve(q)
+        assert o.g2_mul(q, o.R - 1) == o.g2_neg(q)
+    assert not o.g2_is_on_curve(((1, 2), (3, 4)))
+    e = o.pairing(o.G2_GEN, o.G1_GEN)
+    assert e != o._F12_ONE and o._f12_pow(e, o.R) == o._F12_ONE
+    a, b = 0x1234567890ABCDEF1234567, 0xFEDCBA09876543210FEDCBA0987
+    assert o.pairing(o.G2_GEN, o.g1_mul(o.G1_GEN, a)) == o._f12_pow(e, a)
+    assert o.pairing(o.g2_mul(o.G2_GEN, b), o.G1_GEN) == o._f12_pow(e, b)
+    assert o.pairing(o.g2_mul(o.G2_GEN, b), o.g1_mul(o.G1_GEN, a)) == o._f12_pow(e, a * b % o.R)
+    assert o.pairing(None, o.G1_GEN) == o._F12_ONE and o.pairing(o.G2_GEN, None) == o._F12_ONE
+    x = o._f12_pow(e, 12345)
+    assert o._f12_mul(x, o._f12_inv(x)) == o._F12_ONE
+
+
+def test_config1_prove_verify_on_the_oracle():
+    """BASELINE configs[0] restated on the CPU oracle with the synthetic SRS: commit_blob + compute_blob_proof +
+    verify_blob_kzg_proof (verifier/src/verify.rs:10-115) with [tau]G2 injected; tampering fails
+    (verifier/tests/tests.rs:28-192); batch verification (batch.rs:16-69) true / false."""
+    srs = o.synthetic_srs(64)
+    g2_tau = o.g2_mul(o.G2_GEN, o.SYNTH_TAU)
+    blobs = [o.Blob.from_raw_data(g.gettysburg()), o.Blob.from_raw_data(b"second blob " * 20), o.Blob.from_raw_data(bytes(31 * 5))]
+    cs, ps = [], []
+    for blob in blobs:
+        k = o.KZG()
+        k.calculate_and_store_roots_of_unity(len(blob))
+        c = k.commit_blob(blob, srs)
+        cs.append(c)
+        ps.append(k.compute_blob_proof(blob, c, srs))
+    assert o.verify_blob_kzg_proof(blobs[0], cs[0], ps[0], g2_tau)
+    assert not o.verify_blob_kzg_proof(blobs[0], cs[0], ps[0])  # the mainnet G2_TAU is a different tau
+    assert not o.verify_blob_kzg_proof(blobs[0], cs[0], ps[1], g2_tau)
+    assert not o.verify_blob_kzg_proof(blobs[1], cs[0], ps[0], g2_tau)
+    assert o.verify_blob_kzg_proof(blobs[2], cs[2], ps[2], g2_tau)  # zero blob: identity commitment and proof
+    assert cs[2] is None and ps[2] is None
+    with pytest.raises(o.KzgError) as e:
+        o.verify_blob_kzg_proof(blobs[0], (1, 3), ps[0], g2_tau)
+    assert e.value.variant == "NotOnCurveError"
+    z = 987654321
+    y = o.evaluate_polynomial_in_evaluation_form(blobs[0].to_polynomial_eval_form(), z)
+    k = o.KZG()
+    k.calculate_and_store_roots_of_unity(len(blobs[0]))
+    pi = k.compute_proof(blobs[0].to_polynomial_eval_form(), z, srs)
+    assert o.verify_proof(cs[0], pi, y, z, g2_tau)
+    assert not o.verify_proof(cs[0], pi, (y + 1) % o.R, z, g2_tau)
+    with pytest.raises(o.KzgError) as e:
+        o.verify_proof(cs[0], pi, y, o.SYNTH_TAU, g2_tau)  # z == tau (verify.rs:55-59)
+    assert e.value.msg == "Evaluation point equals trusted setup secret"
+    assert o.verify_blob_kzg_proof_batch(blobs, cs, ps, g2_tau)
+    assert not o.verify_blob_kzg_proof_batch(blobs, cs, [ps[1], ps[0], ps[2]], g2_tau)
