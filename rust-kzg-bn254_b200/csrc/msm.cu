@@ -218,7 +218,7 @@ __device__ __forceinline__ void xyzz_madd_call(XYZZ& acc, const Affine& q) {
 // Source of the entries: SRC_REFS = sorted refs into the table (gather), SRC_POINTS = the affine
 // points left by the batch-affine levels (entry `pos` is points[pos]; bucket offsets are the level-0
 // offsets >> shift).
-template <bool CALL, bool PREFETCH, bool DIRECT, bool LAZY = false, bool RELAXED = false>
+template <bool CALL, bool PREFETCH, bool DIRECT, bool LAZY = false, bool RELAXED = false, bool L2PF = false>
 __device__ __forceinline__ void accumulate_body(const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ offsets,
                                                 const Affine* __restrict__ table, uint32_t nb, uint32_t acc_threads,
                                                 uint32_t chunk, int shift,
@@ -249,6 +249,10 @@ __device__ __forceinline__ void accumulate_body(const uint32_t* __restrict__ sor
         Affine qn;
         if (PREFETCH) { if (pos + 1 < end) qn = fetch(pos + 1); }  // next point in flight during this addition
         else q = fetch(pos);
+        if (L2PF && !DIRECT && pos + 1 < end) {  // pull the NEXT point into L2 while this addition runs (no registers held)
+            uint32_t rn = sorted[pos + 1];
+            if (rn != REF_IDENT) asm volatile("prefetch.global.L2 [%0];" ::"l"(&table[rn & 0x7fffffffu]));
+        }
         if (pos >= next) {
             bool complete = (run_begin >= start);  // its end (`next`) is <= pos < end
             if (RELAXED) xyzz_relaxed_normalise(acc);
@@ -293,6 +297,13 @@ __global__ void __launch_bounds__(128, MINB) k_accumulate_relaxed(const uint32_t
                                                                     uint32_t chunk, int shift,
                                                                     XYZZ* __restrict__ buckets, XYZZ* __restrict__ partial) {
     accumulate_body<false, false, false, true, true>(sorted, offsets, table, nb, acc_threads, chunk, shift, buckets, partial);
+}
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_accumulate_relaxed_pf(const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ offsets,
+                                                                       const Affine* __restrict__ table, uint32_t nb, uint32_t acc_threads,
+                                                                       uint32_t chunk, int shift,
+                                                                       XYZZ* __restrict__ buckets, XYZZ* __restrict__ partial) {
+    accumulate_body<false, false, false, true, true, true>(sorted, offsets, table, nb, acc_threads, chunk, shift, buckets, partial);
 }
 // Same body under a hard register cap instead of a blocks-per-SM hint: at 112 registers four blocks leave
 // 8 K registers of every SM free, so the small blocks of the other lanes' sort kernels can be resident
@@ -887,6 +898,8 @@ void msm_launch(const MsmPlan& p, const MsmWorkspace& ws, const Fr* scalars, boo
                 case 3: KZ_ACC(4, true, true, false); break;
                 case 9: KZ_ACC(5, false, true, false); break;
                 case 15: k_accumulate_lazy<4><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, L, ws.buckets, ws.partial); break;
+                case 19: k_accumulate_relaxed_pf<4><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, L, ws.buckets, ws.partial); break;
+                case 21: k_accumulate_relaxed<5><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, L, ws.buckets, ws.partial); break;
                 case 17: k_accumulate_relaxed<3><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, L, ws.buckets, ws.partial); break;
                 case 11: k_accumulate_r<112><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, L, ws.buckets, ws.partial); break;
                 case 12: k_accumulate_r<96><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, L, ws.buckets, ws.partial); break;
