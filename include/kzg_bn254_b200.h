@@ -112,6 +112,14 @@ int kzgb_msm_var(kzgb_ctx* ctx, const uint64_t* bases_xy, const uint8_t* bases_i
 int kzgb_g1_add(const uint64_t a_xy[8], uint8_t a_inf, const uint64_t b_xy[8], uint8_t b_inf, uint64_t out_xy[8],
                 uint8_t* out_inf);
 
+/* ---- roots of unity (helpers::calculate_roots_of_unity, primitives/src/helpers.rs:553-610; KZG::calculate_and_store_roots_of_unity,
+ * prover/src/kzg.rs:65-72) ---- */
+/* w^0 .. w^(n-1), Montgomery, n = next_pow2(ceil(length_of_data_after_padding / 32)); *n_out = n.  out == NULL only queries n.
+ * Errors (GenericError) with the reference's texts: "Length of data after padding is 0", "the length of data after padding is
+ * not valid with respect to the SRS". */
+int kzgb_roots_of_unity(kzgb_ctx* ctx, uint64_t length_of_data_after_padding, uint64_t* out_mont, size_t out_capacity,
+                        size_t* n_out);
+
 /* ---- Fr (I)NTT (ark-poly fft/ifft at primitives/src/polynomial.rs:131-135, 242-246) -------- */
 /* In place, natural order in and out; n must be a power of two (<= 2^28). inverse != 0 -> ifft (with 1/n). */
 int kzgb_ntt_fr(kzgb_ctx* ctx, uint64_t* inout_mont, size_t n, int inverse);

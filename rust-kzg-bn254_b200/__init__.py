@@ -211,8 +211,15 @@ def g1_lincomb(points: Sequence[Affine], scalars: Sequence[int], engine: Optiona
     return e._point_call(lambda h, *a: lib.kzgb_msm_var(h, xy, inf, fr_to_mont_bytes(scalars), len(points), *a))
 
 
-def calculate_roots_of_unity(length_of_data_after_padding: int) -> List[int]:
-    """primitives/src/helpers.rs:553-610 (host: n multiplications of Python ints)."""
+def calculate_roots_of_unity(length_of_data_after_padding: int, engine: Optional["Engine"] = None) -> List[int]:
+    """primitives/src/helpers.rs:553-610.  With an engine: kzgb_roots_of_unity (one kernel on the GPU); without: the
+    host loop below (the no-GPU tests use it)."""
+    if engine is not None:
+        n = C.c_size_t(0)
+        engine.check(lib.kzgb_roots_of_unity(engine.h, length_of_data_after_padding, None, 0, C.byref(n)))
+        out = C.create_string_buffer(32 * n.value)
+        engine.check(lib.kzgb_roots_of_unity(engine.h, length_of_data_after_padding, out, n.value, C.byref(n)))
+        return fr_from_mont_bytes(out.raw)
     if length_of_data_after_padding == 0:
         raise KzgError("GenericError", "Length of data after padding is 0")
     nelem = -(-length_of_data_after_padding // 32)

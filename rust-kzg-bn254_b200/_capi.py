@@ -47,6 +47,7 @@ SIGNATURES = {
     "kzgb_fr_powers_dev": (C.c_int, [ctx_p, buf, C.c_size_t, C.c_size_t, buf]),
     "kzgb_msm_var": (C.c_int, [ctx_p, buf, buf, buf, C.c_size_t, buf, u8p]),
     "kzgb_g1_add": (C.c_int, [buf, C.c_uint8, buf, C.c_uint8, buf, u8p]),
+    "kzgb_roots_of_unity": (C.c_int, [ctx_p, C.c_uint64, buf, C.c_size_t, C.POINTER(C.c_size_t)]),
     "kzgb_ntt_fr": (C.c_int, [ctx_p, buf, C.c_size_t, C.c_int]),
     "kzgb_to_fr_array": (C.c_int, [ctx_p, buf, C.c_size_t, buf]),
     "kzgb_to_byte_array": (C.c_int, [ctx_p, buf, C.c_size_t, buf]),

@@ -997,6 +997,30 @@ int kzgb_g1_add(const uint64_t a_xy[8], uint8_t a_inf, const uint64_t b_xy[8], u
     return KZGB_OK;
 }
 
+// ------------------------------------------------------------------------------- roots of unity
+// helpers::calculate_roots_of_unity (primitives/src/helpers.rs:553-589; expand_root_of_unity :592-610): w^0 .. w^(n-1) for
+// n = next_pow2(ceil(len / 32)), w = PRIMITIVE_ROOTS_OF_UNITY[log2 n] (consts.rs:22-52).  The reference builds them with n serial
+// multiplications (and again inside every evaluation, helpers.rs:482); here one kernel, each power by square-and-multiply.
+int kzgb_roots_of_unity(kzgb_ctx* c, uint64_t length_of_data_after_padding, uint64_t* out, size_t out_capacity, size_t* n_out) {
+    if (length_of_data_after_padding == 0) return fail(c, KZGB_ERR_GENERIC, "Length of data after padding is 0");
+    uint64_t nelem = (length_of_data_after_padding + 31) / 32;
+    if (nelem > ((uint64_t)1 << 28))
+        return fail(c, KZGB_ERR_GENERIC, "the length of data after padding is not valid with respect to the SRS");
+    size_t n = next_pow2((size_t)nelem);
+    if (n_out) *n_out = n;
+    if (!out) return KZGB_OK;  // size query
+    if (out_capacity < n) return fail(c, KZGB_ERR_GENERIC, "output buffer too small for the roots of unity");
+    Guard g(c);
+    Lane& L = c->lanes[0];
+    CK(c, L.work.reserve(n * sizeof(Fr)));
+    Fr w = root_of_unity_mont(log2_exact(n));
+    fr_powers_launch((Fr*)L.work.p, (uint32_t)n, &w, L.st);
+    CK(c, cudaMemcpyAsync(out, L.work.p, n * sizeof(Fr), cudaMemcpyDeviceToHost, L.st));
+    CK(c, cudaStreamSynchronize(L.st));
+    CK(c, cudaGetLastError());
+    return KZGB_OK;
+}
+
 // ------------------------------------------------------------------------------- NTT / codecs
 int kzgb_ntt_fr(kzgb_ctx* c, uint64_t* inout, size_t n, int inverse) {
     Guard g(c);

@@ -33,6 +33,7 @@ extern "C" {
     pub fn kzgb_srs_get_affine_mont(ctx: *mut kzgb_ctx, start: usize, count: usize, out_xy: *mut u64, out_inf: *mut u8) -> c_int;
     pub fn kzgb_msm_var(ctx: *mut kzgb_ctx, bases_xy: *const u64, bases_inf: *const u8, scalars: *const u64, m: usize,
                         out_xy: *mut u64, out_inf: *mut u8) -> c_int;
+    pub fn kzgb_roots_of_unity(ctx: *mut kzgb_ctx, length_of_data_after_padding: u64, out: *mut u64, out_capacity: usize, n_out: *mut usize) -> c_int;
     pub fn kzgb_ntt_fr(ctx: *mut kzgb_ctx, inout: *mut u64, n: usize, inverse: c_int) -> c_int;
     pub fn kzgb_commit_eval(ctx: *mut kzgb_ctx, evals: *const u64, n: usize, out_xy: *mut u64, out_inf: *mut u8) -> c_int;
     pub fn kzgb_commit_coeff(ctx: *mut kzgb_ctx, coeffs: *const u64, n: usize, out_xy: *mut u64, out_inf: *mut u8) -> c_int;

@@ -101,6 +101,19 @@ def main():
     emit("a10", "PolynomialEvalForm::to_coeff_form (Fr IFFT)", g, c, buf.raw == cbuf.raw,
          f"device-resident: {ms.value:.3f} ms per transform")
 
+    # a9 roots of unity (the CPU leg is the reference's own algorithm: n serial multiplications, here Python big ints on one thread)
+    rbuf = C.create_string_buffer(32 * n)
+    rn = C.c_size_t(0)
+    g = best(lambda: eng.check(lib.kzgb_roots_of_unity(eng.h, 32 * n, rbuf, n, C.byref(rn))), args.reps)
+    from oracle import bn254 as o_
+
+    t0 = time.perf_counter()
+    roots_o = o_.calculate_roots_of_unity(32 * n)
+    c9 = time.perf_counter() - t0
+    sample = [0, 1, 2, n // 2, n - 1, 777 % n]
+    par9 = all(pkg.fr_from_mont_bytes(rbuf.raw[32 * i : 32 * i + 32])[0] == roots_o[i] for i in sample)
+    emit("a9", "helpers::calculate_roots_of_unity", g, c9, par9, "CPU = the reference's serial loop in Python big ints, 1 thread; parity on sampled indices")
+
     # a1 commit_eval_form
     eng.check(lib.kzgb_commit_eval(eng.h, evals_b, n, out, C.byref(inf)))
     g = best(lambda: eng.check(lib.kzgb_commit_eval(eng.h, evals_b, n, out, C.byref(inf))), args.reps)

@@ -131,6 +131,25 @@ def test_streamed_ingest_and_point_cache(pkg, ref_srs_points, tmp_path):
         lib.kzgb_set_option(b"srs_chunk_points", 0)
 
 
+def test_roots_of_unity_match_the_reference_table(pkg, eng):
+    """helpers::calculate_roots_of_unity (helpers.rs:553-610) on the GPU vs the oracle and the literal
+    table of primitives/tests/helpers_test.rs:587-628 (first/last entries); error texts of :554-566."""
+    for nbytes in (1, 32, 33, 1536, 32 * 4096, 32 * 5000):
+        got = pkg.calculate_roots_of_unity(nbytes, eng)
+        assert got == o.calculate_roots_of_unity(nbytes)
+    n = 1 << 19
+    big = pkg.calculate_roots_of_unity(32 * n, eng)
+    w = o.PRIMITIVE_ROOTS_OF_UNITY[19]
+    assert len(big) == n and big[0] == 1 and big[1] == w and big[n // 2] == o.R - 1
+    assert big[n - 1] == pow(w, n - 1, o.R) and big[12345] == pow(w, 12345, o.R)
+    with pytest.raises(pkg.KzgError) as e:
+        pkg.calculate_roots_of_unity(0, eng)
+    assert e.value.msg == "Length of data after padding is 0"
+    with pytest.raises(pkg.KzgError) as e:
+        pkg.calculate_roots_of_unity(32 * ((1 << 28) + 1), eng)
+    assert e.value.msg == "the length of data after padding is not valid with respect to the SRS"
+
+
 def test_to_fr_array_kat(pkg, eng):
     assert pkg.to_fr_array(g.blobs_txt(), eng) == g.blobs_from_fr()
     for raw in (b"", b"\x01", bytes(range(33)), b"\xff" * 95, g.gettysburg()):
