@@ -580,12 +580,14 @@ def test_g1_ifft_closed_form_large(pkg):
 
 def test_device_fiat_shamir_matches_host_and_oracle(pkg, ref_srs, ref_srs_points):
     """The per-blob challenges of verify_blob_kzg_proof_batch hashed on the GPU (fs.cu, one thread per
-    transcript) against the host SHA-256 pool and the oracle: polynomial lengths 1, 2, 4, 64, 256
+    transcript) against the host SHA-256 pool and the oracle: polynomial lengths 1, 2, 4, 16, 32, 64, 256, 1024
     (odd / even block structure of the transcript), ragged and non-canonical blobs, identity commitment."""
     rnd = random.Random(33)
     eng = ref_srs.engine
     raws = [b"x", b"y" * 31, b"ab" * 20, b"cd" * 40, g.gettysburg(), g.gettysburg()[:700], bytes(31 * 200), b"z",
-            bytes(rnd.getrandbits(8) for _ in range(31 * 256 - 7)), bytes(rnd.getrandbits(8) for _ in range(31 * 250))]
+            bytes(rnd.getrandbits(8) for _ in range(31 * 256 - 7)), bytes(rnd.getrandbits(8) for _ in range(31 * 250)),
+            bytes(rnd.getrandbits(8) for _ in range(31 * 10)), bytes(rnd.getrandbits(8) for _ in range(31 * 13)),
+            bytes(rnd.getrandbits(8) for _ in range(31 * 1000))]  # n = 16 (quad kernel, 7 middle blocks), 16, 1024
     blobs = [pkg.Blob.from_raw_data(r) for r in raws]
     blobs.append(pkg.Blob.from_unchecked(b"\xff" * 45 + bytes(range(50))))  # non-canonical, ragged
     blobs.sort(key=lambda b: len(b))  # equal lengths adjacent -> batched chunks
