@@ -214,6 +214,8 @@ int kzgb_msm_tuning(int batch_affine_levels, int min_avg_bucket, int pairs_per_t
  *   "fs_device"            -1 auto (default), 0 host SHA-256 pool, 1 device kernel for the per-blob
  *                          Fiat-Shamir challenges of kzgb_verify_batch_rlc (auto: >= 256 blobs of <= 2^13 Fr)
  *   "batch_affine_levels"  as in kzgb_msm_tuning
+ *   "fs_force_generic"     1: the device-hashed challenges of kzgb_verify_batch_rlc are all flagged "in the domain", so the
+ *                          per-polynomial choice made on the device takes the generic inverses everywhere (tests)
  *   "eval_structured"      1 (default): for z outside the domain the barycentric denominators 1/(z - w_i) come from
  *                          the factorisation of z^n - 1 (~3 multiplications each); 0: generic prefix/suffix products
  *   "srs_chunk_points"     points per chunk of the streamed SRS ingest (0 = default 2^22)

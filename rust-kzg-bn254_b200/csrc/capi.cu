@@ -1607,7 +1607,7 @@ int kzgb_verify_batch_rlc(kzgb_ctx* c, const uint8_t* const* blobs, const size_t
         CK(c, L.evals.reserve(b * n * sizeof(Fr)));
         CK(c, L.bytes.reserve(b * n * 32));
         CK(c, L.eval_scratch.reserve(eval_quotient_scratch_elems((uint32_t)n, (uint32_t)b) * sizeof(Fr)));
-        CK(c, L.work.reserve(4 * b * sizeof(Fr)));
+        CK(c, L.work.reserve(5 * b * sizeof(Fr)));
         bool full = (uint64_t)b * n < 0xffffffffull;  // every blob fills its polynomial: one conversion launch
         for (size_t k = 0; k < b && full; k++) full = lens[i0 + k] == n * 32;
         for (size_t k = 0; k < b;) {
@@ -1627,13 +1627,15 @@ int kzgb_verify_batch_rlc(kzgb_ctx* c, const uint8_t* const* blobs, const size_t
         Fr ninv = ninv_mont(logn);
         std::vector<Fr> tinvs;
         std::vector<uint8_t> cbytes;
-        bool any_in_domain = false;  // (challenges hashed on the device are not known here: generic inverses)
+        bool any_in_domain = false;
+        uint32_t* d_in_domain = nullptr;  // challenges hashed on the device: the device says which z are roots of the domain
         if (fs_device) {
             uint8_t* d_c32 = (uint8_t*)(d_y + b);
             cbytes.resize(b * 32);
             for (size_t k = 0; k < b; k++) serialize_compressed(Cs[i0 + k], &cbytes[32 * k]);
             CK(c, cudaMemcpyAsync(d_c32, cbytes.data(), b * 32, cudaMemcpyHostToDevice, L.st));
-            fs_challenges_launch((Fr*)L.evals.p, (uint32_t)n, logn, (uint32_t)b, d_c32, &ninv, d_z, d_t, L.st);
+            d_in_domain = (uint32_t*)(d_c32 + 32 * b);
+            fs_challenges_launch((Fr*)L.evals.p, (uint32_t)n, logn, (uint32_t)b, d_c32, &ninv, d_z, d_t, L.st, d_in_domain);
             CK(c, cudaMemcpyAsync(&zs[i0], d_z, b * sizeof(Fr), cudaMemcpyDeviceToHost, L.st));
         } else {
             tinvs.resize(b);
@@ -1642,7 +1644,7 @@ int kzgb_verify_batch_rlc(kzgb_ctx* c, const uint8_t* const* blobs, const size_t
             CK(c, cudaMemcpyAsync(d_t, tinvs.data(), b * sizeof(Fr), cudaMemcpyHostToDevice, L.st));
         }
         eval_quotient_launch((Fr*)L.evals.p, (uint32_t)n, logn, (uint32_t)b, d_z, d_t, c->tw, c->logN, &ninv,
-                             (Fr*)L.eval_scratch.p, nullptr, d_y, L.st, !fs_device && !any_in_domain);
+                             (Fr*)L.eval_scratch.p, nullptr, d_y, L.st, !fs_device && !any_in_domain, d_in_domain);
         CK(c, cudaMemcpyAsync(&ys[i0], d_y, b * sizeof(Fr), cudaMemcpyDeviceToHost, L.st));
         CK(c, cudaStreamSynchronize(L.st));
         CK(c, cudaGetLastError());
@@ -1837,6 +1839,7 @@ int kzgb_set_option(const char* name, long value) {
     if (!name) return KZGB_ERR_GENERIC;
     if (!strcmp(name, "fs_device")) { g_fs_device.store((int)value); return KZGB_OK; }
     if (!strcmp(name, "srs_chunk_points")) { g_srs_chunk.store(value < 0 ? 0 : value); return KZGB_OK; }
+    if (!strcmp(name, "fs_force_generic")) { fs_set_force_flag((int)value); return KZGB_OK; }
     if (!strcmp(name, "eval_structured")) { eval_set_structured((int)value); return KZGB_OK; }
     if (!strcmp(name, "group")) { g_group.store((int)value); return KZGB_OK; }
     if (!strcmp(name, "lagrange")) { g_lagrange.store(value != 0); return KZGB_OK; }

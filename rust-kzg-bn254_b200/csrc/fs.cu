@@ -53,7 +53,8 @@ __device__ __forceinline__ void fr_to_be_words(uint32_t* w, const Fr& mont) {
 
 __global__ void __launch_bounds__(64) k_fs_challenges(const Fr* __restrict__ evals, uint32_t n, int logn, uint32_t batch,
                                                        const uint8_t* __restrict__ commit32, Fr ninv,
-                                                       Fr* __restrict__ z_out, Fr* __restrict__ tinv_out) {
+                                                       Fr* __restrict__ z_out, Fr* __restrict__ tinv_out,
+                                                       uint32_t* __restrict__ in_domain_out, bool force_flag) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= batch) return;
     const Fr* f = evals + (size_t)k * n;
@@ -105,9 +106,11 @@ __global__ void __launch_bounds__(64) k_fs_challenges(const Fr* __restrict__ eva
     for (int s = 0; s < logn; s++) fe_sqr(zn, zn);
     fe_one(one);
     Fr t;
-    if (fe_eq(zn, one)) fe_mul(t, z, ninv);
+    const bool in_domain = fe_eq(zn, one);
+    if (in_domain) fe_mul(t, z, ninv);
     else { fe_sub(zn, zn, one); fe_inv_fast(t, zn); }
     fe_store(&tinv_out[k], t);
+    if (in_domain_out) in_domain_out[k] = (in_domain || force_flag) ? 1u : 0u;
 }
 
 // ---- four lanes per blob ----------------------------------------------------------------------------------
@@ -132,7 +135,8 @@ __device__ __forceinline__ void sha256_schedule_k(uint32_t wk[64], uint32_t w[16
 
 __global__ void __launch_bounds__(128) k_fs_challenges_quad(const Fr* __restrict__ evals, uint32_t n, int logn, uint32_t batch,
                                                              const uint8_t* __restrict__ commit32, Fr ninv,
-                                                             Fr* __restrict__ z_out, Fr* __restrict__ tinv_out) {
+                                                             Fr* __restrict__ z_out, Fr* __restrict__ tinv_out,
+                                                             uint32_t* __restrict__ in_domain_out, bool force_flag) {
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t k = tid >> 2, sub = tid & 3u;
     const bool valid = k < batch;
@@ -215,19 +219,25 @@ __global__ void __launch_bounds__(128) k_fs_challenges_quad(const Fr* __restrict
     for (int s = 0; s < logn; s++) fe_sqr(zn, zn);
     fe_one(one);
     Fr t;
-    if (fe_eq(zn, one)) fe_mul(t, z, ninv);
+    const bool in_domain = fe_eq(zn, one);
+    if (in_domain) fe_mul(t, z, ninv);
     else { fe_sub(zn, zn, one); fe_inv_fast(t, zn); }
     fe_store(&tinv_out[k], t);
+    if (in_domain_out) in_domain_out[k] = (in_domain || force_flag) ? 1u : 0u;
 }
 
+// tests: flag every polynomial as "z in the domain" so the device-side choice takes the generic inverses everywhere
+static std::atomic<int> g_fs_force_flag{0};
+void fs_set_force_flag(int on) { g_fs_force_flag.store(on != 0); }
+
 void fs_challenges_launch(const Fr* evals, uint32_t n, int logn, uint32_t batch, const uint8_t* commit32_dev,
-                          const Fr* ninv_mont_host, Fr* z_out, Fr* tinv_out, cudaStream_t st) {
+                          const Fr* ninv_mont_host, Fr* z_out, Fr* tinv_out, cudaStream_t st, uint32_t* in_domain_out) {
     if (!batch) return;
     static const int quad = getenv("KZGB_FS_QUAD") ? atoi(getenv("KZGB_FS_QUAD")) : 1;
     if (quad && n >= 16)
-        k_fs_challenges_quad<<<(batch * 4 + 127) / 128, 128, 0, st>>>(evals, n, logn, batch, commit32_dev, *ninv_mont_host, z_out, tinv_out);
+        k_fs_challenges_quad<<<(batch * 4 + 127) / 128, 128, 0, st>>>(evals, n, logn, batch, commit32_dev, *ninv_mont_host, z_out, tinv_out, in_domain_out, g_fs_force_flag.load() != 0);
     else
-        k_fs_challenges<<<(batch + 63) / 64, 64, 0, st>>>(evals, n, logn, batch, commit32_dev, *ninv_mont_host, z_out, tinv_out);
+        k_fs_challenges<<<(batch + 63) / 64, 64, 0, st>>>(evals, n, logn, batch, commit32_dev, *ninv_mont_host, z_out, tinv_out, in_domain_out, g_fs_force_flag.load() != 0);
     g_launch_count++;
 }
 

@@ -116,7 +116,11 @@ void fr_to_bytes_launch(const Fr* in, uint8_t* out, uint32_t n, cudaStream_t st)
 // tinv_mont_dev[batch]: 1/(z^n - 1), or z/n when z^n == 1 (one host inversion per polynomial).
 void eval_quotient_launch(const Fr* evals, uint32_t n, int logn, uint32_t batch, const Fr* z_mont_dev,
                           const Fr* tinv_mont_dev, const Fr* tw, int logN, const Fr* ninv_mont_host, Fr* scratch,
-                          Fr* q_out, Fr* y_out, cudaStream_t st, bool z_outside_domain = false);
+                          Fr* q_out, Fr* y_out, cudaStream_t st, bool z_outside_domain = false,
+                          const uint32_t* in_domain_dev = nullptr);
+// in_domain_dev (device, batch words, e.g. from fs_challenges_launch): per-polynomial choice made ON THE DEVICE --
+// polynomials with flag 0 take the structured inverses, flagged ones the generic form (both kernel sets are
+// launched; blocks of the wrong kind exit at once).
 // z_outside_domain: the caller knows that no z of the batch is a root of the domain (z^n != 1); the
 // inverses then come from the factorisation of z^n - 1 (~3 instead of ~10 multiplications per element).
 size_t eval_quotient_scratch_elems(uint32_t n, uint32_t batch);
@@ -125,8 +129,10 @@ void eval_set_structured(int on);
 // Fiat-Shamir challenges of `batch` blobs of n evaluations each on the device (fs.cu; reference
 // primitives/src/helpers.rs:411-472): z_out[k] (Montgomery) and tinv_out[k] = 1/(z^n - 1) (or z/n in the
 // domain).  commit32_dev: batch x 32 bytes, arkworks-compressed commitments.
+void fs_set_force_flag(int on);
+// in_domain_out (optional, batch words): 1 where z_k turned out to be a root of the domain.
 void fs_challenges_launch(const Fr* evals, uint32_t n, int logn, uint32_t batch, const uint8_t* commit32_dev,
-                          const Fr* ninv_mont_host, Fr* z_out, Fr* tinv_out, cudaStream_t st);
+                          const Fr* ninv_mont_host, Fr* z_out, Fr* tinv_out, cudaStream_t st, uint32_t* in_domain_out = nullptr);
 // out[i] = base^(first + i) (Montgomery), i < n
 void fr_powers_launch(Fr* out, uint32_t n, const Fr* base_mont_host, cudaStream_t st, uint32_t first = 0);
 // out[i] = a[i] * b[i]

@@ -156,9 +156,11 @@ __device__ __forceinline__ void warp_scan_products(const Fr& v, uint32_t lane, F
 __global__ void __launch_bounds__(EVAL_THREADS) k_eval_block_products(uint32_t n, int logn, const Fr* __restrict__ z_all,
                                                                       const Fr* __restrict__ tw, int logN,
                                                                       Fr* __restrict__ bprod_all, uint32_t nparts,
-                                                                      uint32_t* __restrict__ zidx_all) {
+                                                                      uint32_t* __restrict__ zidx_all,
+                                                                      const uint32_t* __restrict__ only_flagged) {
     __shared__ uint32_t wt[8][EVAL_THREADS / 32];
     const uint32_t bi = blockIdx.y;
+    if (only_flagged && !only_flagged[bi]) return;
     const Fr z = fe_load(&z_all[bi]);
     const uint32_t base = blockIdx.x * EVAL_TILE + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -190,9 +192,11 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_eval_block_products(uint32_t n
 
 // E2 (one block per polynomial): fac[j] = T^-1 * prod_{k != j} bprod[k]
 __global__ void __launch_bounds__(EVAL_THREADS) k_eval_block_factors(const Fr* __restrict__ bprod_all, uint32_t nparts,
-                                                                     const Fr* __restrict__ tinv_all, Fr* __restrict__ fac_all) {
+                                                                     const Fr* __restrict__ tinv_all, Fr* __restrict__ fac_all,
+                                                                     const uint32_t* __restrict__ only_flagged) {
     __shared__ Fr pre[EVAL_THREADS], post[EVAL_THREADS];
     const uint32_t bi = blockIdx.x, tid = threadIdx.x;
+    if (only_flagged && !only_flagged[bi]) return;
     const Fr* bprod = bprod_all + (size_t)bi * nparts;
     Fr* fac = fac_all + (size_t)bi * nparts;
     const uint32_t per = (nparts + EVAL_THREADS - 1) / EVAL_THREADS;
@@ -235,9 +239,10 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_eval_inverses(const Fr* __rest
                                                                 const Fr* __restrict__ z_all, const Fr* __restrict__ tw,
                                                                 int logN, const Fr* __restrict__ fac_all,
                                                                 Fr* __restrict__ inv_all, Fr* __restrict__ partial_all,
-                                                                uint32_t nparts) {
+                                                                uint32_t nparts, const uint32_t* __restrict__ only_flagged) {
     __shared__ uint32_t wt[8][EVAL_THREADS / 32];
     const uint32_t bi = blockIdx.y;
+    if (only_flagged && !only_flagged[bi]) return;
     const Fr* evals = evals_all + (size_t)bi * n;
     Fr* inv = inv_all + (size_t)bi * n;
     Fr* partial = partial_all + (size_t)bi * nparts;
@@ -304,9 +309,11 @@ static std::atomic<int> g_eval_structured{getenv("KZGB_EVAL_STRUCTURED") ? atoi(
 void eval_set_structured(int on) { g_eval_structured.store(on != 0); }
 static constexpr int ZP_STRIDE = 32;  // Z_j slots per polynomial
 
-__global__ void __launch_bounds__(64) k_eval_zpowers(const Fr* __restrict__ z_all, int logn, uint32_t batch, Fr* __restrict__ zp_all) {
+__global__ void __launch_bounds__(64) k_eval_zpowers(const Fr* __restrict__ z_all, int logn, uint32_t batch, Fr* __restrict__ zp_all,
+                                                     const uint32_t* __restrict__ skip_flagged) {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= batch) return;
+    if (skip_flagged && skip_flagged[b]) return;
     Fr z = fe_load(&z_all[b]);
     for (int j = 0; j < logn; j++) {
         fe_store(&zp_all[(size_t)b * ZP_STRIDE + j], z);
@@ -318,9 +325,10 @@ __global__ void __launch_bounds__(EV2_THREADS) k_eval_inverses2(const Fr* __rest
                                                                  const Fr* __restrict__ tw, int logN,
                                                                  const Fr* __restrict__ tinv_all, const Fr* __restrict__ zp_all,
                                                                  Fr* __restrict__ inv_all, Fr* __restrict__ partial_all,
-                                                                 uint32_t nparts) {
+                                                                 uint32_t nparts, const uint32_t* __restrict__ skip_flagged) {
     __shared__ Fr zs[ZP_STRIDE];
     const uint32_t bi = blockIdx.y;
+    if (skip_flagged && skip_flagged[bi]) return;
     if ((int)threadIdx.x < logn) zs[threadIdx.x] = fe_load(&zp_all[(size_t)bi * ZP_STRIDE + threadIdx.x]);
     __syncthreads();
     const Fr* evals = evals_all + (size_t)bi * n;
@@ -514,7 +522,7 @@ size_t eval_quotient_scratch_elems(uint32_t n, uint32_t batch) {
 
 void eval_quotient_launch(const Fr* evals, uint32_t n, int logn, uint32_t batch, const Fr* z_mont_dev,
                           const Fr* tinv_mont_dev, const Fr* tw, int logN, const Fr* ninv_mont_host, Fr* scratch,
-                          Fr* q_out, Fr* y_out, cudaStream_t st, bool z_outside_domain) {
+                          Fr* q_out, Fr* y_out, cudaStream_t st, bool z_outside_domain, const uint32_t* in_domain_dev) {
     if (!batch) return;
     uint32_t parts1 = (n + EVAL_TILE - 1) / EVAL_TILE;
     uint32_t parts2 = (n + EVAL_THREADS - 1) / EVAL_THREADS;
@@ -526,18 +534,23 @@ void eval_quotient_launch(const Fr* evals, uint32_t n, int logn, uint32_t batch,
     uint32_t* zidx = reinterpret_cast<uint32_t*>(partial2 + (size_t)batch * parts2);
     Fr* zp = partial2 + (size_t)batch * parts2 + (((size_t)batch * 4 + 31) / 32 + 1);
     cudaMemsetAsync(zidx, 0, (size_t)batch * 4, st);
-    if (z_outside_domain && g_eval_structured.load() && logn >= 6 && logn <= 28) {
-        // every z is outside the domain: inverses from the factorisation of z^n - 1 (EVAL_TILE = 16 * EV2_THREADS,
+    const bool can_structure = g_eval_structured.load() && logn >= 6 && logn <= 28;
+    const bool per_poly = in_domain_dev != nullptr && can_structure;  // the device decides per polynomial
+    if ((z_outside_domain && can_structure) || per_poly) {
+        // z outside the domain: inverses from the factorisation of z^n - 1 (EVAL_TILE = 16 * EV2_THREADS,
         // so the per-block partial sums land exactly where k_eval_finish expects them)
         static_assert(16 * EV2_THREADS == EVAL_TILE, "partial-sum layout");
-        k_eval_zpowers<<<(batch + 63) / 64, 64, 0, st>>>(z_mont_dev, logn, batch, zp);
-        k_eval_inverses2<<<dim3(parts1, batch), EV2_THREADS, 0, st>>>(evals, n, logn, tw, logN, tinv_mont_dev, zp, inv, partial1, parts1);
+        const uint32_t* skip = per_poly ? in_domain_dev : nullptr;
+        k_eval_zpowers<<<(batch + 63) / 64, 64, 0, st>>>(z_mont_dev, logn, batch, zp, skip);
+        k_eval_inverses2<<<dim3(parts1, batch), EV2_THREADS, 0, st>>>(evals, n, logn, tw, logN, tinv_mont_dev, zp, inv, partial1, parts1, skip);
         g_launch_count += 2;
-    } else {
-        k_eval_block_products<<<dim3(parts1, batch), EVAL_THREADS, 0, st>>>(n, logn, z_mont_dev, tw, logN, bprod, parts1, zidx);
-        k_eval_block_factors<<<batch, EVAL_THREADS, 0, st>>>(bprod, parts1, tinv_mont_dev, fac);
+    }
+    if (!(z_outside_domain && can_structure)) {
+        const uint32_t* only = per_poly ? in_domain_dev : nullptr;
+        k_eval_block_products<<<dim3(parts1, batch), EVAL_THREADS, 0, st>>>(n, logn, z_mont_dev, tw, logN, bprod, parts1, zidx, only);
+        k_eval_block_factors<<<batch, EVAL_THREADS, 0, st>>>(bprod, parts1, tinv_mont_dev, fac, only);
         k_eval_inverses<<<dim3(parts1, batch), EVAL_THREADS, 0, st>>>(evals, n, logn, z_mont_dev, tw, logN, fac, inv, partial1,
-                                                                      parts1);
+                                                                      parts1, only);
         g_launch_count += 3;
     }
     k_eval_finish<<<batch, EVAL_THREADS, 0, st>>>(evals, n, logn, z_mont_dev, *ninv_mont_host, partial1, parts1, zidx, y_out);

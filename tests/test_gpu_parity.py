@@ -597,11 +597,15 @@ def test_device_fiat_shamir_matches_host_and_oracle(pkg, ref_srs, ref_srs_points
     try:
         pkg.lib.kzgb_set_option(b"fs_device", 1)
         dev = pkg.verify_blob_kzg_proof_batch_rlc(blobs, cpts, ppts, eng)
+        pkg.lib.kzgb_set_option(b"fs_force_generic", 1)  # device-side choice: generic inverses for every polynomial
+        dev_generic = pkg.verify_blob_kzg_proof_batch_rlc(blobs, cpts, ppts, eng)
+        pkg.lib.kzgb_set_option(b"fs_force_generic", 0)
         pkg.lib.kzgb_set_option(b"fs_device", 0)
         host = pkg.verify_blob_kzg_proof_batch_rlc(blobs, cpts, ppts, eng)
     finally:
         pkg.lib.kzgb_set_option(b"fs_device", -1)
-    assert dev == host
+        pkg.lib.kzgb_set_option(b"fs_force_generic", 0)
+    assert dev == host == dev_generic
     bo = [o.Blob.from_unchecked(b.data()) for b in blobs]
     assert dev == o.verify_blob_kzg_proof_batch_rlc(bo, cpts, ppts)
     assert pkg.lib.kzgb_set_option(b"no_such_option", 1) != 0
