@@ -106,6 +106,28 @@ impl SRS<'_> {
     }
 }
 
+/// Additions next to the reference's API (nothing above changes meaning): warm-up and caching hooks.
+impl SRS<'_> {
+    /// Builds the resident Lagrange-basis window table for evaluation-form polynomials of `n` elements now
+    /// instead of on the first commit of that size (the cached form of the `g1_ifft` that
+    /// `KZG::commit_eval_form` runs on every call in the reference, prover/src/kzg.rs:98).
+    pub fn prepare_lagrange(&self, n: usize) -> Result<(), KzgError> {
+        with_ctx(self, |ctx| {
+            let rc = unsafe { ffi::kzgb_srs_prepare_lagrange(ctx, n) };
+            if rc != 0 { Err(to_err(ctx, rc, n, self.g1.len())) } else { Ok(()) }
+        })
+    }
+    /// Writes the decompressed points so that a later process can skip the per-point square root
+    /// (`kzgb_srs_load_cache` checks every point to be on the curve instead).
+    pub fn save_cache(&self, path: &str) -> Result<(), KzgError> {
+        let cpath = CString::new(path).unwrap();
+        with_ctx(self, |ctx| {
+            let rc = unsafe { ffi::kzgb_srs_save_cache(ctx, cpath.as_ptr()) };
+            if rc != 0 { Err(to_err(ctx, rc, 0, 0)) } else { Ok(()) }
+        })
+    }
+}
+
 fn with_ctx<T>(srs: &SRS, f: impl FnOnce(*mut ffi::kzgb_ctx) -> T) -> T {
     let key = (srs.g1.as_ptr() as usize, srs.g1.len());
     let mut reg = REGISTRY.lock().unwrap();
