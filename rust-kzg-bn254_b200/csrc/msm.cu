@@ -17,6 +17,7 @@
 // scalar i belongs to MSM i / batch_n, which owns bucket set i / batch_n -- how runs of small blobs are committed.
 #include <cstdlib>
 #include "kzgb_internal.hpp"
+#include "ec_dfma.cuh"
 
 namespace kzgb {
 
@@ -314,6 +315,59 @@ __global__ void __maxnreg__(MAXR) k_accumulate_r(const uint32_t* __restrict__ so
                                                   uint32_t chunk, int shift,
                                                   XYZZ* __restrict__ buckets, XYZZ* __restrict__ partial) {
     accumulate_body<false, false, false>(sorted, offsets, table, nb, acc_threads, chunk, shift, buckets, partial);
+}
+
+// ---- FP64-pipe accumulation (experimental, opt-in: accumulate variants 23-26) ----------------------------
+// The same fixed-size-chunk walk as accumulate_body with the accumulator held as 5 x 52-bit double limbs
+// (ec_dfma.cuh): the products run on the FP64 pipe (DFMA hi/lo halves) and the ALU instead of the IMAD.WIDE pipe
+// that bounds k_accumulate_relaxed.  Results are canonical XYZZ like every other variant, so k_bucket_fix and the
+// reduction are unchanged.  (The walk is repeated here rather than templated into accumulate_body so that the
+// production kernels stay byte-identical while this is being measured.)
+__device__ __forceinline__ void accumulate_body_dfma(const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ offsets,
+                                                     const Affine* __restrict__ table, uint32_t nb, uint32_t acc_threads,
+                                                     uint32_t chunk, XYZZ* __restrict__ buckets, XYZZ* __restrict__ partial) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= acc_threads) return;
+    const uint32_t M = offsets[nb];
+    uint64_t start64 = (uint64_t)t * chunk;
+    if (start64 >= M) return;
+    uint32_t start = (uint32_t)start64;
+    uint32_t end = (uint32_t)min((uint64_t)M, start64 + chunk);
+    uint32_t lo = 0, hi = nb;  // invariant: offsets[lo] <= start < offsets[hi]
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (offsets[mid] <= start) lo = mid; else hi = mid;
+    }
+    uint32_t b = lo;
+    uint32_t run_begin = offsets[b], next = offsets[b + 1];
+    dfma::XYZZ5 acc; dfma::xyzz5_set_inf(acc);
+    auto flush = [&](XYZZ* dst) {
+        XYZZ out;
+        dfma::xyzz5_to_xyzz(out, acc);
+        xyzz_store(dst, out);
+    };
+    for (uint32_t pos = start; pos < end; pos++) {
+        Affine q = load_point(table, sorted[pos]);
+        if (pos >= next) {
+            flush((run_begin >= start) ? &buckets[b] : &partial[2 * t]);
+            dfma::xyzz5_set_inf(acc);
+            do { b++; } while (offsets[b + 1] <= pos);
+            run_begin = offsets[b]; next = offsets[b + 1];
+        }
+        dfma::xyzz5_madd(acc, q);
+    }
+    bool complete = (run_begin >= start) && (next <= end);
+    flush(complete ? &buckets[b] : (run_begin <= start) ? &partial[2 * t] : &partial[2 * t + 1]);
+}
+// DFMA_OF4 of every 4 consecutive blocks accumulate on the FP64 pipe, the rest on the IMAD.WIDE pipe (the
+// relaxed integer body): blocks of both kinds are resident on every SM, so the two pipes are busy at once.
+// DFMA_OF4 = 4: every block on the FP64 pipe.
+template <int DFMA_OF4, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_accumulate_hybrid(const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ offsets,
+                                                                   const Affine* __restrict__ table, uint32_t nb, uint32_t acc_threads,
+                                                                   uint32_t chunk, XYZZ* __restrict__ buckets, XYZZ* __restrict__ partial) {
+    if (DFMA_OF4 == 4 || (int)(blockIdx.x & 3) < DFMA_OF4) accumulate_body_dfma(sorted, offsets, table, nb, acc_threads, chunk, buckets, partial);
+    else accumulate_body<false, false, false, true, true>(sorted, offsets, table, nb, acc_threads, chunk, 0, buckets, partial);
 }
 
 // Buckets whose entries span more than LONG_SPAN chunks (hot buckets: equal scalars, a top window with a
@@ -906,6 +960,12 @@ void msm_launch(const MsmPlan& p, const MsmWorkspace& ws, const Fr* scalars, boo
                 case 13: k_accumulate_r<104><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, L, ws.buckets, ws.partial); break;
                 case 14: k_accumulate_r<80><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, L, ws.buckets, ws.partial); break;
                 case 20: KZ_ACC(4, false, false, false); break;  // every product reduced on its own (the default until the lazy Y3)
+                // FP64-pipe accumulation (ec_dfma.cuh): 23 = every block, 24/25/26 = 1/2/3 of every 4 blocks, the rest integer
+                case 23: k_accumulate_hybrid<4, 3><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, ws.buckets, ws.partial); break;
+                case 24: k_accumulate_hybrid<1, 3><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, ws.buckets, ws.partial); break;
+                case 25: k_accumulate_hybrid<2, 3><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, ws.buckets, ws.partial); break;
+                case 26: k_accumulate_hybrid<3, 3><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, ws.buckets, ws.partial); break;
+                case 27: k_accumulate_hybrid<2, 4><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, ws.buckets, ws.partial); break;
                 case 16: k_accumulate_lazy<3><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, L, ws.buckets, ws.partial); break;
                 default: k_accumulate_relaxed<4><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, L, ws.buckets, ws.partial); break;
             }
