@@ -234,3 +234,121 @@ impl KZG {
         })
     }
 }
+
+impl KZG {
+    /// prover/src/kzg.rs:237-260: the quotient's evaluation at the domain point z = w_m itself,
+    /// q_m = sum_{i != m} (f_i - y) w_i / (z (z - w_i)).  Host-side (the GPU computes the same value inside
+    /// `kzgb_compute_proof`; this stays callable on its own as in the reference): ONE batched inversion for all
+    /// denominators instead of the reference's n separate ones.
+    pub fn compute_quotient_eval_on_domain(&self, z_fr: &Fr, eval_fr: &[Fr], value_fr: &Fr) -> Fr {
+        use ark_ff::{batch_inversion, One};
+        let roots = &self.expanded_roots_of_unity;
+        let mut denominators: Vec<Fr> = roots.iter().map(|w| if w == z_fr { Fr::one() } else { *z_fr * (*z_fr - *w) }).collect();
+        batch_inversion(&mut denominators);
+        let mut quotient = Fr::zero();
+        for ((w, f), d_inv) in roots.iter().zip(eval_fr.iter()).zip(denominators.iter()) {
+            if w == z_fr {
+                continue;
+            }
+            quotient += (*f - *value_fr) * *w * *d_inv;
+        }
+        quotient
+    }
+
+    /// Addition next to the reference's API (BASELINE config 3): commit_blob + compute_blob_proof for a batch of
+    /// blobs in ONE call -- the pipelined / grouped path of `kzgb_commit_and_prove_blobs`.  Returns the arkworks
+    /// compressed bytes of (commitment, proof) per blob, the encoding the reference's transcripts use.
+    pub fn commit_and_prove_blobs(&self, blobs: &[Blob], srs: &SRS) -> Result<Vec<([u8; 32], [u8; 32])>, KzgError> {
+        let ptrs: Vec<*const u8> = blobs.iter().map(|b| b.data().as_ptr()).collect();
+        let lens: Vec<usize> = blobs.iter().map(|b| b.data().len()).collect();
+        let mut commitments = vec![0u8; 32 * blobs.len()];
+        let mut proofs = vec![0u8; 32 * blobs.len()];
+        with_ctx(srs, |ctx| {
+            let rc = unsafe {
+                ffi::kzgb_commit_and_prove_blobs(ctx, ptrs.as_ptr(), lens.as_ptr(), blobs.len(), commitments.as_mut_ptr(), proofs.as_mut_ptr())
+            };
+            if rc != 0 {
+                return Err(to_err(ctx, rc, 0, srs.g1.len()));
+            }
+            Ok((0..blobs.len())
+                .map(|i| (commitments[32 * i..32 * i + 32].try_into().unwrap(), proofs[32 * i..32 * i + 32].try_into().unwrap()))
+                .collect())
+        })
+    }
+}
+
+/// Entry points of `primitives` / `verifier` that sit on the path but need no SRS: they run on a default context
+/// (device 0, created on first use).  The reference crates call these from the bodies named in each doc comment;
+/// `primitives` cannot depend on this crate, so the two-line patches go behind a `gpu` feature there
+/// (INTEGRATION.md 4).
+pub mod backend {
+    use super::*;
+
+    static DEFAULT_CTX: Mutex<Option<Ctx>> = Mutex::new(None);
+
+    fn with_default_ctx<T>(f: impl FnOnce(*mut ffi::kzgb_ctx) -> T) -> Result<T, KzgError> {
+        let mut guard = DEFAULT_CTX.lock().unwrap();
+        if guard.is_none() {
+            let mut ctx = std::ptr::null_mut();
+            if unsafe { ffi::kzgb_ctx_create(&mut ctx, 0, std::ptr::null_mut()) } != 0 {
+                return Err(KzgError::GenericError("no usable CUDA device".into()));
+            }
+            *guard = Some(Ctx(ctx));
+        }
+        Ok(f(guard.as_ref().unwrap().0))
+    }
+
+    /// Body of `PolynomialEvalForm::to_coeff_form` (inverse = true) / `PolynomialCoeffForm::to_eval_form`
+    /// (primitives/src/polynomial.rs:130-140, :241-251): natural order in and out, in place.
+    pub fn ntt_fr_in_place(data: &mut [Fr], inverse: bool) -> Result<(), KzgError> {
+        let n = data.len();
+        with_default_ctx(|ctx| {
+            let rc = unsafe { ffi::kzgb_ntt_fr(ctx, data.as_mut_ptr() as *mut u64, n, inverse as i32) };
+            if rc != 0 { Err(to_err(ctx, rc, n, 0)) } else { Ok(()) }
+        })?
+    }
+
+    /// `helpers::g1_lincomb` (primitives/src/helpers.rs:328-337): variable-base MSM, result in affine form.
+    pub fn g1_lincomb(points: &[G1Affine], scalars: &[Fr]) -> Result<G1Affine, KzgError> {
+        if points.len() != scalars.len() {
+            return Err(KzgError::MsmError(format!("bases and scalars differ in length: {} vs {}", points.len(), scalars.len())));
+        }
+        let (xy, inf) = pack_points(points);
+        let (mut out, mut out_inf) = ([0u64; 8], 0u8);
+        with_default_ctx(|ctx| {
+            let rc = unsafe { ffi::kzgb_msm_var(ctx, xy.as_ptr(), inf.as_ptr(), fr_words(scalars), points.len(), out.as_mut_ptr(), &mut out_inf) };
+            if rc != 0 { Err(to_err(ctx, rc, points.len(), 0)) } else { Ok(unpack_point(&out, out_inf)) }
+        })?
+    }
+
+    /// `verifier::batch::verify_blob_kzg_proof_batch` (verifier/src/batch.rs:16-255): the input checks and the final
+    /// pairing stay the reference's code; per-blob challenges and evaluations, the RLC scalar and the three linear
+    /// combinations (batch.rs:40-249) are one `kzgb_verify_batch_rlc` call.
+    pub fn verify_blob_kzg_proof_batch(blobs: &[Blob], commitments: &[G1Affine], proofs: &[G1Affine]) -> Result<bool, KzgError> {
+        use ark_bn254::G2Affine;
+        use rust_kzg_bn254_primitives::consts::G2_TAU;
+        if !(commitments.len() == blobs.len() && proofs.len() == blobs.len()) {
+            return Err(KzgError::GenericError("length's of the input are not the same".to_string()));
+        }
+        for c in commitments.iter() {
+            helpers::validate_g1_point(c)?;
+        }
+        for p in proofs.iter() {
+            helpers::validate_g1_point(p)?;
+        }
+        let ptrs: Vec<*const u8> = blobs.iter().map(|b| b.data().as_ptr()).collect();
+        let lens: Vec<usize> = blobs.iter().map(|b| b.data().len()).collect();
+        let (cxy, cinf) = pack_points(commitments);
+        let (pxy, pinf) = pack_points(proofs);
+        let (mut lhs, mut lhs_inf, mut rhs, mut rhs_inf) = ([0u64; 8], 0u8, [0u64; 8], 0u8);
+        let (proof_lincomb, rhs_g1) = with_default_ctx(|ctx| {
+            let rc = unsafe {
+                ffi::kzgb_verify_batch_rlc(ctx, ptrs.as_ptr(), lens.as_ptr(), blobs.len(), cxy.as_ptr(), cinf.as_ptr(), pxy.as_ptr(),
+                                           pinf.as_ptr(), lhs.as_mut_ptr(), &mut lhs_inf, rhs.as_mut_ptr(), &mut rhs_inf)
+            };
+            if rc != 0 { Err(to_err(ctx, rc, 0, 0)) } else { Ok((unpack_point(&lhs, lhs_inf), unpack_point(&rhs, rhs_inf))) }
+        })??;
+        // e(sum r^i proof_i, [tau]G2) == e(sum r^i (C_i - [y_i]) + sum r^i z_i proof_i, G2)   (batch.rs:253-254)
+        Ok(helpers::pairings_verify(proof_lincomb, G2_TAU, rhs_g1, G2Affine::generator()))
+    }
+}
