@@ -331,6 +331,28 @@ def main():
         "hbm_gather_GBps_isolated": adds_per_launch * 64 / (iso_acc.value * 1e-3) / 1e9 if iso_acc.value else None,
     }
 
+    # FP64-pipe probe (csrc/dfma.cu): is there multiply throughput beside the IMAD.WIDE pipe?  Measured
+    # live so the "ceiling stands" statement carries its own evidence; never allowed to break the bench line.
+    try:
+        dev = int(os.environ.get("LOCAL_RANK", "0"))
+        fp64 = {}
+        for key, kind, ii, idf in (("dfma_per_s", 0, 0, 1024), ("fqmul_int_per_s", 3, 256, 0), ("fqmul_dfma_per_s", 1, 0, 256),
+                                   ("fqmul_hybrid_int256_dfma128_per_s", 2, 256, 128)):
+            v = C.c_double(0)
+            rc = lib.kzgb_dfma_microbench(dev, kind, ii, idf, C.byref(v))
+            fp64[key] = v.value if rc == 0 else f"rc={rc}"
+        mix = {}
+        for name, m in (("wide_alone", 0), ("dfma_alone", 1), ("wide_and_dfma", 2)):
+            v = C.c_double(0)
+            rc = lib.kzgb_pipe_mix_probe(dev, m, 1024, C.byref(v))
+            mix[name] = v.value if rc == 0 else f"rc={rc}"
+        fp64["pipe_mix_ms"] = mix
+        fp64["note"] = ("IMAD.WIDE and DFMA warps on the same schedulers: wide_and_dfma ~ wide_alone + dfma_alone means one shared "
+                        "resource, so FP64 limb products cannot add to the integer-pipe ceiling")
+        roofline["fp64_pipe_probe"] = fp64
+    except Exception as e:  # noqa: BLE001
+        roofline["fp64_pipe_probe"] = {"error": repr(e)}
+
     cpu_baseline = None
     if world == 1 and not args.skip_cpu_baseline:
         olib = load_oracle_lib()
