@@ -317,6 +317,79 @@ __global__ void __maxnreg__(MAXR) k_accumulate_r(const uint32_t* __restrict__ so
     accumulate_body<false, false, false>(sorted, offsets, table, nb, acc_threads, chunk, shift, buckets, partial);
 }
 
+// ---- relaxed accumulation with the identity case peeled (experimental, opt-in: accumulate variant 28) --------------
+// In accumulate_body the "accumulator is still the identity" case of xyzz_madd_relaxed is if-converted by the compiler:
+// every iteration copies the accumulator and materialises (q.x, q.y, 1, 1) before the branch (~80 register moves per
+// addition in SASS).  Here the state "accumulator empty" is a flag, the first point of a run is installed by an
+// out-of-line path the compiler cannot speculate, and the addition itself never tests for the identity.
+__device__ __forceinline__ bool xyzz_madd_relaxed_nonempty(XYZZ& acc, const Affine& q) {  // false: the sum is the identity
+    Fq U2, S2, Pp, Rr, PP, PPP, Q, t;
+    fq_mulnr_ptx(U2.l, q.x.l, acc.zz.l);
+    fq_mulnr_ptx(S2.l, q.y.l, acc.zzz.l);
+    fq_sub2p_ptx(Pp.l, U2.l, acc.x.l);
+    fq_sub2p_ptx(Rr.l, S2.l, acc.y.l);
+    if (fq_is_zero_mod(Pp)) {
+        if (!fq_is_zero_mod(Rr)) return false;
+        xyzz_dbl_affine(acc, q);  // canonical result from the canonical q
+        return !xyzz_is_inf(acc);
+    }
+    fq_mulnr_ptx(PP.l, Pp.l, Pp.l);
+    fq_mulnr_ptx(PPP.l, Pp.l, PP.l);
+    fq_mulnr_ptx(Q.l, acc.x.l, PP.l);
+    fq_mulnr_ptx(acc.zz.l, acc.zz.l, PP.l);
+    fq_mulnr_ptx(acc.zzz.l, acc.zzz.l, PPP.l);
+    fq_mulnr_ptx(t.l, Rr.l, Rr.l);
+    fq_sub2p_ptx(t.l, t.l, PPP.l); fq_sub2p_ptx(t.l, t.l, Q.l); fq_sub2p_ptx(t.l, t.l, Q.l);  // X3
+    fq_sub2p_ptx(Q.l, Q.l, t.l);
+    fq_mul2subnr_ptx(acc.y.l, Rr.l, Q.l, acc.y.l, PPP.l);
+    acc.x = t;
+    return true;
+}
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_accumulate_relaxed2(const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ offsets,
+                                                                     const Affine* __restrict__ table, uint32_t nb, uint32_t acc_threads,
+                                                                     uint32_t chunk, XYZZ* __restrict__ buckets, XYZZ* __restrict__ partial) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= acc_threads) return;
+    const uint32_t M = offsets[nb];
+    uint64_t start64 = (uint64_t)t * chunk;
+    if (start64 >= M) return;
+    uint32_t start = (uint32_t)start64;
+    uint32_t end = (uint32_t)min((uint64_t)M, start64 + chunk);
+    uint32_t lo = 0, hi = nb;  // invariant: offsets[lo] <= start < offsets[hi]
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (offsets[mid] <= start) lo = mid; else hi = mid;
+    }
+    uint32_t b = lo;
+    uint32_t run_begin = offsets[b], next = offsets[b + 1];
+    XYZZ acc; xyzz_set_inf(acc);
+    bool nonempty = false;
+    auto flush = [&](XYZZ* dst) {
+        if (nonempty) xyzz_relaxed_normalise(acc); else xyzz_set_inf(acc);
+        xyzz_store(dst, acc);
+    };
+    for (uint32_t pos = start; pos < end; pos++) {
+        Affine q = load_point(table, sorted[pos]);
+        if (pos >= next) {
+            flush((run_begin >= start) ? &buckets[b] : &partial[2 * t]);
+            nonempty = false;
+            do { b++; } while (offsets[b + 1] <= pos);
+            run_begin = offsets[b]; next = offsets[b + 1];
+        }
+        if (aff_is_inf(q)) continue;
+        if (!nonempty) {
+            asm volatile("" ::: "memory");  // keep this path a real branch: nothing of it is worth speculating
+            acc.x = q.x; acc.y = q.y; fe_one(acc.zz); fe_one(acc.zzz);
+            nonempty = true;
+            continue;
+        }
+        nonempty = xyzz_madd_relaxed_nonempty(acc, q);
+    }
+    bool complete = (run_begin >= start) && (next <= end);
+    flush(complete ? &buckets[b] : (run_begin <= start) ? &partial[2 * t] : &partial[2 * t + 1]);
+}
+
 // ---- FP64-pipe accumulation (experimental, opt-in: accumulate variants 23-26) ----------------------------
 // The same fixed-size-chunk walk as accumulate_body with the accumulator held as 5 x 52-bit double limbs
 // (ec_dfma.cuh): the products run on the FP64 pipe (DFMA hi/lo halves) and the ALU instead of the IMAD.WIDE pipe
@@ -966,6 +1039,7 @@ void msm_launch(const MsmPlan& p, const MsmWorkspace& ws, const Fr* scalars, boo
                 case 25: k_accumulate_hybrid<2, 3><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, ws.buckets, ws.partial); break;
                 case 26: k_accumulate_hybrid<3, 3><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, ws.buckets, ws.partial); break;
                 case 27: k_accumulate_hybrid<2, 4><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, ws.buckets, ws.partial); break;
+                case 28: k_accumulate_relaxed2<4><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, ws.buckets, ws.partial); break;
                 case 16: k_accumulate_lazy<3><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, L, ws.buckets, ws.partial); break;
                 default: k_accumulate_relaxed<4><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, L, ws.buckets, ws.partial); break;
             }
