@@ -58,9 +58,7 @@ def test_generated_constants_are_current():
     spec = importlib.util.spec_from_file_location("gen_dfma", os.path.join(path, "gen_dfma.py"))
     gen = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(gen)
-    before = open(os.path.join(path, "field_dfma_consts.cuh")).read()
-    gen.main()
-    assert open(os.path.join(path, "field_dfma_consts.cuh")).read() == before
+    assert open(os.path.join(path, "field_dfma_consts.cuh")).read() == gen.render()  # (never rewritten: it is a build input)
 
 
 def test_montgomery_product(lib):
