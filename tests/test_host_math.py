@@ -49,6 +49,8 @@ def test_ptx_generator_emulator():
     # the committed generated header is what the generator produces now
     cur = open(os.path.join(ROOT, "rust-kzg-bn254_b200", "csrc", "field_gen.cuh")).read()
     assert cur == gen_field.emit_header()
+    curx = open(os.path.join(ROOT, "rust-kzg-bn254_b200", "csrc", "field_gen_x.cuh")).read()
+    assert curx == gen_field.emit_header_experimental()
 
 
 def test_relaxed_madd_sequence_on_the_emulator():

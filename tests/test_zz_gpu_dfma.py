@@ -64,10 +64,10 @@ VARIANT_SCRIPT = textwrap.dedent("""
 
 
 @pytest.mark.xfail(strict=False, reason="opt-in kernels; their first run through the whole MSM on hardware")
-@pytest.mark.parametrize("variant", [23, 25, 28])
+@pytest.mark.parametrize("variant", [23, 25, 28, 29])
 def test_fp64_accumulate_variants_match_the_oracle(variant):
     """The experimental accumulate kernels (23: every block, 25: half of the blocks on the FP64 pipe; 28: the integer kernel with
-    the identity case peeled out of the loop) behind the unchanged sort,
+    the identity case peeled out of the loop, 29: + dedicated squarings) behind the unchanged sort,
     bucket-fix and reduction: commitments must equal the oracle's MSM.  The variant is read once per process from
     KZGB_ACC_VARIANT, hence the subprocess."""
     env = dict(os.environ, KZGB_ACC_VARIANT=str(variant))
