@@ -53,8 +53,10 @@ def test_ptx_generator_emulator():
     assert curx == gen_field.emit_header_experimental()
 
 
-def test_relaxed_madd_sequence_on_the_emulator():
-    """The accumulation loop's XYZZ += affine on relaxed [0, 2p) coordinates (ec.cuh xyzz_madd_relaxed), replayed
+@pytest.mark.parametrize("squaring", [False, True])
+def test_relaxed_madd_sequence_on_the_emulator(squaring):
+    """squaring: PP and R^2 through the dedicated squaring of accumulate variant 29 (gen_field.py sqrnr).
+    The accumulation loop's XYZZ += affine on relaxed [0, 2p) coordinates (ec.cuh xyzz_madd_relaxed), replayed
     instruction by instruction on the PTX emulator: after every addition all coordinates stay below 2p and the
     accumulator equals the oracle's sum -- the carry chains and range invariants checked without a GPU."""
     sys.path.insert(0, os.path.join(ROOT, "rust-kzg-bn254_b200", "csrc"))
@@ -65,6 +67,7 @@ def test_relaxed_madd_sequence_on_the_emulator():
     mont = lambda v: v * MONT % P
     unmont = lambda v: v * pow(MONT, -1, P) % P
     mulnr = lambda a, b: gf.emulate("fq", "mulnr", a, b)
+    sqrnr = (lambda a: gf.emulate("fq", "sqrnr", a)) if squaring else (lambda a: mulnr(a, a))
     sub2p = lambda a, b: gf.emulate("fq", "sub2p", a, b)
     pts = g.srs_points_string()[3:12]
     # a P + (-P) pair and a doubling are handled by the exceptional paths in the kernel; here: distinct points
@@ -78,12 +81,12 @@ def test_relaxed_madd_sequence_on_the_emulator():
         Pp = sub2p(U2, acc[0])
         Rr = sub2p(S2, acc[1])
         assert Pp % P != 0
-        PP = mulnr(Pp, Pp)
+        PP = sqrnr(Pp)
         PPP = mulnr(Pp, PP)
         Q = mulnr(acc[0], PP)
         zz = mulnr(acc[2], PP)
         zzz = mulnr(acc[3], PPP)
-        t = mulnr(Rr, Rr)
+        t = sqrnr(Rr)
         t = sub2p(t, PPP)
         t = sub2p(t, Q)
         t = sub2p(t, Q)
