@@ -8,11 +8,11 @@ mkdir -p gpurun_out
 out=gpurun_out/r02_variant_sweep.txt
 : > $out
 echo "## parity (xfail-marked tests report XPASS when the variants are exact)" >> $out
-timeout 120 python scripts/variant_check.py 0 28 29 23 25 >> $out 2>&1
+timeout 120 python scripts/variant_check.py 0 28 29 30 23 25 >> $out 2>&1
 timeout 600 python -m pytest tests/test_zz_gpu_dfma.py -q -m gpu -rxX 2>&1 | tail -12 >> $out
 echo "## isolated 2^19 MSM: total and accumulate kernel (scripts/msm_sweep.py)" >> $out
 for w in 4 2 1; do
-  for v in 0 28 29 23 25; do
+  for v in 0 28 29 30 23 25; do
     echo "# waves=$w variant=$v" >> $out
     KZGB_ACC_WAVES=$w KZGB_ACC_VARIANT=$v timeout 120 python scripts/msm_sweep.py 19 2>&1 | tail -1 >> $out
   done
