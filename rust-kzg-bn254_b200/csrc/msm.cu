@@ -323,8 +323,9 @@ __global__ void __maxnreg__(MAXR) k_accumulate_r(const uint32_t* __restrict__ so
 // every iteration copies the accumulator and materialises (q.x, q.y, 1, 1) before the branch (~80 register moves per
 // addition in SASS).  Here the state "accumulator empty" is a flag, the first point of a run is installed by an
 // out-of-line path the compiler cannot speculate, and the addition itself never tests for the identity.
-// SQR: PP = P^2 and R^2 through the dedicated squaring (gen_field.py sqrnr: 36 instead of 64 wide multiplies in the product)
-template <bool SQR>
+// SQR (bit mask): 1 = PP = P^2, 2 = R^2 through the dedicated squaring (gen_field.py sqrnr: 36 instead of 64 wide multiplies
+// in the product)
+template <int SQR>
 __device__ __forceinline__ bool xyzz_madd_relaxed_nonempty(XYZZ& acc, const Affine& q) {  // false: the sum is the identity
     Fq U2, S2, Pp, Rr, PP, PPP, Q, t;
     fq_mulnr_ptx(U2.l, q.x.l, acc.zz.l);
@@ -336,19 +337,19 @@ __device__ __forceinline__ bool xyzz_madd_relaxed_nonempty(XYZZ& acc, const Affi
         xyzz_dbl_affine(acc, q);  // canonical result from the canonical q
         return !xyzz_is_inf(acc);
     }
-    if (SQR) fq_sqrnr_ptx(PP.l, Pp.l); else fq_mulnr_ptx(PP.l, Pp.l, Pp.l);
+    if (SQR & 1) fq_sqrnr_ptx(PP.l, Pp.l); else fq_mulnr_ptx(PP.l, Pp.l, Pp.l);
     fq_mulnr_ptx(PPP.l, Pp.l, PP.l);
     fq_mulnr_ptx(Q.l, acc.x.l, PP.l);
     fq_mulnr_ptx(acc.zz.l, acc.zz.l, PP.l);
     fq_mulnr_ptx(acc.zzz.l, acc.zzz.l, PPP.l);
-    if (SQR) fq_sqrnr_ptx(t.l, Rr.l); else fq_mulnr_ptx(t.l, Rr.l, Rr.l);
+    if (SQR & 2) fq_sqrnr_ptx(t.l, Rr.l); else fq_mulnr_ptx(t.l, Rr.l, Rr.l);
     fq_sub2p_ptx(t.l, t.l, PPP.l); fq_sub2p_ptx(t.l, t.l, Q.l); fq_sub2p_ptx(t.l, t.l, Q.l);  // X3
     fq_sub2p_ptx(Q.l, Q.l, t.l);
     fq_mul2subnr_ptx(acc.y.l, Rr.l, Q.l, acc.y.l, PPP.l);
     acc.x = t;
     return true;
 }
-template <int MINB, bool SQR>
+template <int MINB, int SQR>
 __global__ void __launch_bounds__(128, MINB) k_accumulate_relaxed2(const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ offsets,
                                                                      const Affine* __restrict__ table, uint32_t nb, uint32_t acc_threads,
                                                                      uint32_t chunk, XYZZ* __restrict__ buckets, XYZZ* __restrict__ partial) {
@@ -1042,9 +1043,11 @@ void msm_launch(const MsmPlan& p, const MsmWorkspace& ws, const Fr* scalars, boo
                 case 25: k_accumulate_hybrid<2, 3><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, ws.buckets, ws.partial); break;
                 case 26: k_accumulate_hybrid<3, 3><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, ws.buckets, ws.partial); break;
                 case 27: k_accumulate_hybrid<2, 4><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, ws.buckets, ws.partial); break;
-                case 28: k_accumulate_relaxed2<4, false><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, ws.buckets, ws.partial); break;
-                case 29: k_accumulate_relaxed2<4, true><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, ws.buckets, ws.partial); break;
-                case 30: k_accumulate_relaxed2<3, true><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, ws.buckets, ws.partial); break;
+                case 28: k_accumulate_relaxed2<4, 0><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, ws.buckets, ws.partial); break;
+                case 29: k_accumulate_relaxed2<4, 3><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, ws.buckets, ws.partial); break;
+                case 30: k_accumulate_relaxed2<3, 3><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, ws.buckets, ws.partial); break;
+                case 31: k_accumulate_relaxed2<4, 1><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, ws.buckets, ws.partial); break;
+                case 32: k_accumulate_relaxed2<4, 2><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, ws.buckets, ws.partial); break;
                 case 16: k_accumulate_lazy<3><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, L, ws.buckets, ws.partial); break;
                 default: k_accumulate_relaxed<4><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, L, ws.buckets, ws.partial); break;
             }

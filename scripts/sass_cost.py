@@ -9,6 +9,7 @@ Address ranges (hex, half-open) select the hot path by hand from the kernel's br
 without its bucket-flush block and without the exceptional (P == Q) path.  Prints the census and the modelled cycles.
 """
 import re
+import signal
 import subprocess
 import sys
 from collections import Counter
@@ -45,4 +46,5 @@ def main():
 
 
 if __name__ == "__main__":
+    signal.signal(signal.SIGPIPE, signal.SIG_DFL)  # "| head" is a normal way to use this
     main()

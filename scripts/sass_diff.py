@@ -8,6 +8,7 @@ Used before shipping a library whose GPU tests cannot be re-run: a change that o
 every existing kernel byte-identical.
 """
 import re
+import signal
 import subprocess
 import sys
 
@@ -43,4 +44,5 @@ def main():
 
 
 if __name__ == "__main__":
+    signal.signal(signal.SIGPIPE, signal.SIG_DFL)  # "| head" is a normal way to use this
     main()
