@@ -324,14 +324,15 @@ __global__ void __maxnreg__(MAXR) k_accumulate_r(const uint32_t* __restrict__ so
 // addition in SASS).  Here the state "accumulator empty" is a flag, the first point of a run is installed by an
 // out-of-line path the compiler cannot speculate, and the addition itself never tests for the identity.
 // SQR (bit mask): 1 = PP = P^2, 2 = R^2 through the dedicated squaring (gen_field.py sqrnr: 36 instead of 64 wide multiplies
-// in the product)
+// in the product); 4 = a - b (+ 2p) with predicated additions instead of a masked 2p (sub2pp: 18 instead of 25 instructions)
 template <int SQR>
 __device__ __forceinline__ bool xyzz_madd_relaxed_nonempty(XYZZ& acc, const Affine& q) {  // false: the sum is the identity
     Fq U2, S2, Pp, Rr, PP, PPP, Q, t;
+#define SUB2P(r, a, b) do { if (SQR & 4) fq_sub2pp_ptx(r, a, b); else fq_sub2p_ptx(r, a, b); } while (0)
     fq_mulnr_ptx(U2.l, q.x.l, acc.zz.l);
     fq_mulnr_ptx(S2.l, q.y.l, acc.zzz.l);
-    fq_sub2p_ptx(Pp.l, U2.l, acc.x.l);
-    fq_sub2p_ptx(Rr.l, S2.l, acc.y.l);
+    SUB2P(Pp.l, U2.l, acc.x.l);
+    SUB2P(Rr.l, S2.l, acc.y.l);
     if (fq_is_zero_mod(Pp)) {
         if (!fq_is_zero_mod(Rr)) return false;
         xyzz_dbl_affine(acc, q);  // canonical result from the canonical q
@@ -343,11 +344,12 @@ __device__ __forceinline__ bool xyzz_madd_relaxed_nonempty(XYZZ& acc, const Affi
     fq_mulnr_ptx(acc.zz.l, acc.zz.l, PP.l);
     fq_mulnr_ptx(acc.zzz.l, acc.zzz.l, PPP.l);
     if (SQR & 2) fq_sqrnr_ptx(t.l, Rr.l); else fq_mulnr_ptx(t.l, Rr.l, Rr.l);
-    fq_sub2p_ptx(t.l, t.l, PPP.l); fq_sub2p_ptx(t.l, t.l, Q.l); fq_sub2p_ptx(t.l, t.l, Q.l);  // X3
-    fq_sub2p_ptx(Q.l, Q.l, t.l);
+    SUB2P(t.l, t.l, PPP.l); SUB2P(t.l, t.l, Q.l); SUB2P(t.l, t.l, Q.l);  // X3
+    SUB2P(Q.l, Q.l, t.l);
     fq_mul2subnr_ptx(acc.y.l, Rr.l, Q.l, acc.y.l, PPP.l);
     acc.x = t;
     return true;
+#undef SUB2P
 }
 template <int MINB, int SQR>
 __global__ void __launch_bounds__(128, MINB) k_accumulate_relaxed2(const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ offsets,
@@ -1048,6 +1050,8 @@ void msm_launch(const MsmPlan& p, const MsmWorkspace& ws, const Fr* scalars, boo
                 case 30: k_accumulate_relaxed2<3, 3><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, ws.buckets, ws.partial); break;
                 case 31: k_accumulate_relaxed2<4, 1><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, ws.buckets, ws.partial); break;
                 case 32: k_accumulate_relaxed2<4, 2><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, ws.buckets, ws.partial); break;
+                case 33: k_accumulate_relaxed2<4, 5><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, ws.buckets, ws.partial); break;
+                case 34: k_accumulate_relaxed2<4, 4><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, ws.buckets, ws.partial); break;
                 case 16: k_accumulate_lazy<3><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, L, ws.buckets, ws.partial); break;
                 default: k_accumulate_relaxed<4><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, L, ws.buckets, ws.partial); break;
             }
