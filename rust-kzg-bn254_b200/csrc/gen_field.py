@@ -624,6 +624,29 @@ def gen_sub2p_pred(field: str) -> Prog:
     return pr
 
 
+def gen_cneg(field: str) -> Prog:
+    """r = flag ? p - a : a for a in (0, p]: the conditional negation of a table point's y as 8 PREDICATED subtractions
+    (the sign of a signed digit differs lane by lane, so a branch would run both sides anyway).  a = 0 is excluded by the
+    caller (the identity is filtered out before); the result lies in [0, p).  Inputs: a0..a7, b0 = flag."""
+    mod = FIELDS[field]
+    pl = limbs(mod)
+    a = [f"a{i}" for i in range(8)]
+    r = [f"r{i}" for i in range(8)]
+    pr = Prog(f"{field}_cneg", a + ["b0"], r)
+    t = [pr.tmp(f"t{i}") for i in range(8)]
+    neg = pr.pred("neg")
+    for i in range(8):
+        pr.op("mov.u32", t[i], a[i])
+    pr.op("setp.ne.u32", neg, "b0", 0)
+    pr.op(f"@{neg} sub.cc.u32", t[0], pl[0], t[0])
+    for i in range(1, 7):
+        pr.op(f"@{neg} subc.cc.u32", t[i], pl[i], t[i])
+    pr.op(f"@{neg} subc.u32", t[7], pl[7], t[7])
+    for i in range(8):
+        pr.op("mov.u32", r[i], t[i])
+    return pr
+
+
 def gen_reduce_once(field: str) -> Prog:
     """r = a - p if a >= p else a  (for a < 2p)."""
     mod = FIELDS[field]
@@ -646,6 +669,7 @@ ROUTINES = {
     "sub2p": gen_sub2p,
     "sqrnr": gen_sqrnr,
     "sub2pp": gen_sub2p_pred,
+    "cneg": gen_cneg,
     "add": gen_add,
     "sub": gen_sub,
     "reduce_once": gen_reduce_once,
@@ -725,6 +749,9 @@ def emit_header_experimental() -> str:
     pr = ROUTINES["sub2pp"]("fq")
     out.append(pr.emit("fq_sub2pp_ptx(uint32_t* r, const uint32_t* a, const uint32_t* b)", [f"r[{i}]" for i in range(8)],
                        [f"a[{i}]" for i in range(8)] + [f"b[{i}]" for i in range(8)]))
+    pr = ROUTINES["cneg"]("fq")
+    out.append(pr.emit("fq_cneg_ptx(uint32_t* r, const uint32_t* a, uint32_t flag)", [f"r[{i}]" for i in range(8)],
+                       [f"a[{i}]" for i in range(8)] + ["flag"]))
     out.append("#endif  // __CUDACC__")
     return "\n".join(out) + "\n"
 
@@ -773,6 +800,8 @@ def selftest(iters: int = 300) -> None:
             for y in ((1 << 256) - 1, (1 << 256) - 2, 1 << 255, mod, 2 * mod, 5 * mod + 7):
                 assert emulate(field, "mul", x, y) == x * y * rinv % mod, (field, "mulwide", x, y)
                 assert emulate(field, "mulk", x, y) == x * y * rinv % mod, (field, "mulkwide", x, y)
+        for x in [1, 2, mod - 1, mod, (mod - 1) // 2, (1 << 32) - 1, 1 << 32, 1 << 224] + [rnd.randrange(1, mod) for _ in range(iters)]:
+            assert emulate(field, "cneg", x, 0) == x and emulate(field, "cneg", x, 1) == mod - x and emulate(field, "cneg", x, 1 << 31) == mod - x
         for x in edge + [rnd.randrange(2 * mod) for _ in range(iters)] + [mod, mod + 1, 2 * mod - 1]:
             assert emulate(field, "reduce_once", x) == x % mod
     print("gen_field selftest OK")

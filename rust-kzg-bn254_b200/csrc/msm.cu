@@ -324,7 +324,8 @@ __global__ void __maxnreg__(MAXR) k_accumulate_r(const uint32_t* __restrict__ so
 // addition in SASS).  Here the state "accumulator empty" is a flag, the first point of a run is installed by an
 // out-of-line path the compiler cannot speculate, and the addition itself never tests for the identity.
 // SQR (bit mask): 1 = PP = P^2, 2 = R^2 through the dedicated squaring (gen_field.py sqrnr: 36 instead of 64 wide multiplies
-// in the product); 4 = a - b (+ 2p) with predicated additions instead of a masked 2p (sub2pp: 18 instead of 25 instructions)
+// in the product); 4 = a - b (+ 2p) with predicated additions instead of a masked 2p (sub2pp: 18 instead of 25 instructions);
+// 8 = the loop head without a materialised zero point and with the digit's sign applied by predicated subtractions
 template <int SQR>
 __device__ __forceinline__ bool xyzz_madd_relaxed_nonempty(XYZZ& acc, const Affine& q) {  // false: the sum is the identity
     Fq U2, S2, Pp, Rr, PP, PPP, Q, t;
@@ -375,15 +376,31 @@ __global__ void __launch_bounds__(128, MINB) k_accumulate_relaxed2(const uint32_
         if (nonempty) xyzz_relaxed_normalise(acc); else xyzz_set_inf(acc);
         xyzz_store(dst, acc);
     };
+    auto boundary = [&](uint32_t pos) {  // entry `pos` opens a new bucket run: store the finished one
+        flush((run_begin >= start) ? &buckets[b] : &partial[2 * t]);
+        nonempty = false;
+        do { b++; } while (offsets[b + 1] <= pos);
+        run_begin = offsets[b]; next = offsets[b + 1];
+    };
     for (uint32_t pos = start; pos < end; pos++) {
-        Affine q = load_point(table, sorted[pos]);
-        if (pos >= next) {
-            flush((run_begin >= start) ? &buckets[b] : &partial[2 * t]);
-            nonempty = false;
-            do { b++; } while (offsets[b + 1] <= pos);
-            run_begin = offsets[b]; next = offsets[b + 1];
+        Affine q;
+        if (SQR & 8) {
+            // the padding slot never materialises a zero point, and the sign of the digit is applied by predicated
+            // subtractions (fq_cneg_ptx) instead of a divergent branch around a masked negation
+            uint32_t ref = sorted[pos];
+            if (ref == REF_IDENT) {
+                if (pos >= next) boundary(pos);
+                continue;
+            }
+            q = aff_gather_ro(&table[ref & 0x7fffffffu]);
+            if (pos >= next) boundary(pos);
+            if (aff_is_inf(q)) continue;
+            fq_cneg_ptx(q.y.l, q.y.l, ref & 0x80000000u);
+        } else {
+            q = load_point(table, sorted[pos]);
+            if (pos >= next) boundary(pos);
+            if (aff_is_inf(q)) continue;
         }
-        if (aff_is_inf(q)) continue;
         if (!nonempty) {
             asm volatile("" ::: "memory");  // keep this path a real branch: nothing of it is worth speculating
             acc.x = q.x; acc.y = q.y; fe_one(acc.zz); fe_one(acc.zzz);
@@ -1052,6 +1069,7 @@ void msm_launch(const MsmPlan& p, const MsmWorkspace& ws, const Fr* scalars, boo
                 case 32: k_accumulate_relaxed2<4, 2><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, ws.buckets, ws.partial); break;
                 case 33: k_accumulate_relaxed2<4, 5><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, ws.buckets, ws.partial); break;
                 case 34: k_accumulate_relaxed2<4, 4><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, ws.buckets, ws.partial); break;
+                case 35: k_accumulate_relaxed2<4, 13><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, ws.buckets, ws.partial); break;
                 case 16: k_accumulate_lazy<3><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, L, ws.buckets, ws.partial); break;
                 default: k_accumulate_relaxed<4><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, L, ws.buckets, ws.partial); break;
             }

@@ -8,17 +8,17 @@ mkdir -p gpurun_out
 out=gpurun_out/r02_variant_sweep.txt
 : > $out
 echo "## parity (xfail-marked tests report XPASS when the variants are exact)" >> $out
-timeout 120 python scripts/variant_check.py 0 28 34 31 33 32 29 30 23 25 >> $out 2>&1
+timeout 120 python scripts/variant_check.py 0 28 34 31 33 35 32 29 30 23 25 >> $out 2>&1
 timeout 600 python -m pytest tests/test_zz_gpu_dfma.py -q -m gpu -rxX 2>&1 | tail -12 >> $out
 echo "## isolated 2^19 MSM: total and accumulate kernel (scripts/msm_sweep.py)" >> $out
 for w in 4 2 1; do
-  for v in 0 28 34 31 33 29 30 23 25; do
+  for v in 0 28 34 31 33 35 29 30 23 25; do
     echo "# waves=$w variant=$v" >> $out
     KZGB_ACC_WAVES=$w KZGB_ACC_VARIANT=$v timeout 120 python scripts/msm_sweep.py 19 2>&1 | tail -1 >> $out
   done
 done
 echo "## headline pipeline (bench.py --skip-cpu-baseline): blobs/s resident, e2e" >> $out
-for cfg in "4 0" "4 28" "4 31" "4 33" "4 29" "2 0" "2 28" "1 0" "1 28" "1 33"; do
+for cfg in "4 0" "4 28" "4 31" "4 33" "4 35" "4 29" "2 0" "2 28" "1 0" "1 28" "1 35"; do
   set -- $cfg
   echo "# waves=$1 variant=$2" >> $out
   KZGB_ACC_WAVES=$1 KZGB_ACC_VARIANT=$2 timeout 200 python bench.py --skip-cpu-baseline --steps 8 --warmup 3 2>/dev/null \

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Accumulate-kernel variants through the whole MSM, fast (ctypes only, a few seconds per variant):
-    python scripts/variant_check.py [variant ...]          (default: 0 28 34 31 33 32 29 30 23 25)
+    python scripts/variant_check.py [variant ...]          (default: 0 28 34 31 33 35 32 29 30 23 25)
 Each variant runs in its own process (KZGB_ACC_VARIANT is read once per process): synthetic SRS tau^i G of 2^16 points,
 commit_coeff of pseudo-random scalars compared with the closed form (sum s_i tau^i) G from the CPU oracle, an
 all-equal-scalars vector (hot buckets spanning many chunks), then kzgb_bench_msm (total / accumulate milliseconds).
@@ -50,7 +50,7 @@ def child():
 def main():
     if os.environ.get("KZGB_VARIANT_CHILD"):
         return child()
-    variants = sys.argv[1:] or ["0", "28", "34", "31", "33", "32", "29", "30", "23", "25"]
+    variants = sys.argv[1:] or ["0", "28", "34", "31", "33", "35", "32", "29", "30", "23", "25"]
     for v in variants:
         env = dict(os.environ, KZGB_ACC_VARIANT=v, KZGB_VARIANT_CHILD="1")
         r = subprocess.run([sys.executable, os.path.abspath(__file__)], env=env, capture_output=True, text=True, timeout=120)

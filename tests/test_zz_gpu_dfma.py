@@ -64,7 +64,7 @@ VARIANT_SCRIPT = textwrap.dedent("""
 
 
 @pytest.mark.xfail(strict=False, reason="opt-in kernels; their first run through the whole MSM on hardware")
-@pytest.mark.parametrize("variant", [23, 25, 28, 29, 31, 33])
+@pytest.mark.parametrize("variant", [23, 25, 28, 29, 31, 33, 35])
 def test_fp64_accumulate_variants_match_the_oracle(variant):
     """The experimental accumulate kernels (23: every block, 25: half of the blocks on the FP64 pipe; 28: the integer kernel with
     the identity case peeled out of the loop, 29: + dedicated squarings) behind the unchanged sort,
