@@ -1,9 +1,10 @@
 #!/bin/bash
 # First GPU call of the next round: parity of the opt-in accumulate variants through the whole MSM, then what they are worth.
-#   23 = every block on the FP64 pipe, 25 = half of the blocks, 28 = integer kernel with the identity case peeled
+#   23 = every block on the FP64 pipe, 25 = half of the blocks, 28 = integer kernel with the identity case peeled,
+#   34 = 28 + predicated subtractions, 31 = 28 + PP squaring, 33 = both, 35 = 33 + lean loop head (modelled -4.2 %), 29/30 = both squarings
 #   (modelled -1.5 %, profiles/r01_accumulate_sass_census.txt); KZGB_ACC_WAVES 1/2/4 = accumulate threads (fewer waves =
 #   fewer chunk partials for k_bucket_fix to stitch: 303 k x 14 Fq-mul at 4 waves, a quarter of that at 1).
-# Usage (about 6 GPU-minutes):  gpurun --timeout 900 -- 'bash scripts/r02_variant_sweep.sh'
+# Usage (about 10 GPU-minutes):  gpurun --timeout 900 -- 'bash scripts/r02_variant_sweep.sh'
 mkdir -p gpurun_out
 out=gpurun_out/r02_variant_sweep.txt
 : > $out
