@@ -233,7 +233,8 @@ int kzgb_set_option(const char* name, long value);
  * kind 0: independent DFMA chains (DFMA/s); 1: the DFMA Fq multiplication on every warp (Fq-mul/s);
  * 2: hybrid -- in every block the warps of half of each scheduler run the integer multiplication (iters_int x 4
  * per thread), the others the DFMA one (iters_dfma x 4): total Fq-mul/s; 3: integer multiplication in the same harness.
- * The accumulate kernels built on it are selected with KZGB_ACC_VARIANT=23..27 (msm.cu), default off. */
+ * The accumulate kernels built on it are selected with KZGB_ACC_VARIANT=23..27 (msm.cu), default off; 28..35 select the
+ * integer-kernel variants with fewer non-multiply instructions, also default off until timed. */
 int kzgb_dfma_microbench(int device, int kind, int iters_int, int iters_dfma, double* ops_per_second);
 /* Do DFMA and IMAD.WIDE share an execution pipe?  In every 256-thread block the two warp halves of each scheduler
  * run (mix) 0: IMAD.WIDE | idle, 1: DFMA | idle, 2: IMAD.WIDE | DFMA, 3: IMAD.WIDE | IMAD.WIDE, 4: DFMA | DFMA,
