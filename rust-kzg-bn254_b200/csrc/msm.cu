@@ -1062,6 +1062,10 @@ void msm_launch(const MsmPlan& p, const MsmWorkspace& ws, const Fr* scalars, boo
                 case 25: k_accumulate_hybrid<2, 3><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, ws.buckets, ws.partial); break;
                 case 26: k_accumulate_hybrid<3, 3><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, ws.buckets, ws.partial); break;
                 case 27: k_accumulate_hybrid<2, 4><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, ws.buckets, ws.partial); break;
+                // k_accumulate_relaxed2<blocks/SM, mask>: the production arithmetic with fewer non-multiply instructions (opt-in until
+                // timed; modelled cycles per addition in profiles/r01_accumulate_sass_census.txt, production 5560): 28 = identity case
+                // peeled (5489), 34 = + predicated subtractions (5453), 31 = + PP squaring (5417), 32 = + R^2 squaring (5472),
+                // 29 = + both squarings (5402), 30 = 29 at 3 blocks/SM (5317), 33 = 31 + 34 (5358), 35 = 33 + lean loop head (5327)
                 case 28: k_accumulate_relaxed2<4, 0><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, ws.buckets, ws.partial); break;
                 case 29: k_accumulate_relaxed2<4, 3><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, ws.buckets, ws.partial); break;
                 case 30: k_accumulate_relaxed2<3, 3><<<g, 128, 0, sa>>>(ws.sorted, ws.hist, tail_src, p.nbuckets, p.acc_threads, p.chunk, ws.buckets, ws.partial); break;
