@@ -148,6 +148,8 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--blobs-per-step", type=int, default=16)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--window-bits", type=int, default=0, help="fixed-base window bits c (0 = the library's choice)")
+    ap.add_argument("--option", action="append", default=[], metavar="NAME=VALUE", help="kzgb_set_option before the run (sweeps)")
     ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4", "c5"],
                     help="c2 (default, headline): 16 MiB blobs; c3: 1024 x 2^16-Fr blobs sharded by blob; "
                          "c4: 2^26-point MSM sharded by point range; c5: batch-verify RLC over 4096 pairs")
@@ -179,6 +181,10 @@ def main():
 
     pkg = load_package()
     lib = pkg.lib
+    for kv in args.option:
+        name, _, val = kv.partition("=")
+        if lib.kzgb_set_option(name.encode(), int(val)) != 0:
+            raise SystemExit(f"unknown option {name}")
     eng = pkg.Engine(local_rank)
     n = 1 << LOG_N
     B = args.blobs_per_step
@@ -186,7 +192,7 @@ def main():
     # synthetic SRS tau^i G generated on the GPU + fixed-base window tables (one-time setup)
     t_setup = time.perf_counter()
     srs = pkg.SRS.synthetic(n, TAU, engine=eng)
-    srs.precompute(n, int(os.environ.get("KZGB_WINDOW_BITS", "0")))
+    srs.precompute(n, args.window_bits)
     setup_s = time.perf_counter() - t_setup
     cbits, cwin, ctab = C.c_int(0), C.c_int(0), C.c_size_t(0)
     lib.kzgb_msm_config(eng.h, C.byref(cbits), C.byref(cwin), C.byref(ctab))
@@ -317,7 +323,7 @@ def main():
         "single_2p19_butterfly_fr_mul_per_s": (1 << LOG_N) * LOG_N / 2.0 / (ntt1_ms.value * 1e-3),
     }
     roofline = {
-        "kernel": "k_accumulate_relaxed (MSM bucket accumulation, XYZZ += affine)", "bound": "integer-pipe (IMAD)",
+        "kernel": "k_accumulate (MSM bucket accumulation, XYZZ += affine)", "bound": "integer-pipe (IMAD)",
         "achieved": achieved_iso, "peak": peak, "unit": "GFqmul/s", "frac": achieved_iso / peak if peak else None,
         "traffic": traffic,
         "achieved_in_pipeline": achieved, "frac_in_pipeline": achieved / peak if peak else None,
@@ -330,28 +336,6 @@ def main():
         "imad_per_s": imad.value, "imad_wide_per_s": imadw.value, "carry_chain_imad_wide_per_s": imadx.value, "fqmul_microbench_per_s": fqpeak.value,
         "hbm_gather_GBps_isolated": adds_per_launch * 64 / (iso_acc.value * 1e-3) / 1e9 if iso_acc.value else None,
     }
-
-    # FP64-pipe probe (csrc/dfma.cu): is there multiply throughput beside the IMAD.WIDE pipe?  Measured
-    # live so the "ceiling stands" statement carries its own evidence; never allowed to break the bench line.
-    try:
-        dev = int(os.environ.get("LOCAL_RANK", "0"))
-        fp64 = {}
-        for key, kind, ii, idf in (("dfma_per_s", 0, 0, 1024), ("fqmul_int_per_s", 3, 256, 0), ("fqmul_dfma_per_s", 1, 0, 256),
-                                   ("fqmul_hybrid_int256_dfma128_per_s", 2, 256, 128)):
-            v = C.c_double(0)
-            rc = lib.kzgb_dfma_microbench(dev, kind, ii, idf, C.byref(v))
-            fp64[key] = v.value if rc == 0 else f"rc={rc}"
-        mix = {}
-        for name, m in (("wide_alone", 0), ("dfma_alone", 1), ("wide_and_dfma", 2)):
-            v = C.c_double(0)
-            rc = lib.kzgb_pipe_mix_probe(dev, m, 1024, C.byref(v))
-            mix[name] = v.value if rc == 0 else f"rc={rc}"
-        fp64["pipe_mix_ms"] = mix
-        fp64["note"] = ("IMAD.WIDE and DFMA warps on the same schedulers: wide_and_dfma ~ wide_alone + dfma_alone means one shared "
-                        "resource, so FP64 limb products cannot add to the integer-pipe ceiling")
-        roofline["fp64_pipe_probe"] = fp64
-    except Exception as e:  # noqa: BLE001
-        roofline["fp64_pipe_probe"] = {"error": repr(e)}
 
     cpu_baseline = None
     if world == 1 and not args.skip_cpu_baseline:

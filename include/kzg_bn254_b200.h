@@ -203,17 +203,11 @@ int kzgb_timer_end(kzgb_ctx* ctx, double* ms_out);
 /* Bucket-accumulation kernel statistics since the last reset: summed CUDA-event duration of the
  * launches (each bracketed on its own stream), launch count, and point additions performed. */
 int kzgb_stats(kzgb_ctx* ctx, double* acc_ms, uint64_t* acc_launches, uint64_t* acc_point_adds, int reset);
-/* Bucket-accumulation tuning (process-wide): number of batch-affine levels in front of the XYZZ
- * accumulation (default 0 = off: measured slower than XYZZ
- * accumulation on B200), the minimum average bucket occupancy at which they are used
- * (default 64), pairs per thread at level 0 (0 = default: sized so every level is one full wave of
- * the GPU).  Negative values keep the current setting.
- * Results never depend on it (exact group arithmetic); tests use it to force every code path. */
-int kzgb_msm_tuning(int batch_affine_levels, int min_avg_bucket, int pairs_per_thread);
 /* Process-wide switches that never change results, only which exact code path produces them:
  *   "fs_device"            -1 auto (default), 0 host SHA-256 pool, 1 device kernel for the per-blob
  *                          Fiat-Shamir challenges of kzgb_verify_batch_rlc (auto: >= 256 blobs of <= 2^13 Fr)
- *   "batch_affine_levels"  as in kzgb_msm_tuning
+ *   "acc_waves"            waves of bucket-accumulation blocks the sorted list is cut into (default 4; any value >= 1
+ *                          gives the same result -- tests use it to move the chunk boundaries)
  *   "fs_force_generic"     1: the device-hashed challenges of kzgb_verify_batch_rlc are all flagged "in the domain", so the
  *                          per-polynomial choice made on the device takes the generic inverses everywhere (tests)
  *   "eval_structured"      1 (default): for z outside the domain the barycentric denominators 1/(z - w_i) come from
@@ -226,24 +220,6 @@ int kzgb_msm_tuning(int batch_affine_levels, int min_avg_bucket, int pairs_per_t
  *                          table of their size (kzgb_srs_prepare_lagrange); 0: Fr-IFFT + monomial table
  * Unknown names return KZGB_ERR_GENERIC. */
 int kzgb_set_option(const char* name, long value);
-/* ---- FP64-pipe experiments (csrc/dfma.cu, csrc/field_dfma.cuh; not on the product path) -------------- *
- * Fq on 5 x 52-bit double limbs: limb products are DFMA hi/lo pairs, so multiplications run on the FP64 and ALU
- * pipes instead of the IMAD.WIDE pipe that bounds the bucket accumulation.  Both calls are context-free: they
- * select `device`, allocate, run, free.
- * kind 0: independent DFMA chains (DFMA/s); 1: the DFMA Fq multiplication on every warp (Fq-mul/s);
- * 2: hybrid -- in every block the warps of half of each scheduler run the integer multiplication (iters_int x 4
- * per thread), the others the DFMA one (iters_dfma x 4): total Fq-mul/s; 3: integer multiplication in the same harness.
- * The accumulate kernels built on it are selected with KZGB_ACC_VARIANT=23..27 (msm.cu), default off; 28..35 select the
- * integer-kernel variants with fewer non-multiply instructions, also default off until timed. */
-int kzgb_dfma_microbench(int device, int kind, int iters_int, int iters_dfma, double* ops_per_second);
-/* Do DFMA and IMAD.WIDE share an execution pipe?  In every 256-thread block the two warp halves of each scheduler
- * run (mix) 0: IMAD.WIDE | idle, 1: DFMA | idle, 2: IMAD.WIDE | DFMA, 3: IMAD.WIDE | IMAD.WIDE, 4: DFMA | DFMA,
- * 5: DADD | idle, 6: DADD | DFMA, 7: DADD | IMAD.WIDE, iters x 128 operations per active thread; returns the
- * kernel's milliseconds.  Independent pipes: t(2) = max(t(0), t(1)); one pipe: t(2) = t(0) + t(1). */
-int kzgb_pipe_mix_probe(int device, int mix, int iters, double* ms_out);
-/* n threads each check a*b both ways and an XYZZ += affine chain of `chain` points (with a doubling, a
- * cancellation and negated points) both ways on the device; *mismatches = threads that disagreed (0 expected). */
-int kzgb_dfma_selftest(int device, uint32_t n, uint32_t chain, uint32_t* mismatches);
 /* Fixed-base table in use: window bits c, windows W, points covered (0 = none). */
 int kzgb_msm_config(const kzgb_ctx* ctx, int* window_bits, int* windows, size_t* table_points);
 

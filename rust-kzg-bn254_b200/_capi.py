@@ -83,10 +83,6 @@ SIGNATURES = {
     "kzgb_timer_end": (C.c_int, [ctx_p, C.POINTER(C.c_double)]),
     "kzgb_stats": (C.c_int, [ctx_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_int]),
     "kzgb_set_option": (C.c_int, [C.c_char_p, C.c_long]),
-    "kzgb_msm_tuning": (C.c_int, [C.c_int, C.c_int, C.c_int]),
-    "kzgb_dfma_microbench": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
-    "kzgb_pipe_mix_probe": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
-    "kzgb_dfma_selftest": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]),
     "kzgb_msm_config": (C.c_int, [ctx_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
 }
 

@@ -56,7 +56,6 @@ struct Lane {
     Fr* h_fr = nullptr;       // pinned, 16 elements
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_done = nullptr;
     bool ev_pending = false;
-    bool throughput = false;  // driven by a batch pipeline: plans trade MSM latency for less work
     double acc_ms = 0;        // summed duration of bucket-accumulation kernels
     uint64_t acc_launches = 0;
     uint64_t acc_adds = 0;    // point additions those kernels performed (n * W upper bound)
@@ -389,7 +388,7 @@ int msm_enqueue(kzgb_ctx* c, Lane& L, const Fr* d_scalars, bool canonical, size_
     MsmPlan p;
     const Affine* table;
     if (lag) {
-        p = msm_make_plan((uint32_t)n, lag->c, true, (uint32_t)lag->n, 0, 0, L.throughput);
+        p = msm_make_plan((uint32_t)n, lag->c, true, (uint32_t)lag->n, 0);
         table = lag->table;
     } else if (!var_bases) {
         if (first + n > c->srs_n) return fail(c, KZGB_ERR_GENERIC, "MSM range exceeds the SRS");
@@ -399,7 +398,7 @@ int msm_enqueue(kzgb_ctx* c, Lane& L, const Fr* d_scalars, bool canonical, size_
             if (rc && rc != KZGB_ERR_DEVICE) return rc;
         }
         if (c->wtable && first + n <= c->wt_n) {
-            p = msm_make_plan((uint32_t)n, c->wt_c, true, (uint32_t)c->wt_n, (uint32_t)first, 0, L.throughput);
+            p = msm_make_plan((uint32_t)n, c->wt_c, true, (uint32_t)c->wt_n, (uint32_t)first);
             table = c->wtable;
         } else {
             p = msm_make_plan((uint32_t)n, choose_c_var(n), false, 0, 0);
@@ -477,11 +476,11 @@ int msm_enqueue_batched(kzgb_ctx* c, Lane& L, const Fr* d_scalars, size_t n_per,
     const Affine* table;
     MsmPlan p;
     if (lag) {
-        p = msm_make_plan((uint32_t)(n_per * batch), lag->c, true, (uint32_t)lag->n, 0, (uint32_t)batch, L.throughput);
+        p = msm_make_plan((uint32_t)(n_per * batch), lag->c, true, (uint32_t)lag->n, 0, (uint32_t)batch);
         table = lag->table;
     } else {
         if (!c->wtable || n_per > c->wt_n) return fail(c, KZGB_ERR_GENERIC, "batched MSM needs a fixed-base table");
-        p = msm_make_plan((uint32_t)(n_per * batch), c->wt_c, true, (uint32_t)c->wt_n, 0, (uint32_t)batch, L.throughput);
+        p = msm_make_plan((uint32_t)(n_per * batch), c->wt_c, true, (uint32_t)c->wt_n, 0, (uint32_t)batch);
         table = c->wtable;
     }
     if ((uint64_t)n_per * batch * p.W >= 0xfff00000ull) return fail(c, KZGB_ERR_GENERIC, "MSM too large for one launch");
@@ -1339,8 +1338,6 @@ static int batch_impl(kzgb_ctx* c, const uint8_t* const* blobs_dev, const uint8_
         auto group_main = [&](int li) {
             cudaSetDevice(c->device);
             Lane& L = c->lanes[li];
-            L.throughput = true;
-            struct Reset { Lane& l; ~Reset() { l.throughput = false; } } reset{L};
             std::vector<Affine> pts;
             std::vector<Fr> zt;
             for (;;) {
@@ -1450,8 +1447,6 @@ static int batch_impl(kzgb_ctx* c, const uint8_t* const* blobs_dev, const uint8_
     auto lane_main = [&](int li) {
         cudaSetDevice(c->device);
         Lane& L = c->lanes[li];
-        L.throughput = count > 1;
-        struct Reset { Lane& l; ~Reset() { l.throughput = false; } } reset{L};
         for (;;) {
             size_t i = 0;
             bool is_proof = false;
@@ -1843,13 +1838,8 @@ int kzgb_set_option(const char* name, long value) {
     if (!strcmp(name, "eval_structured")) { eval_set_structured((int)value); return KZGB_OK; }
     if (!strcmp(name, "group")) { g_group.store((int)value); return KZGB_OK; }
     if (!strcmp(name, "lagrange")) { g_lagrange.store(value != 0); return KZGB_OK; }
-    if (!strcmp(name, "batch_affine_levels")) { msm_set_tuning((int)value, -1, -1); return KZGB_OK; }
+    if (!strcmp(name, "acc_waves")) { msm_set_acc_waves((int)value); return KZGB_OK; }
     return KZGB_ERR_GENERIC;
-}
-
-int kzgb_msm_tuning(int batch_affine_levels, int min_avg_bucket, int pairs_per_thread) {
-    msm_set_tuning(batch_affine_levels, min_avg_bucket, pairs_per_thread);
-    return KZGB_OK;
 }
 
 int kzgb_msm_config(const kzgb_ctx* c, int* window_bits, int* windows, size_t* table_points) {

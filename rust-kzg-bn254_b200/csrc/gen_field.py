@@ -730,20 +730,7 @@ def emit_header() -> str:
         pr = ROUTINES[what]("fq")
         out.append(pr.emit(f"fq_{what}_ptx(uint32_t* r, const uint32_t* a, const uint32_t* b)",
                            [f"r[{i}]" for i in range(8)], [f"a[{i}]" for i in range(8)] + [f"b[{i}]" for i in range(8)]))
-    out.append("#endif  // __CUDACC__")
-    return "\n".join(out) + "\n"
-
-
-def emit_header_experimental() -> str:
-    """Routines behind opt-in kernel variants only (field_gen_x.cuh, included by msm.cu): kept out of field_gen.cuh so
-    that trying one never touches a build input of the production kernels."""
-    out = [
-        "// GENERATED by gen_field.py -- do not edit.  Experimental routines (opt-in accumulate variants).",
-        "#pragma once",
-        "#include <stdint.h>",
-        "",
-        "#ifdef __CUDACC__",
-    ]
+    # bucket accumulation (msm.cu k_accumulate): dedicated squaring, predicated a - b (+ 2p), conditional negation
     pr = ROUTINES["sqrnr"]("fq")
     out.append(pr.emit("fq_sqrnr_ptx(uint32_t* r, const uint32_t* a)", [f"r[{i}]" for i in range(8)], [f"a[{i}]" for i in range(8)]))
     pr = ROUTINES["sub2pp"]("fq")
@@ -814,6 +801,4 @@ if __name__ == "__main__":
         here = os.path.dirname(os.path.abspath(__file__))
         with open(os.path.join(here, "field_gen.cuh"), "w") as f:
             f.write(emit_header())
-        with open(os.path.join(here, "field_gen_x.cuh"), "w") as f:
-            f.write(emit_header_experimental())
-        print("wrote field_gen.cuh, field_gen_x.cuh")
+        print("wrote field_gen.cuh")

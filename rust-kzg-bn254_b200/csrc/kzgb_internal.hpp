@@ -28,12 +28,9 @@ struct MsmPlan {
     uint32_t base_offset;   // first point of this launch inside the table (point-range sharding)
     uint32_t acc_threads;   // threads of the accumulate kernel (fixed-size chunks)
     uint32_t chunk;         // sorted entries per accumulate thread
-    uint32_t slice;         // buckets per bucket-reduce thread
-    // batch-affine front end (msm.cu): ba_levels pairwise affine levels over the padded sorted list,
-    // then the XYZZ accumulation of what is left (1 / 2^ba_levels of the entries)
-    int ba_levels;          // 0 = XYZZ accumulation straight from the table
-    uint32_t ba_k[4];       // pairs per thread at each level
-    uint32_t max_entries;   // upper bound of the (padded) sorted list: n*W + nbuckets * (2^ba_levels - 1)
+    // bucket matrix of one set for the 2-D reduction: 2^(c-1) buckets = 2^h_bits rows x 2^a_bits columns
+    int a_bits, h_bits;
+    int ngroups;            // bit groups of the weighted sums (= c - 1, or a_bits + 1 when h_bits == 0)
 };
 
 struct MsmWorkspace {
@@ -43,28 +40,20 @@ struct MsmWorkspace {
     uint32_t* sorted;   // n * W point refs grouped by bucket
     XYZZ* buckets;      // nbuckets
     XYZZ* partial;      // 2 * acc_threads
-    XYZZ* slice_sums;   // nbuckets / slice
+    XYZZ* line_sums;    // sets * (2^h_bits + 2^a_bits): row sums, then column sums of every set
+    XYZZ* group_sums;   // sets * ngroups
     XYZZ* set_sums;     // sets (device), copied to host by the caller
     uint32_t* tile_tot; // scan tile totals (<= 1024)
     uint32_t* long_list; // [0] counter, [1..] buckets spanning many accumulate chunks (k_bucket_fix_long)
-    Affine* ba_pts[2];  // level outputs, ping-pong: max_entries/2 and max_entries/4 points
-    Fq* ba_prefix;      // max_entries/2
-    Fq* ba_others;      // one per thread of the widest level
-    Fq* ba_blk_tot;     // one per block of the widest level
-    Fq* ba_blk_inv;
 };
 
 size_t msm_workspace_bytes(const MsmPlan& p);
 void msm_workspace_carve(const MsmPlan& p, void* base, MsmWorkspace* ws);
 // batch > 0 (fixed base only): n = batch * (n / batch) scalars of `batch` independent MSMs over the same
 // table points [base_offset, base_offset + n / batch); set_sums[k] is the result of MSM k.
-// throughput: the MSM runs inside a pipeline of several lanes (longer bucket-reduce slices: less work, more latency).
-MsmPlan msm_make_plan(uint32_t n, int c, bool fixed_base, uint32_t table_stride, uint32_t base_offset, uint32_t batch = 0,
-                      bool throughput = false);
-// Batch-affine tuning: levels (default 0 = off), minimum average bucket occupancy for it to be
-// used (default 64), pairs per thread at level 0 (0 = default: one wave per level).  Negative values keep
-// the current setting.
-void msm_set_tuning(int ba_levels, int ba_min_avg_bucket, int ba_k0);
+MsmPlan msm_make_plan(uint32_t n, int c, bool fixed_base, uint32_t table_stride, uint32_t base_offset, uint32_t batch = 0);
+// waves of accumulate blocks (4 blocks of 128 threads per SM and wave) the sorted list is cut into; default 4
+void msm_set_acc_waves(int waves);
 
 // scalars: n Fr (Montgomery unless scalars_canonical).  Result: ws.set_sums[0..sets) on the device.
 // The optional events bracket the bucket-accumulation kernel (roofline timing).

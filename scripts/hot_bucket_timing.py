@@ -6,7 +6,7 @@ pkg = load_package()
 n = 1 << 19
 eng = pkg.Engine(0)
 srs = pkg.SRS.synthetic(n, 2480609854371098259468018140899271569021640719453669963486734696239309822386, engine=eng)
-srs.precompute(n, int(os.environ.get("KZGB_WINDOW_BITS", "0")))
+srs.precompute(n, int(sys.argv[2]) if len(sys.argv) > 2 else 0)
 R = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
 import random
 rnd = random.Random(1)

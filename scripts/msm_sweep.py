@@ -7,8 +7,8 @@ logn = int(sys.argv[1]) if len(sys.argv) > 1 else 19
 n = 1 << logn
 eng = pkg.Engine(0)
 srs = pkg.SRS.synthetic(n, 2480609854371098259468018140899271569021640719453669963486734696239309822386, engine=eng)
-srs.precompute(n, int(os.environ.get('KZGB_WINDOW_BITS', '0')))
+srs.precompute(n, int(sys.argv[2]) if len(sys.argv) > 2 else 0)
 tot, acc = C.c_double(0), C.c_double(0)
 eng.check(pkg.lib.kzgb_bench_msm(eng.h, n, 10, C.byref(tot), C.byref(acc)))
-print(f"variant={os.environ.get('KZGB_ACC_VARIANT','0')} n=2^{logn} msm_total={tot.value:.3f} ms accumulate={acc.value:.3f} ms "
+print(f"n=2^{logn} msm_total={tot.value:.3f} ms accumulate={acc.value:.3f} ms "
       f"-> {10 * 16 * n / acc.value / 1e6:.1f} GFqmul/s")

@@ -178,10 +178,10 @@ def _geom(n):
     return (pow(TAU, n, o.R) - 1) * pow(TAU - 1, -1, o.R) % o.R
 
 
-@pytest.mark.parametrize("levels", [0, 3])
-def test_adversarial_scalar_distributions_2p16(pkg, levels):
-    """SURVEY.md 8d 'D3' inputs at n = 2^16 on the fixed-base table, with and without the batch-affine
-    front end: all scalars equal (every point of a window in ONE bucket -> buckets spanning thousands
+@pytest.mark.parametrize("waves", [4, 1])
+def test_adversarial_scalar_distributions_2p16(pkg, waves):
+    """SURVEY.md 8d 'D3' inputs at n = 2^16 on the fixed-base table, for two chunkings of the sorted list:
+    all scalars equal (every point of a window in ONE bucket -> buckets spanning thousands
     of chunks), all r - 1 (all digits negative / carries through every window), a single non-zero
     scalar, all zero (identity), and two distinct values (two hot buckets per window).  Closed forms
     from SRS_i = tau^i G."""
@@ -193,7 +193,7 @@ def test_adversarial_scalar_distributions_2p16(pkg, levels):
     G = o.G1_GEN
     s = 0x2F0E1D3C4B5A69788796A5B4C3D2E1F00112233445566778899AABBCCDDEEFF % o.R
     try:
-        pkg.lib.kzgb_msm_tuning(levels, 0, 0)
+        pkg.lib.kzgb_set_option(b"acc_waves", waves)
         assert kzg.commit_coeff_form(pkg.PolynomialCoeffForm([s] * n), srs) == o.g1_mul(G, s * _geom(n) % o.R)
         assert kzg.commit_coeff_form(pkg.PolynomialCoeffForm([o.R - 1] * n), srs) == o.g1_mul(G, (o.R - 1) * _geom(n) % o.R)
         one = [0] * n
@@ -205,7 +205,7 @@ def test_adversarial_scalar_distributions_2p16(pkg, levels):
         two = [s, t] * (n // 2)
         assert kzg.commit_coeff_form(pkg.PolynomialCoeffForm(two), srs) == o.g1_mul(G, (s * even + t * TAU % o.R * even) % o.R)
     finally:
-        pkg.lib.kzgb_msm_tuning(0, 64, 0)
+        pkg.lib.kzgb_set_option(b"acc_waves", 4)
 
 
 def test_zero_and_constant_blobs_2p16(pkg):

@@ -433,15 +433,15 @@ def test_verify_batch_rlc(pkg, ref_srs, ref_srs_points):
         pkg.verify_blob_kzg_proof_batch_rlc(blobs, cs[:2], ps, ref_srs.engine)
 
 
-@pytest.mark.parametrize("levels,k0", [(1, 8), (2, 4), (3, 32), (4, 16), (3, 0)])
-def test_batch_affine_levels_exact(pkg, eng, ref_srs, ref_srs_points, levels, k0):
-    """The batch-affine bucket accumulation (pairwise affine additions sharing one inversion per
-    level) forced on at small sizes: results must equal the oracle for random inputs and for every
-    exceptional pair -- identity bases and padding slots (pass-through), duplicate bases with equal
-    digits (P + P -> tangent), P and -P (-> identity), all-equal scalars (one hot bucket), zeros."""
-    rnd = random.Random(100 + levels)
+@pytest.mark.parametrize("waves", [1, 4, 32])
+def test_msm_exceptional_pairs_exact(pkg, eng, ref_srs, ref_srs_points, waves):
+    """Bucket accumulation, chunk stitching and the quad-cooperative 2-D bucket reduction at small sizes, for
+    several chunkings of the sorted list: results must equal the oracle for random inputs and for every
+    exceptional pair -- identity bases (pass-through), duplicate bases with equal digits (P + P ->
+    tangent), P and -P (-> identity), all-equal scalars (one hot bucket), zeros."""
+    rnd = random.Random(100 + waves)
     try:
-        pkg.lib.kzgb_msm_tuning(levels, 0, k0)
+        pkg.lib.kzgb_set_option(b"acc_waves", waves)
         P1, P2, P3 = ref_srs_points[1], ref_srs_points[2], ref_srs_points[3]
         # variable-base: duplicates / negations / identity with equal scalars land in the same buckets
         pts = [P1, P1, P2, o.g1_neg(P2), None, P1, P2, P2, P3, P3, P3, P3, None, o.g1_neg(P1), P1, P1]
@@ -465,7 +465,7 @@ def test_batch_affine_levels_exact(pkg, eng, ref_srs, ref_srs_points, levels, k0
         assert kzg.commit_coeff_form(pkg.PolynomialCoeffForm(sc), ref_srs) == o.msm(ref_srs_points[:2048], sc)
         assert kzg.commit_coeff_form(pkg.PolynomialCoeffForm([0] * 64), ref_srs) is None
     finally:
-        pkg.lib.kzgb_msm_tuning(0, 64, 0)
+        pkg.lib.kzgb_set_option(b"acc_waves", 4)
 
 
 def test_lagrange_table_and_monomial_paths_agree(pkg, ref_srs_points):
