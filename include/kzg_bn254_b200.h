@@ -32,6 +32,7 @@ extern "C" {
 #endif
 
 typedef struct kzgb_ctx kzgb_ctx;
+typedef struct kzgb_group kzgb_group; /* several GPUs of one box behind one handle, see "multi-GPU" below */
 
 typedef enum kzgb_status {
     KZGB_OK = 0,
@@ -83,13 +84,23 @@ int kzgb_srs_get_affine_mont(kzgb_ctx* ctx, size_t start, size_t count, uint64_t
 /* Build the fixed-base window tables (2^(c*w) * P_i) for MSMs of up to `max_n` points.  Called lazily
  * by the first commit if the caller does not; window_bits = 0 picks c from max_n. */
 int kzgb_srs_precompute(kzgb_ctx* ctx, size_t max_n, int window_bits);
+/* The same over SRS points [first, first + count) only: the table of one member's share of a point-range-sharded
+ * MSM (kzgb_group_srs_precompute_ranges).  A context holds one monomial window table at a time. */
+int kzgb_srs_precompute_range(kzgb_ctx* ctx, size_t first, size_t count, int window_bits);
+/* dst gets a copy of src's resident SRS points, device to device (a peer copy over NVLink when the contexts sit
+ * on different GPUs).  src must not be reloaded while the call runs. */
+int kzgb_srs_clone(kzgb_ctx* dst, kzgb_ctx* src);
 /* Build the Lagrange-basis window table for evaluation-form polynomials of exactly n = 2^k elements:
  * L = IFFT_G1(SRS[..n]) -- the points KZG::commit_eval_form recomputes with g1_ifft on EVERY call
  * (kzg.rs:98) -- computed once per size on the GPU and kept resident with their window shifts, so that
  * commit_eval_form / commit_blob / compute_proof* are one MSM on the evaluations themselves with no
- * Fr NTT on the path.  Called lazily by the first evaluation-form commit of a size if the caller does not
- * (option "lagrange", default on); without the table those calls use Fr-IFFT + the monomial table.
- * Same group element either way.  Err KZGB_ERR_FFT / KZGB_ERR_SRS_CAPACITY as kzgb_g1_ifft. */
+ * Fr NTT on the path.  Policy when the caller does not call this: the table of a size is built by the k-th
+ * evaluation-form commitment / proof of that size (option "lagrange_after", default 2; a batch of b blobs counts
+ * b) -- a one-off commit of a new size is not charged a G1 NTT (12 ms at n = 64, 0.5 s at 2^19); tables are kept
+ * within a memory budget (option "lagrange_budget_mib", default half of the device memory), least recently used
+ * dropped first; domains above 2^22 never get one.  Without the table the same group element comes from
+ * Fr-IFFT + the monomial table.  Err KZGB_ERR_FFT / KZGB_ERR_SRS_CAPACITY as kzgb_g1_ifft; KZGB_ERR_DEVICE if the
+ * table cannot be built (switched off, above 2^22, over the budget). */
 int kzgb_srs_prepare_lagrange(kzgb_ctx* ctx, size_t n);
 
 /* ---- MSM (ark-ec VariableBaseMSM::msm call sites) ---------------------------------------- */
@@ -218,8 +229,51 @@ int kzgb_stats(kzgb_ctx* ctx, double* acc_ms, uint64_t* acc_launches, uint64_t* 
  *                          holds <= 2^21 Fr and <= 64 blobs); 0: one blob at a time; k > 0: k blobs per group
  *   "lagrange"             1 (default): evaluation-form commits/proofs build and use the Lagrange-basis
  *                          table of their size (kzgb_srs_prepare_lagrange); 0: Fr-IFFT + monomial table
+ *   "lagrange_after", "lagrange_budget_mib"   the table policy described at kzgb_srs_prepare_lagrange
+ *   "lanes"                lanes (host thread + streams) of the blob-batch pipelines, 0 = the library's choice
+ *   "hash_threads"         host SHA-256 pool threads of a batch call, 0 = the library's choice
+ *   "lane_wait"            -1 auto, 0 lanes spin on their stream, 1 lanes poll with short sleeps (when lane threads
+ *                          outnumber spare cores)
+ *   "stream_priority"      1 (default): bucket accumulation runs on a low-priority stream of its lane
+ *   "l2_fetch_64"          1 (default): contexts that own their stream set the device's L2 fetch granularity to 64 B
+ *                          (random 64-byte gathers) and restore it when the last of them is destroyed
+ *   "batch_keep_mib"       blob staging memory kept between batch calls (default 4096)
+ *   "fs_quad"              1 (default): four lanes per blob in the device-side Fiat-Shamir hashing
+ * The library reads NO environment variables of its own (torchrun's LOCAL_WORLD_SIZE is consulted for "lane_wait" auto).
  * Unknown names return KZGB_ERR_GENERIC. */
 int kzgb_set_option(const char* name, long value);
+/* ---- multi-GPU: one handle over several GPUs of one box ------------------------------------
+ * The path shards by blob (batches) and by point range (one large MSM) and has no exchange step besides adding
+ * G partial sums of 64 bytes, which happens on the host: one process, one host thread per GPU for the duration of
+ * a call, no collective library needed.  A caller of KZG::commit_blob in a loop (prover/src/kzg.rs:182-185) or of a
+ * 2^26-coefficient KZG::commit_coeff_form (kzg.rs:107-125) reaches every GPU of the box through these.
+ * devices == NULL or n_devices <= 0: every visible device.  A device may be listed more than once (independent
+ * contexts on one GPU).  The SRS is decompressed ONCE (member 0) and replicated device to device. */
+int kzgb_group_create(kzgb_group** out, const int* devices, int n_devices);
+void kzgb_group_destroy(kzgb_group* group);
+int kzgb_group_size(const kzgb_group* group);
+/* Member context (owned by the group): for per-GPU calls such as kzgb_msm_config or kzgb_stats. */
+kzgb_ctx* kzgb_group_ctx(kzgb_group* group, int member);
+const char* kzgb_group_last_error(const kzgb_group* group);
+int kzgb_group_sync(kzgb_group* group);
+/* SRS::new and friends, as the kzgb_srs_load_* of a context. */
+int kzgb_group_srs_load_file(kzgb_group* group, const char* path, uint32_t order, uint32_t points_to_load);
+int kzgb_group_srs_load_cache(kzgb_group* group, const char* path, uint32_t points_to_load);
+int kzgb_group_srs_load_gnark_be(kzgb_group* group, const uint8_t* bytes, size_t n_points);
+int kzgb_group_srs_load_affine_mont(kzgb_group* group, const uint64_t* xy, const uint8_t* inf, size_t n_points);
+int kzgb_group_srs_load_synthetic(kzgb_group* group, const uint64_t tau_mont[4], size_t n_points);
+/* kzgb_srs_prepare_lagrange on every member. */
+int kzgb_group_srs_prepare_lagrange(kzgb_group* group, size_t n);
+/* Fixed-base window tables for kzgb_group_msm_srs calls of n points: member i over its own share of the points
+ * (1/G of the table memory per GPU). */
+int kzgb_group_srs_precompute_ranges(kzgb_group* group, size_t n, int window_bits);
+/* kzgb_commit_and_prove_blobs with the batch cut into contiguous shares of about equal bytes, one per member;
+ * byte-identical to the single-context call. */
+int kzgb_group_commit_and_prove_blobs(kzgb_group* group, const uint8_t* const* blobs, const size_t* lens, size_t count,
+                                      uint8_t* commitments32, uint8_t* proofs32);
+/* kzgb_msm_srs with the points cut into G contiguous ranges; the partial sums are added on the host. */
+int kzgb_group_msm_srs(kzgb_group* group, const uint64_t* scalars_mont, size_t n, uint64_t out_xy[8], uint8_t* out_inf);
+
 /* Fixed-base table in use: window bits c, windows W, points covered (0 = none). */
 int kzgb_msm_config(const kzgb_ctx* ctx, int* window_bits, int* windows, size_t* table_points);
 

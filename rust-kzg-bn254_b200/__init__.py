@@ -89,10 +89,12 @@ class Engine:
             raise KzgError("GenericError", f"kzgb_ctx_create failed ({rc}): no usable CUDA device {device}")
         self.h = h
         self.device = device
+        self._owned = True
 
     def close(self):
         if getattr(self, "h", None):
-            lib.kzgb_ctx_destroy(self.h)
+            if getattr(self, "_owned", True):
+                lib.kzgb_ctx_destroy(self.h)
             self.h = None
 
     def __del__(self):
@@ -115,6 +117,88 @@ class Engine:
 
     def launch_count(self) -> int:
         return int(lib.kzgb_launch_count(self.h))
+
+
+class Group:
+    """Several GPUs of one box behind one handle (``kzgb_group``): batches of blobs are cut by blob, one large
+    MSM by point range; the SRS is decompressed once and replicated device to device.  ``devices=None`` takes
+    every visible GPU; a device may be listed twice (independent contexts on one GPU)."""
+
+    def __init__(self, devices: Optional[Sequence[int]] = None):
+        h = C.c_void_p()
+        if devices is None:
+            rc = lib.kzgb_group_create(C.byref(h), None, 0)
+        else:
+            arr = (C.c_int * len(devices))(*devices)
+            rc = lib.kzgb_group_create(C.byref(h), arr, len(devices))
+        if rc != 0:
+            raise KzgError("GenericError", f"kzgb_group_create failed ({rc})")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib.kzgb_group_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return int(lib.kzgb_group_size(self.h))
+
+    def check(self, rc: int):
+        if rc != 0:
+            msg = lib.kzgb_group_last_error(self.h)
+            raise KzgError(_capi.STATUS_VARIANT.get(rc, "GenericError"), msg.decode() if msg else "")
+
+    def member(self, i: int) -> "Engine":
+        """Borrowed view of member i's context (owned by the group)."""
+        e = Engine.__new__(Engine)
+        e.h = C.c_void_p(lib.kzgb_group_ctx(self.h, i))
+        e._owned = False
+        e.device = -1
+        return e
+
+    # -- SRS ----------------------------------------------------------------------------
+    def load_srs_file(self, path: str, order: int, points_to_load: int) -> None:
+        self.check(lib.kzgb_group_srs_load_file(self.h, path.encode(), order, points_to_load))
+
+    def load_srs_gnark_bytes(self, data: bytes) -> None:
+        self.check(lib.kzgb_group_srs_load_gnark_be(self.h, data, len(data) // 32))
+
+    def load_srs_points(self, pts: Sequence[Affine]) -> None:
+        xy, inf = g1_to_abi(pts)
+        self.check(lib.kzgb_group_srs_load_affine_mont(self.h, xy, inf, len(pts)))
+
+    def load_srs_synthetic(self, n: int, tau: int) -> None:
+        self.check(lib.kzgb_group_srs_load_synthetic(self.h, fr_to_mont_bytes([tau]), n))
+
+    def prepare_lagrange(self, n: int) -> None:
+        self.check(lib.kzgb_group_srs_prepare_lagrange(self.h, n))
+
+    def precompute_ranges(self, n: int, window_bits: int = 0) -> None:
+        self.check(lib.kzgb_group_srs_precompute_ranges(self.h, n, window_bits))
+
+    # -- the sharded calls --------------------------------------------------------------
+    def commit_and_prove_blobs(self, blobs: Sequence["Blob"]) -> Tuple[List[bytes], List[bytes]]:
+        count = len(blobs)
+        keep = [C.create_string_buffer(b.blob_data, max(1, len(b.blob_data))) for b in blobs]
+        ptrs = (C.c_void_p * count)(*[C.cast(k, C.c_void_p).value for k in keep])
+        lens = (C.c_size_t * count)(*[len(b.blob_data) for b in blobs])
+        cs = C.create_string_buffer(32 * count if count else 1)
+        ps = C.create_string_buffer(32 * count if count else 1)
+        self.check(lib.kzgb_group_commit_and_prove_blobs(self.h, ptrs, lens, count, cs, ps))
+        return ([cs.raw[32 * i : 32 * i + 32] for i in range(count)], [ps.raw[32 * i : 32 * i + 32] for i in range(count)])
+
+    def commit_coeff_form(self, polynomial: "PolynomialCoeffForm") -> Affine:
+        """KZG::commit_coeff_form with the points cut into one range per GPU (prover/src/kzg.rs:107-125)."""
+        out = C.create_string_buffer(64)
+        inf = C.c_uint8(0)
+        self.check(lib.kzgb_group_msm_srs(self.h, fr_to_mont_bytes(polynomial.coeffs), len(polynomial), out, C.byref(inf)))
+        return g1_from_abi(out.raw, bytes([inf.value]))[0]
 
 
 _default_engine: Optional[Engine] = None

@@ -22,6 +22,7 @@ lib = C.CDLL(LIB_PATH)
 u8p = C.POINTER(C.c_uint8)
 u64p = C.POINTER(C.c_uint64)
 ctx_p = C.c_void_p
+grp_p = C.c_void_p
 buf = C.c_void_p  # any host/device buffer: bytes, ctypes arrays or integer addresses
 
 # name -> (restype, argtypes); mirrors include/kzg_bn254_b200.h one to one
@@ -84,6 +85,24 @@ SIGNATURES = {
     "kzgb_stats": (C.c_int, [ctx_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_int]),
     "kzgb_set_option": (C.c_int, [C.c_char_p, C.c_long]),
     "kzgb_msm_config": (C.c_int, [ctx_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
+    "kzgb_srs_precompute_range": (C.c_int, [ctx_p, C.c_size_t, C.c_size_t, C.c_int]),
+    "kzgb_srs_clone": (C.c_int, [ctx_p, ctx_p]),
+    # multi-GPU group
+    "kzgb_group_create": (C.c_int, [C.POINTER(grp_p), C.POINTER(C.c_int), C.c_int]),
+    "kzgb_group_destroy": (None, [grp_p]),
+    "kzgb_group_size": (C.c_int, [grp_p]),
+    "kzgb_group_ctx": (ctx_p, [grp_p, C.c_int]),
+    "kzgb_group_last_error": (C.c_char_p, [grp_p]),
+    "kzgb_group_sync": (C.c_int, [grp_p]),
+    "kzgb_group_srs_load_file": (C.c_int, [grp_p, C.c_char_p, C.c_uint32, C.c_uint32]),
+    "kzgb_group_srs_load_cache": (C.c_int, [grp_p, C.c_char_p, C.c_uint32]),
+    "kzgb_group_srs_load_gnark_be": (C.c_int, [grp_p, buf, C.c_size_t]),
+    "kzgb_group_srs_load_affine_mont": (C.c_int, [grp_p, buf, buf, C.c_size_t]),
+    "kzgb_group_srs_load_synthetic": (C.c_int, [grp_p, buf, C.c_size_t]),
+    "kzgb_group_srs_prepare_lagrange": (C.c_int, [grp_p, C.c_size_t]),
+    "kzgb_group_srs_precompute_ranges": (C.c_int, [grp_p, C.c_size_t, C.c_int]),
+    "kzgb_group_commit_and_prove_blobs": (C.c_int, [grp_p, C.c_void_p, C.c_void_p, C.c_size_t, buf, buf]),
+    "kzgb_group_msm_srs": (C.c_int, [grp_p, buf, C.c_size_t, buf, C.POINTER(C.c_uint8)]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

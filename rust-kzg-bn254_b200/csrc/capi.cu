@@ -53,12 +53,13 @@ struct Lane {
     bool own_stream = false;
     DevBuf bytes, evals, work, ntt_scratch, eval_scratch, msm_ws, small, bases;
     XYZZ* h_sets = nullptr;   // pinned
+    uint32_t* h_entries = nullptr;  // pinned: length of the sorted list of the MSM in flight (= its point additions)
     Fr* h_fr = nullptr;       // pinned, 16 elements
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_done = nullptr;
     bool ev_pending = false;
     double acc_ms = 0;        // summed duration of bucket-accumulation kernels
     uint64_t acc_launches = 0;
-    uint64_t acc_adds = 0;    // point additions those kernels performed (n * W upper bound)
+    uint64_t acc_adds = 0;    // sorted-list entries those kernels consumed (every entry is one point addition or install)
 };
 
 }  // namespace
@@ -72,13 +73,16 @@ struct kzgb_ctx {
     // SRS
     Affine* srs = nullptr;
     size_t srs_n = 0;
-    Affine* wtable = nullptr;
-    size_t wt_n = 0;
+    Affine* wtable = nullptr;   // fixed-base window table over SRS points [wt_first, wt_first + wt_n)
+    size_t wt_first = 0, wt_n = 0;
     int wt_c = 0, wt_W = 0;
     bool auto_precompute = true;
+    std::atomic<bool> lanes_running{false};  // a batch pipeline is driving the lanes: tables are read-only
+    bool set_l2_limit = false;
     // Lagrange-basis tables, one per domain size 2^k: window table over L = IFFT_G1(SRS[..2^k]) so that
     // evaluation-form commitments are ONE MSM on the evaluations themselves (no Fr NTT on the path)
-    struct LagTable { Affine* table = nullptr; size_t n = 0; int c = 0, W = 0; } lag[29];
+    struct LagTable { Affine* table = nullptr; size_t n = 0; int c = 0, W = 0; uint64_t last_use = 0; uint32_t calls = 0; } lag[29];
+    uint64_t lag_clock = 0;
     DevBuf batch_bytes;  // blob bytes of the batch in flight (commit_and_prove_blobs)
     // twiddles
     Fr* tw = nullptr;
@@ -91,13 +95,23 @@ namespace {
 
 std::mutex g_err_mu;
 // -1: choose per call, 0: host SHA-256 pool, 1: device kernel (verify_batch_rlc challenges)
-std::atomic<int> g_fs_device{getenv("KZGB_FS_DEVICE") ? atoi(getenv("KZGB_FS_DEVICE")) : -1};
+std::atomic<int> g_fs_device{-1};
 // 1: evaluation-form commitments use a Lagrange-basis window table (built on first use per size), 0: Fr-IFFT + monomial table
-// -1: KZGB_GROUP env / auto, 0: one blob at a time, > 0: blobs per group in the small-blob batch path
+// -1: auto, 0: one blob at a time, > 0: blobs per group in the small-blob batch path
 std::atomic<int> g_group{-1};
 // points per chunk of the streamed SRS ingest (0 = 2^22); tests shrink it to cross chunk boundaries
 std::atomic<long> g_srs_chunk{0};
-std::atomic<int> g_lagrange{getenv("KZGB_LAGRANGE") ? atoi(getenv("KZGB_LAGRANGE")) : 1};
+std::atomic<int> g_group_members{1};  // largest kzgb_group alive in this process
+std::atomic<int> g_lagrange{1};
+std::atomic<int> g_lagrange_after{2};       // build the Lagrange table of a size at its k-th evaluation-form use
+std::atomic<long> g_lagrange_budget_mib{0}; // 0 = half of the device memory
+// kzgb_set_option knobs that used to be environment switches (0 / -1 = the library's own choice)
+std::atomic<int> g_lanes{0};            // lanes of the blob-batch pipelines
+std::atomic<int> g_hash_threads{0};     // host SHA-256 pool threads per batch call
+std::atomic<int> g_lane_wait{-1};       // -1 auto, 0 spin on the stream, 1 poll with short sleeps
+std::atomic<int> g_stream_priority{1};  // 1: bucket accumulation on a low-priority stream of its own
+std::atomic<int> g_l2_fetch_64{1};
+std::atomic<long> g_batch_keep_mib{4096};  // blob staging buffer of kzgb_commit_and_prove_blobs kept between calls up to this size      // 1: contexts that own their stream set the L2 fetch granularity to 64 B
 int fail(kzgb_ctx* c, int code, const std::string& msg) {
     if (c) { std::lock_guard<std::mutex> lk(g_err_mu); c->err = msg; }
     return code;
@@ -108,6 +122,32 @@ int fail(kzgb_ctx* c, int code, const std::string& msg) {
         if (e_ != cudaSuccess)                                                                     \
             return fail(ctx, KZGB_ERR_DEVICE, std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #call); \
     } while (0)
+
+// The MSM gathers 64-byte points at random from tables far larger than L2: with the default fetch granularity a
+// miss pulls the whole 128-byte line and doubles the DRAM traffic of the accumulation.  The limit is device-wide,
+// so only contexts that own their stream touch it (a caller-supplied stream means the caller owns the device's
+// configuration), the previous value is put back when the last such context of a device is destroyed, and option
+// "l2_fetch_64" = 0 leaves it alone altogether.
+struct L2Limit { int refs = 0; size_t prev = 0; };
+std::mutex g_l2_mu;
+L2Limit g_l2[64];
+void l2_limit_acquire(int device) {  // current device == device
+    if (device < 0 || device >= 64) return;
+    std::lock_guard<std::mutex> lk(g_l2_mu);
+    if (g_l2[device].refs++ == 0) {
+        if (cudaDeviceGetLimit(&g_l2[device].prev, cudaLimitMaxL2FetchGranularity) != cudaSuccess) g_l2[device].prev = 0;
+        cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 64);
+        cudaGetLastError();
+    }
+}
+void l2_limit_release(int device) {
+    if (device < 0 || device >= 64) return;
+    std::lock_guard<std::mutex> lk(g_l2_mu);
+    if (--g_l2[device].refs == 0 && g_l2[device].prev) {
+        cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, g_l2[device].prev);
+        cudaGetLastError();
+    }
+}
 
 // ---------------------------------------------------------------- host field helpers
 const uint32_t ROOT28_CANON[8] = {0x725b19f0u, 0x9bd61b6eu, 0x41112ed4u, 0x402d111eu,
@@ -221,8 +261,7 @@ int lane_init(kzgb_ctx* c, Lane& L, cudaStream_t st) {
         CK(c, cudaDeviceGetStreamPriorityRange(&lo, &hi));  // numerically lower = higher priority
         CK(c, cudaStreamCreateWithPriority(&L.st, cudaStreamNonBlocking, hi));
         L.own_stream = true;
-        static const bool split = getenv("KZGB_NO_PRIORITY") == nullptr;
-        if (split && lo != hi) {
+        if (g_stream_priority.load() && lo != hi) {
             CK(c, cudaStreamCreateWithPriority(&L.st_acc, cudaStreamNonBlocking, lo));
             CK(c, cudaEventCreateWithFlags(&L.ev_fork, cudaEventDisableTiming));
             CK(c, cudaEventCreateWithFlags(&L.ev_join, cudaEventDisableTiming));
@@ -230,6 +269,7 @@ int lane_init(kzgb_ctx* c, Lane& L, cudaStream_t st) {
     }
     CK(c, cudaMallocHost((void**)&L.h_sets, sizeof(XYZZ) * MAX_SETS));
     CK(c, cudaMallocHost((void**)&L.h_fr, sizeof(Fr) * 16));
+    CK(c, cudaMallocHost((void**)&L.h_entries, 16));
     CK(c, cudaEventCreate(&L.ev0));
     CK(c, cudaEventCreate(&L.ev1));
     CK(c, cudaEventCreateWithFlags(&L.ev_done, cudaEventDisableTiming));
@@ -240,6 +280,7 @@ void lane_destroy(Lane& L) {
     L.eval_scratch.release(); L.msm_ws.release(); L.small.release(); L.bases.release();
     if (L.h_sets) cudaFreeHost(L.h_sets);
     if (L.h_fr) cudaFreeHost(L.h_fr);
+    if (L.h_entries) cudaFreeHost(L.h_entries);
     if (L.ev0) cudaEventDestroy(L.ev0);
     if (L.ev1) cudaEventDestroy(L.ev1);
     if (L.ev_done) cudaEventDestroy(L.ev_done);
@@ -258,10 +299,11 @@ int ensure_lanes(kzgb_ctx* c, int want) {
     }
     return KZGB_OK;
 }
+// called once the lane's stream has drained: duration of the accumulate kernel and the additions it performed
 void lane_collect_acc(Lane& L) {
     if (L.ev_pending) {
         float ms = 0;
-        if (cudaEventElapsedTime(&ms, L.ev0, L.ev1) == cudaSuccess) { L.acc_ms += ms; L.acc_launches++; }
+        if (cudaEventElapsedTime(&ms, L.ev0, L.ev1) == cudaSuccess) { L.acc_ms += ms; L.acc_launches++; L.acc_adds += *L.h_entries; }
         L.ev_pending = false;
     }
 }
@@ -287,6 +329,8 @@ int ensure_twiddles(kzgb_ctx* c, int logn) {
 int build_window_table(kzgb_ctx* c, const Affine* points, size_t n, int cb, size_t reusable_bytes, Affine** out, int* W_out) {
     if (cb < 2 || cb > 24) return fail(c, KZGB_ERR_GENERIC, "window_bits out of range");
     int W = (255 + cb - 1) / cb;
+    if ((uint64_t)W * n >= ((uint64_t)1 << 31))  // sorted refs are 31 bits + sign (msm.cu k_scatter)
+        return fail(c, KZGB_ERR_GENERIC, "window table too large: windows x points must stay below 2^31 (use more window bits)");
     size_t bytes = (size_t)W * n * sizeof(Affine);
     size_t free_b = 0, total_b = 0;
     CK(c, cudaMemGetInfo(&free_b, &total_b));
@@ -310,18 +354,28 @@ int build_window_table(kzgb_ctx* c, const Affine* points, size_t n, int cb, size
     return KZGB_OK;
 }
 
-int do_precompute(kzgb_ctx* c, size_t max_n, int window_bits) {
-    if (max_n > c->srs_n) max_n = c->srs_n;
-    if (max_n == 0) return KZGB_OK;
-    int cb = window_bits > 0 ? window_bits : choose_c_fixed(max_n);
+// Fixed-base window table over SRS points [first, first + count).  The fit is checked BEFORE the current table
+// is given up, so a request that cannot be met leaves the context as it was.
+int do_precompute(kzgb_ctx* c, size_t first, size_t count, int window_bits) {
+    if (first >= c->srs_n) return KZGB_OK;
+    if (count > c->srs_n - first) count = c->srs_n - first;
+    if (count == 0) return KZGB_OK;
+    int cb = window_bits > 0 ? window_bits : choose_c_fixed(count);
+    if (cb < 2 || cb > 24) return fail(c, KZGB_ERR_GENERIC, "window_bits out of range");
     for (int i = 0; i < c->n_lanes; i++) CK(c, cudaStreamSynchronize(c->lanes[i].st));
     size_t reusable = c->wtable ? (size_t)c->wt_W * c->wt_n * sizeof(Affine) : 0;
-    if (c->wtable) { cudaFree(c->wtable); c->wtable = nullptr; c->wt_n = 0; }
+    {
+        size_t need = (size_t)((255 + cb - 1) / cb) * count * sizeof(Affine), free_b = 0, total_b = 0;
+        CK(c, cudaMemGetInfo(&free_b, &total_b));
+        if (need + (2ull << 30) > free_b + reusable)
+            return fail(c, KZGB_ERR_DEVICE, "not enough device memory for the fixed-base window tables");
+    }
+    if (c->wtable) { cudaFree(c->wtable); c->wtable = nullptr; c->wt_n = 0; c->wt_first = 0; }
     Affine* table = nullptr;
     int W = 0;
-    int rc = build_window_table(c, c->srs, max_n, cb, reusable, &table, &W);
+    int rc = build_window_table(c, c->srs + first, count, cb, 0, &table, &W);
     if (rc) return rc;
-    c->wtable = table; c->wt_n = max_n; c->wt_c = cb; c->wt_W = W;
+    c->wtable = table; c->wt_first = first; c->wt_n = count; c->wt_c = cb; c->wt_W = W;
     return KZGB_OK;
 }
 
@@ -332,13 +386,47 @@ void lagrange_release(kzgb_ctx* c) {
 // Lagrange-basis window table for the domain of size n = 2^logn: L = IFFT_G1(SRS[..n]) (the points
 // KZG::commit_eval_form recomputes on every call, kzg.rs:98), then the same window shifts as the
 // monomial table.  One G1 inverse NTT per size and context; MSM(L, evals) is the eval-form commitment.
-// Returns KZGB_OK with no table (t.table == nullptr) when the feature is off or memory is short.
-int ensure_lagrange(kzgb_ctx* c, int logn) {
+// Policy (kzgb_set_option):
+//   "lagrange_after" k (default 2)  the table of a size is built when the k-th evaluation-form commitment / proof of
+//                                   that size is requested (`weight` = how many this call stands for: a batch of b
+//                                   blobs counts b); until then, and whenever there is no table, the same group element
+//                                   comes from the Fr-IFFT + monomial MSM.  kzgb_srs_prepare_lagrange builds at once.
+//   "lagrange_budget_mib" (default 0 = half of the device's memory)  bytes of Lagrange tables kept per context; the
+//                                   least recently used ones are dropped to make room, a table that cannot fit is not built.
+// Domains above 2^22 never get a table (W x 2^23 x 64 B = 6.4 GB and a 40 s G1 NTT per size): they stay on the
+// Fr-IFFT + monomial path, documented in include/kzg_bn254_b200.h.
+// Returns KZGB_OK with no table (t.table == nullptr) when the policy says "not yet", the feature is off or memory is short.
+// Called under the context lock, never while lane threads run.
+int ensure_lagrange(kzgb_ctx* c, int logn, uint32_t weight = 1, bool force = false) {
     if (logn < 1 || logn > 28) return KZGB_OK;
     kzgb_ctx::LagTable& t = c->lag[logn];
+    t.last_use = ++c->lag_clock;
+    if (t.calls < 0xffff0000u) t.calls += weight;
     if (t.table) return KZGB_OK;
     const size_t n = (size_t)1 << logn;
     if (!g_lagrange.load() || !c->auto_precompute || n > c->srs_n || n > ((size_t)1 << 22)) return KZGB_OK;
+    if (!force && t.calls < (uint32_t)std::max(1, g_lagrange_after.load())) return KZGB_OK;
+    const int cb_plan = (c->wtable && c->wt_first == 0 && c->wt_n == n) ? c->wt_c : choose_c_fixed(n);
+    {   // memory budget: drop least recently used tables until this one fits
+        size_t free_b = 0, total_b = 0;
+        CK(c, cudaMemGetInfo(&free_b, &total_b));
+        size_t budget = g_lagrange_budget_mib.load() > 0 ? (size_t)g_lagrange_budget_mib.load() << 20 : total_b / 2;
+        const size_t need = (size_t)((255 + cb_plan - 1) / cb_plan) * n * sizeof(Affine);
+        if (need > budget) return KZGB_OK;
+        for (;;) {
+            size_t held = 0;
+            kzgb_ctx::LagTable* lru = nullptr;
+            for (auto& o : c->lag) {
+                if (!o.table) continue;
+                held += (size_t)o.W * o.n * sizeof(Affine);
+                if (!lru || o.last_use < lru->last_use) lru = &o;
+            }
+            if (held + need <= budget || !lru) break;
+            for (int i = 0; i < c->n_lanes; i++) CK(c, cudaStreamSynchronize(c->lanes[i].st));
+            cudaFree(lru->table);
+            lru->table = nullptr; lru->n = 0; lru->calls = 0;
+        }
+    }
     int rc = ensure_twiddles(c, logn);
     if (rc) return rc;
     for (int i = 0; i < c->n_lanes; i++) CK(c, cudaStreamSynchronize(c->lanes[i].st));
@@ -355,7 +443,7 @@ int ensure_lagrange(kzgb_ctx* c, int logn) {
     work.release();
     if (e != cudaSuccess) { pts.release(); CK(c, e); }
     Affine* table = nullptr;
-    int W = 0, cb = (c->wtable && c->wt_n == n) ? c->wt_c : choose_c_fixed(n);  // an explicit window override carries over
+    int W = 0, cb = cb_plan;  // an explicit window override of the monomial table carries over
     rc = build_window_table(c, (const Affine*)pts.p, n, cb, 0, &table, &W);
     pts.release();
     if (rc == KZGB_ERR_DEVICE) { cudaGetLastError(); return KZGB_OK; }  // short of memory: stay on the monomial path
@@ -367,7 +455,7 @@ int ensure_lagrange(kzgb_ctx* c, int logn) {
 int srs_install(kzgb_ctx* c, Affine* dev_points, size_t n) {
     for (int i = 0; i < c->n_lanes; i++) cudaStreamSynchronize(c->lanes[i].st);
     if (c->srs) cudaFree(c->srs);
-    if (c->wtable) { cudaFree(c->wtable); c->wtable = nullptr; c->wt_n = 0; }
+    if (c->wtable) { cudaFree(c->wtable); c->wtable = nullptr; c->wt_n = 0; c->wt_first = 0; }
     lagrange_release(c);
     c->srs = dev_points;
     c->srs_n = n;
@@ -391,14 +479,16 @@ int msm_enqueue(kzgb_ctx* c, Lane& L, const Fr* d_scalars, bool canonical, size_
         p = msm_make_plan((uint32_t)n, lag->c, true, (uint32_t)lag->n, 0);
         table = lag->table;
     } else if (!var_bases) {
-        if (first + n > c->srs_n) return fail(c, KZGB_ERR_GENERIC, "MSM range exceeds the SRS");
-        if (c->auto_precompute && (!c->wtable || first + n > c->wt_n) && c->srs_n <= ((size_t)1 << 22)) {
+        if (first > c->srs_n || n > c->srs_n - first) return fail(c, KZGB_ERR_GENERIC, "MSM range exceeds the SRS");
+        auto covered = [&]() { return c->wtable && first >= c->wt_first && first + n <= c->wt_first + c->wt_n; };
+        // lazily built on the first use -- never from the lane threads of a running batch (they only read the tables)
+        if (c->auto_precompute && !covered() && c->srs_n <= ((size_t)1 << 22) && !c->lanes_running.load()) {
             size_t want = std::min(c->srs_n, next_pow2(first + n));
-            int rc = do_precompute(c, want, 0);
+            int rc = do_precompute(c, 0, want, 0);
             if (rc && rc != KZGB_ERR_DEVICE) return rc;
         }
-        if (c->wtable && first + n <= c->wt_n) {
-            p = msm_make_plan((uint32_t)n, c->wt_c, true, (uint32_t)c->wt_n, (uint32_t)first);
+        if (covered()) {
+            p = msm_make_plan((uint32_t)n, c->wt_c, true, (uint32_t)c->wt_n, (uint32_t)(first - c->wt_first));
             table = c->wtable;
         } else {
             p = msm_make_plan((uint32_t)n, choose_c_var(n), false, 0, 0);
@@ -415,7 +505,7 @@ int msm_enqueue(kzgb_ctx* c, Lane& L, const Fr* d_scalars, bool canonical, size_
     lane_collect_acc(L);
     msm_launch(p, ws, d_scalars, canonical, table, L.st, L.ev0, L.ev1, L.st_acc, L.ev_fork, L.ev_join);
     L.ev_pending = true;
-    L.acc_adds += (uint64_t)n * p.W;
+    CK(c, cudaMemcpyAsync(L.h_entries, ws.hist + p.nbuckets, 4, cudaMemcpyDeviceToHost, L.st));
     CK(c, cudaMemcpyAsync(L.h_sets, ws.set_sums, sizeof(XYZZ) * p.sets, cudaMemcpyDeviceToHost, L.st));
     job->plan = p;
     job->active = true;
@@ -479,7 +569,7 @@ int msm_enqueue_batched(kzgb_ctx* c, Lane& L, const Fr* d_scalars, size_t n_per,
         p = msm_make_plan((uint32_t)(n_per * batch), lag->c, true, (uint32_t)lag->n, 0, (uint32_t)batch);
         table = lag->table;
     } else {
-        if (!c->wtable || n_per > c->wt_n) return fail(c, KZGB_ERR_GENERIC, "batched MSM needs a fixed-base table");
+        if (!c->wtable || c->wt_first != 0 || n_per > c->wt_n) return fail(c, KZGB_ERR_GENERIC, "batched MSM needs a fixed-base table");
         p = msm_make_plan((uint32_t)(n_per * batch), c->wt_c, true, (uint32_t)c->wt_n, 0, (uint32_t)batch);
         table = c->wtable;
     }
@@ -490,7 +580,7 @@ int msm_enqueue_batched(kzgb_ctx* c, Lane& L, const Fr* d_scalars, size_t n_per,
     lane_collect_acc(L);
     msm_launch(p, ws, d_scalars, false, table, L.st, L.ev0, L.ev1, L.st_acc, L.ev_fork, L.ev_join);
     L.ev_pending = true;
-    L.acc_adds += (uint64_t)n_per * batch * p.W;
+    CK(c, cudaMemcpyAsync(L.h_entries, ws.hist + p.nbuckets, 4, cudaMemcpyDeviceToHost, L.st));
     CK(c, cudaMemcpyAsync(L.h_sets, ws.set_sums, sizeof(XYZZ) * p.sets, cudaMemcpyDeviceToHost, L.st));
     job->plan = p;
     job->active = true;
@@ -596,17 +686,14 @@ Fr challenge_finish(Sha256 sh, const Affine& commitment) {
 }
 
 bool lane_wait_polls() {
+    const int opt = g_lane_wait.load();
+    if (opt >= 0) return opt == 1;
     static int mode = -1;
     if (mode < 0) {
-        const char* e = getenv("KZGB_LANE_WAIT");
-        if (e && !strcmp(e, "spin")) mode = 0;
-        else if (e && !strcmp(e, "poll")) mode = 1;
-        else {
-            unsigned hw = std::thread::hardware_concurrency();
-            int local = 1;
-            if (const char* w = getenv("LOCAL_WORLD_SIZE")) { int v = atoi(w); if (v > 0) local = v; }
-            mode = ((unsigned)local * 4u > hw / 2u) ? 1 : 0;
-        }
+        unsigned hw = std::thread::hardware_concurrency();
+        int local = g_group_members.load();  // GPUs driven by this process (kzgb_group)
+        if (const char* w = getenv("LOCAL_WORLD_SIZE")) { int v = atoi(w); if (v > local) local = v; }  // torchrun: ranks on this host
+        mode = ((unsigned)local * 4u > hw / 2u) ? 1 : 0;
     }
     return mode == 1;
 }
@@ -616,10 +703,14 @@ bool lane_wait_polls() {
 // oversubscribed, beats a pool sized to this rank's share of the cores (1545 vs 1222 blobs/s) -- at
 // 8 GPUs the job is bound by the host's aggregate SHA-256 rate (2.1 GB of transcripts per step).
 size_t hash_pool_threads() {
-    if (const char* e = getenv("KZGB_HASH_THREADS")) { int v = atoi(e); if (v > 0) return (size_t)v; }
+    if (int v = g_hash_threads.load()) return (size_t)v;
     unsigned hw = std::thread::hardware_concurrency();
     if (hw == 0) hw = 8;
-    return std::min<size_t>(hw > 4 ? hw - 2 : 2, 32);
+    size_t pool = std::min<size_t>(hw > 4 ? hw - 2 : 2, 32);
+    // the members of a kzgb_group hash at the same time: share the cores (ranks of a torchrun job are separate
+    // processes; measured there, one thread per blob even oversubscribed beats a share of the cores)
+    size_t members = (size_t)std::max(1, g_group_members.load());
+    return std::max<size_t>(2, pool / members);
 }
 
 size_t blob_poly_len(size_t len) { return next_pow2((len + 31) / 32); }  // Rust: 0usize.next_power_of_two() == 1
@@ -742,7 +833,7 @@ int kzgb_ctx_create(kzgb_ctx** out, int device, void* stream) {
     cudaGetDevice(&prev);
     if (cudaSetDevice(device) != cudaSuccess) { delete c; return KZGB_ERR_DEVICE; }
     int rc = lane_init(c, c->lanes[0], (cudaStream_t)stream);
-    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 64);  // the MSM gathers 64-byte points at random
+    if (rc == KZGB_OK && !stream && g_l2_fetch_64.load()) { l2_limit_acquire(device); c->set_l2_limit = true; }
     if (rc == KZGB_OK) {
         c->n_lanes = 1;
         if (cudaEventCreate(&c->t0) != cudaSuccess || cudaEventCreate(&c->t1) != cudaSuccess) rc = KZGB_ERR_DEVICE;
@@ -766,6 +857,7 @@ void kzgb_ctx_destroy(kzgb_ctx* c) {
     c->batch_bytes.release();
     if (c->t0) cudaEventDestroy(c->t0);
     if (c->t1) cudaEventDestroy(c->t1);
+    if (c->set_l2_limit) l2_limit_release(c->device);
     cudaSetDevice(prev);
     delete c;
 }
@@ -867,6 +959,28 @@ int kzgb_srs_load_affine_mont(kzgb_ctx* c, const uint64_t* xy, const uint8_t* in
     return srs_install(c, pts, n);
 }
 
+// dst gets a copy of src's SRS points, device to device (peer copy over NVLink when the contexts sit on different
+// GPUs): how a kzgb_group replicates an SRS that was decompressed once.
+int kzgb_srs_clone(kzgb_ctx* dst, kzgb_ctx* src) {
+    if (!dst || !src || dst == src) return KZGB_ERR_GENERIC;
+    size_t n = 0;
+    const Affine* from = nullptr;
+    int src_dev = 0;
+    {
+        Guard gs(src);
+        for (int i = 0; i < src->n_lanes; i++) CK(src, cudaStreamSynchronize(src->lanes[i].st));
+        n = src->srs_n; from = src->srs; src_dev = src->device;
+    }
+    Guard g(dst);
+    if (n == 0) return fail(dst, KZGB_ERR_GENERIC, "no SRS loaded in the source context");
+    Affine* pts = nullptr;
+    CK(dst, cudaMalloc((void**)&pts, n * sizeof(Affine)));
+    cudaError_t e = (src_dev == dst->device) ? cudaMemcpy(pts, from, n * sizeof(Affine), cudaMemcpyDeviceToDevice)
+                                              : cudaMemcpyPeer(pts, dst->device, from, src_dev, n * sizeof(Affine));
+    if (e != cudaSuccess) { cudaFree(pts); CK(dst, e); }
+    return srs_install(dst, pts, n);
+}
+
 int kzgb_srs_load_synthetic_range(kzgb_ctx* c, const uint64_t tau_mont[4], size_t first, size_t n);
 int kzgb_srs_load_synthetic(kzgb_ctx* c, const uint64_t tau_mont[4], size_t n) {
     return kzgb_srs_load_synthetic_range(c, tau_mont, 0, n);
@@ -888,7 +1002,7 @@ size_t kzgb_srs_len(const kzgb_ctx* c) { return c ? c->srs_n : 0; }
 
 int kzgb_srs_get_affine_mont(kzgb_ctx* c, size_t start, size_t count, uint64_t* out_xy, uint8_t* out_inf) {
     Guard g(c);
-    if (start + count > c->srs_n) return fail(c, KZGB_ERR_GENERIC, "SRS range out of bounds");
+    if (start > c->srs_n || count > c->srs_n - start) return fail(c, KZGB_ERR_GENERIC, "SRS range out of bounds");
     CK(c, cudaMemcpy(out_xy, c->srs + start, count * sizeof(Affine), cudaMemcpyDeviceToHost));
     if (out_inf) {
         const Affine* a = (const Affine*)out_xy;
@@ -902,12 +1016,19 @@ int kzgb_srs_precompute(kzgb_ctx* c, size_t max_n, int window_bits) {
     if (window_bits < 0) {  // disable fixed-base tables (variable-base mode over the monomial points)
         c->auto_precompute = false;
         for (int i = 0; i < c->n_lanes; i++) cudaStreamSynchronize(c->lanes[i].st);
-        if (c->wtable) { cudaFree(c->wtable); c->wtable = nullptr; c->wt_n = 0; }
+        if (c->wtable) { cudaFree(c->wtable); c->wtable = nullptr; c->wt_n = 0; c->wt_first = 0; }
         lagrange_release(c);
         return KZGB_OK;
     }
     if (!c->srs_n) return fail(c, KZGB_ERR_GENERIC, "no SRS loaded");
-    return do_precompute(c, max_n ? max_n : c->srs_n, window_bits);
+    return do_precompute(c, 0, max_n ? max_n : c->srs_n, window_bits);
+}
+
+int kzgb_srs_precompute_range(kzgb_ctx* c, size_t first, size_t count, int window_bits) {
+    Guard g(c);
+    if (!c->srs_n) return fail(c, KZGB_ERR_GENERIC, "no SRS loaded");
+    if (first > c->srs_n || count > c->srs_n - first) return fail(c, KZGB_ERR_GENERIC, "SRS range out of bounds");
+    return do_precompute(c, first, count, window_bits < 0 ? 0 : window_bits);
 }
 
 int kzgb_srs_prepare_lagrange(kzgb_ctx* c, size_t n) {
@@ -919,9 +1040,9 @@ int kzgb_srs_prepare_lagrange(kzgb_ctx* c, size_t n) {
         return fail(c, KZGB_ERR_SRS_CAPACITY, msg);
     }
     int logn = log2_exact(n);
-    int rc = ensure_lagrange(c, logn);
+    int rc = ensure_lagrange(c, logn, 1, true);
     if (rc) return rc;
-    if (logn >= 1 && !c->lag[logn].table) return fail(c, KZGB_ERR_DEVICE, "Lagrange-basis table not built (disabled, or not enough device memory)");
+    if (logn >= 1 && !c->lag[logn].table) return fail(c, KZGB_ERR_DEVICE, "Lagrange-basis table not built (disabled, above 2^22, or over the memory budget)");
     return KZGB_OK;
 }
 
@@ -929,7 +1050,7 @@ int kzgb_srs_prepare_lagrange(kzgb_ctx* c, size_t n) {
 int kzgb_msm_srs_range(kzgb_ctx* c, const uint64_t* scalars, size_t first, size_t n, uint64_t out_xy[8], uint8_t* out_inf) {
     Guard g(c);
     Lane& L = c->lanes[0];
-    if (first + n > c->srs_n) return fail(c, KZGB_ERR_SERIALIZATION, "polynomial length is not correct");
+    if (first > c->srs_n || n > c->srs_n - first) return fail(c, KZGB_ERR_SERIALIZATION, "polynomial length is not correct");
     Affine r;
     if (n == 0) { aff_set_inf(r); affine_to_abi(r, out_xy, out_inf); return KZGB_OK; }
     CK(c, L.work.reserve(n * sizeof(Fr)));
@@ -943,7 +1064,7 @@ int kzgb_msm_srs_range_dev(kzgb_ctx* c, const uint64_t* scalars_dev, size_t firs
                            uint8_t* out_inf) {
     Guard g(c);
     Lane& L = c->lanes[0];
-    if (first + n > c->srs_n) return fail(c, KZGB_ERR_SERIALIZATION, "polynomial length is not correct");
+    if (first > c->srs_n || n > c->srs_n - first) return fail(c, KZGB_ERR_SERIALIZATION, "polynomial length is not correct");
     Affine r;
     int rc = msm_blocking(c, L, (const Fr*)scalars_dev, false, first, n, nullptr, &r);
     if (rc) return rc;
@@ -952,6 +1073,7 @@ int kzgb_msm_srs_range_dev(kzgb_ctx* c, const uint64_t* scalars_dev, size_t firs
 }
 int kzgb_fr_powers_dev(kzgb_ctx* c, const uint64_t base_mont[4], size_t first_exponent, size_t n, uint64_t* out_dev) {
     Guard g(c);
+    if (n > 0xffffffffull || first_exponent > 0xffffffffull - n) return fail(c, KZGB_ERR_GENERIC, "kzgb_fr_powers_dev: exponent range exceeds 32 bits");
     Fr b;
     memcpy(b.l, base_mont, 32);
     fr_powers_launch((Fr*)out_dev, (uint32_t)n, &b, c->lanes[0].st, (uint32_t)first_exponent);
@@ -1268,8 +1390,7 @@ static int batch_impl(kzgb_ctx* c, const uint8_t* const* blobs_dev, const uint8_
     // Small blobs (<= 2^17 Fr): runs of equal-size blobs are processed as groups, every kernel of a phase
     // launched ONCE for the whole group (batched conversion, evaluation/quotient and MSM with one bucket set
     // per blob) -- one blob at a time they are latency-bound (bucket-reduction tail, host hand-off per MSM).
-    static const int group_env = getenv("KZGB_GROUP") ? atoi(getenv("KZGB_GROUP")) : -1;
-    const int group_opt = g_group.load() >= 0 ? g_group.load() : group_env;
+    const int group_opt = g_group.load();
     std::vector<std::pair<size_t, size_t>> groups;  // (first blob, blobs)
     if (group_opt != 0 && count >= 2 && max_n <= ((size_t)1 << 17) && c->auto_precompute && c->srs_n <= ((size_t)1 << 22)) {
         for (size_t i = 0; i < count;) {
@@ -1284,7 +1405,7 @@ static int batch_impl(kzgb_ctx* c, const uint8_t* const* blobs_dev, const uint8_
     }
     // lanes in flight: 3 keep the GPU full on 16 MiB blobs; small blobs are latency-bound per lane
     // (bucket reduction, host hand-offs), so they get more
-    static const int lanes_env = getenv("KZGB_LANES") ? atoi(getenv("KZGB_LANES")) : 0;
+    const int lanes_env = g_lanes.load();
     int want_lanes = lanes_env > 0 ? lanes_env : ((max_n >= ((size_t)1 << 18) && !lane_wait_polls()) ? 4 : 6);
     if (!groups.empty() && lanes_env <= 0) want_lanes = 3;
     int n_lanes = (int)std::min<size_t>(groups.empty() ? count : groups.size(), (size_t)std::min(want_lanes, MAX_LANES));
@@ -1299,15 +1420,15 @@ static int batch_impl(kzgb_ctx* c, const uint8_t* const* blobs_dev, const uint8_
         if (rc) return rc;
         if (!c->lag[logn].table) all_lagrange = false;
     }
-    if (!all_lagrange && c->auto_precompute && (!c->wtable || max_n > c->wt_n) && c->srs_n <= ((size_t)1 << 22)) {
-        rc = do_precompute(c, std::min(c->srs_n, next_pow2(max_n)), 0);
+    if (!all_lagrange && c->auto_precompute && (!c->wtable || c->wt_first != 0 || max_n > c->wt_n) && c->srs_n <= ((size_t)1 << 22)) {
+        rc = do_precompute(c, 0, std::min(c->srs_n, next_pow2(max_n)), 0);
         if (rc && rc != KZGB_ERR_DEVICE) return rc;
     }
     for (size_t gi = 0; gi < groups.size(); gi++) {  // the batched MSM needs a window table for every size
         size_t n = blob_poly_len(lens[groups[gi].first]);
         int logn = log2_exact(n);
         bool lag_ok = c->lag[logn].table && g_lagrange.load();
-        if (!lag_ok && !(c->wtable && n <= c->wt_n)) { groups.clear(); break; }
+        if (!lag_ok && !(c->wtable && c->wt_first == 0 && n <= c->wt_n)) { groups.clear(); break; }
     }
 
     // host hashing pool: transcript midstates (everything but the commitment)
@@ -1332,6 +1453,11 @@ static int batch_impl(kzgb_ctx* c, const uint8_t* const* blobs_dev, const uint8_
 
     std::vector<int> lane_rc(n_lanes, KZGB_OK);
     bool failed = false;
+    struct LanesRunning {  // from here on the lane threads only READ the context's tables (msm_enqueue builds none)
+        kzgb_ctx* c;
+        explicit LanesRunning(kzgb_ctx* ctx) : c(ctx) { c->lanes_running.store(true); }
+        ~LanesRunning() { c->lanes_running.store(false); }
+    } lanes_running(c);
     if (!groups.empty()) {
         // ---- small blobs: groups of equal-size blobs, each phase of a group is ONE batched launch set ----
         std::atomic<size_t> next_group{0};
@@ -1510,6 +1636,7 @@ static int batch_impl(kzgb_ctx* c, const uint8_t* const* blobs_dev, const uint8_
     for (auto& t : lane_threads) t.join();
     next_hash.store(count);
     for (auto& t : hashers) t.join();
+    if (c->batch_bytes.cap > ((size_t)g_batch_keep_mib.load() << 20)) c->batch_bytes.release();  // bounded residency between calls
     for (int li = 0; li < n_lanes; li++) if (lane_rc[li]) return lane_rc[li];
     return KZGB_OK;
 }
@@ -1596,7 +1723,7 @@ int kzgb_verify_batch_rlc(kzgb_ctx* c, const uint8_t* const* blobs, const size_t
     size_t i0 = 0;
     while (i0 < m) {
         size_t n = ns[i0], i1 = i0;
-        while (i1 < m && ns[i1] == n && (i1 - i0 + 1) * n <= std::max(budget_elems, n)) i1++;
+        while (i1 < m && ns[i1] == n && (i1 - i0 + 1) * n <= std::max(budget_elems, n) && i1 - i0 < 65535) i1++;  // b is a gridDim.y
         size_t b = i1 - i0;
         int logn = log2_exact(n);
         CK(c, L.evals.reserve(b * n * sizeof(Fr)));
@@ -1837,8 +1964,19 @@ int kzgb_set_option(const char* name, long value) {
     if (!strcmp(name, "fs_force_generic")) { fs_set_force_flag((int)value); return KZGB_OK; }
     if (!strcmp(name, "eval_structured")) { eval_set_structured((int)value); return KZGB_OK; }
     if (!strcmp(name, "group")) { g_group.store((int)value); return KZGB_OK; }
+    if (!strcmp(name, "lanes")) { g_lanes.store(value < 0 ? 0 : (int)value); return KZGB_OK; }
+    if (!strcmp(name, "hash_threads")) { g_hash_threads.store(value < 0 ? 0 : (int)value); return KZGB_OK; }
+    if (!strcmp(name, "lane_wait")) { g_lane_wait.store(value < 0 ? -1 : (value ? 1 : 0)); return KZGB_OK; }
+    if (!strcmp(name, "stream_priority")) { g_stream_priority.store(value != 0); return KZGB_OK; }
+    if (!strcmp(name, "l2_fetch_64")) { g_l2_fetch_64.store(value != 0); return KZGB_OK; }
+    if (!strcmp(name, "batch_keep_mib")) { g_batch_keep_mib.store(value < 0 ? 0 : value); return KZGB_OK; }
+    if (!strcmp(name, "fs_quad")) { fs_set_quad((int)value); return KZGB_OK; }
+    if (!strcmp(name, "group_members")) { g_group_members.store(value < 1 ? 1 : (int)value); return KZGB_OK; }
     if (!strcmp(name, "lagrange")) { g_lagrange.store(value != 0); return KZGB_OK; }
+    if (!strcmp(name, "lagrange_after")) { g_lagrange_after.store(value < 1 ? 1 : (int)value); return KZGB_OK; }
+    if (!strcmp(name, "lagrange_budget_mib")) { g_lagrange_budget_mib.store(value < 0 ? 0 : value); return KZGB_OK; }
     if (!strcmp(name, "acc_waves")) { msm_set_acc_waves((int)value); return KZGB_OK; }
+    if (!strcmp(name, "msm_debug_sync")) { msm_set_debug_sync((int)value); return KZGB_OK; }
     return KZGB_ERR_GENERIC;
 }
 

@@ -229,11 +229,13 @@ __global__ void __launch_bounds__(128) k_fs_challenges_quad(const Fr* __restrict
 // tests: flag every polynomial as "z in the domain" so the device-side choice takes the generic inverses everywhere
 static std::atomic<int> g_fs_force_flag{0};
 void fs_set_force_flag(int on) { g_fs_force_flag.store(on != 0); }
+static std::atomic<int> g_fs_quad{1};  // 1: four lanes per blob (k_fs_challenges_quad), 0: one thread per blob
+void fs_set_quad(int on) { g_fs_quad.store(on != 0); }
 
 void fs_challenges_launch(const Fr* evals, uint32_t n, int logn, uint32_t batch, const uint8_t* commit32_dev,
                           const Fr* ninv_mont_host, Fr* z_out, Fr* tinv_out, cudaStream_t st, uint32_t* in_domain_out) {
     if (!batch) return;
-    static const int quad = getenv("KZGB_FS_QUAD") ? atoi(getenv("KZGB_FS_QUAD")) : 1;
+    const int quad = g_fs_quad.load();
     if (quad && n >= 16)
         k_fs_challenges_quad<<<(batch * 4 + 127) / 128, 128, 0, st>>>(evals, n, logn, batch, commit32_dev, *ninv_mont_host, z_out, tinv_out, in_domain_out, g_fs_force_flag.load() != 0);
     else

@@ -54,6 +54,7 @@ void msm_workspace_carve(const MsmPlan& p, void* base, MsmWorkspace* ws);
 MsmPlan msm_make_plan(uint32_t n, int c, bool fixed_base, uint32_t table_stride, uint32_t base_offset, uint32_t batch = 0);
 // waves of accumulate blocks (4 blocks of 128 threads per SM and wave) the sorted list is cut into; default 4
 void msm_set_acc_waves(int waves);
+void msm_set_debug_sync(int on);
 
 // scalars: n Fr (Montgomery unless scalars_canonical).  Result: ws.set_sums[0..sets) on the device.
 // The optional events bracket the bucket-accumulation kernel (roofline timing).
@@ -119,6 +120,7 @@ void eval_set_structured(int on);
 // primitives/src/helpers.rs:411-472): z_out[k] (Montgomery) and tinv_out[k] = 1/(z^n - 1) (or z/n in the
 // domain).  commit32_dev: batch x 32 bytes, arkworks-compressed commitments.
 void fs_set_force_flag(int on);
+void fs_set_quad(int on);
 // in_domain_out (optional, batch words): 1 where z_k turned out to be a root of the domain.
 void fs_challenges_launch(const Fr* evals, uint32_t n, int logn, uint32_t batch, const uint8_t* commit32_dev,
                           const Fr* ninv_mont_host, Fr* z_out, Fr* tinv_out, cudaStream_t st, uint32_t* in_domain_out = nullptr);

@@ -23,6 +23,7 @@
 // The caller copies `sets` XYZZ points (128 B each) back and finishes on the host.
 // One launch set can also carry `batch` independent fixed-base MSMs over the same table (MsmPlan.batch_n):
 // scalar i belongs to MSM i / batch_n, which owns bucket set i / batch_n -- how runs of small blobs are committed.
+#include <cstdio>
 #include "kzgb_internal.hpp"
 
 namespace kzgb {
@@ -358,7 +359,10 @@ __device__ __forceinline__ Fq fq_sel(bool c, const Fq& a, const Fq& b) {
 __device__ __noinline__ Fq quad_dbl(Fq a) {
     const int lane = threadIdx.x & 31, r = lane & 3, base = lane & ~3;
     const bool z = fe_is_zero(a);
-    const bool inf = __shfl_sync(FULL, z, base + 2) || __shfl_sync(FULL, z, base + 1);  // ZZ == 0 or Y == 0
+    // (two statements: `a || b` would let the lanes of an identity quad skip the second full-mask shuffle -- a deadlock)
+    const bool zz0 = __shfl_sync(FULL, z, base + 2);
+    const bool y0 = __shfl_sync(FULL, z, base + 1);
+    const bool inf = zz0 || y0;
     Fq u; fe_dbl(u, a);                                   // lane 1: U = 2Y
     const Fq s1 = fq_sel(r == 1, u, a);
     Fq m1; fe_mul(m1, s1, s1);                            // lane 0: X^2, lane 1: V = U^2
@@ -541,6 +545,15 @@ __global__ void __launch_bounds__(32) k_reduce_final(const XYZZ* __restrict__ gr
 
 // ---------------------------------------------------------------------------------
 static std::atomic<int> g_acc_waves{4};
+static std::atomic<int> g_debug_sync{0};  // option "msm_debug_sync": synchronise and report after every kernel of msm_launch
+void msm_set_debug_sync(int on) { g_debug_sync.store(on); }
+#define KZ_DBG(name)                                                                                         \
+    do {                                                                                                     \
+        if (g_debug_sync.load()) {                                                                           \
+            cudaError_t e1_ = cudaStreamSynchronize(st), e2_ = cudaStreamSynchronize(sa);                    \
+            fprintf(stderr, "[msm] %s: %s / %s\n", name, cudaGetErrorString(e1_), cudaGetErrorString(e2_)); \
+        }                                                                                                    \
+    } while (0)
 void msm_set_acc_waves(int waves) { g_acc_waves.store(waves < 1 ? 1 : (waves > 64 ? 64 : waves)); }
 
 MsmPlan msm_make_plan(uint32_t n, int c, bool fixed_base, uint32_t table_stride, uint32_t base_offset, uint32_t batch) {
@@ -623,12 +636,14 @@ void msm_launch(const MsmPlan& p, const MsmWorkspace& ws, const Fr* scalars, boo
         }
     }
     if (p.n) k_scatter<<<gb, 256, 0, st>>>(ws.canon, p, ws.cursor, ws.sorted);
+    KZ_DBG("sort");
     if (split) { cudaEventRecord(ev_fork, st); cudaStreamWaitEvent(sa, ev_fork, 0); }
     if (ev_acc_begin) cudaEventRecord(ev_acc_begin, sa);
     k_accumulate<<<(p.acc_threads + 127) / 128, 128, 0, sa>>>(ws.sorted, ws.hist, table, p.nbuckets, p.acc_threads, p.chunk,
                                                               ws.buckets, ws.partial);
     if (ev_acc_end) cudaEventRecord(ev_acc_end, sa);
     if (split) { cudaEventRecord(ev_join, sa); cudaStreamWaitEvent(st, ev_join, 0); }
+    KZ_DBG("accumulate");
     {
         const uint32_t long_cap = p.acc_threads / LONG_SPAN + 4;  // a long bucket owns >= LONG_SPAN chunks
         uint32_t* long_count = ws.long_list;                      // [0] = counter, [1..] = queue
@@ -638,10 +653,14 @@ void msm_launch(const MsmPlan& p, const MsmWorkspace& ws, const Fr* scalars, boo
         k_bucket_fix_long<<<LONG_BLOCKS, LONG_THREADS, 0, st>>>(ws.hist, p.chunk, ws.buckets, ws.partial, long_count,
                                                                   ws.long_list + 1, long_cap);
     }
+    KZ_DBG("bucket_fix");
     k_reduce_lines<<<dim3((unsigned)lines_per_set(p), (unsigned)p.sets), LINE_THREADS, 0, st>>>(ws.buckets, p.a_bits, p.h_bits, ws.line_sums);
+    KZ_DBG("reduce_lines");
     k_reduce_groups<<<dim3((unsigned)p.ngroups, (unsigned)p.sets), GROUP_THREADS, 0, st>>>(ws.line_sums, p.a_bits, p.h_bits, p.ngroups,
                                                                                           ws.group_sums);
+    KZ_DBG("reduce_groups");
     k_reduce_final<<<p.sets, 32, 0, st>>>(ws.group_sums, p.ngroups, ws.set_sums);
+    KZ_DBG("reduce_final");
     g_launch_count += 6;  // accumulate, bucket_fix, bucket_fix_long, reduce_lines, reduce_groups, reduce_final
 }
 

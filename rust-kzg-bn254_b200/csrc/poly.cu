@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_eval_inverses(const Fr* __rest
 // among all of them and the lower ones pairwise -> (k - 3) + 30 multiplications per 16 inverses (2.8 per
 // element instead of ~10 for the prefix/suffix products), no block or grid level products at all.
 static constexpr int EV2_THREADS = 128;
-static std::atomic<int> g_eval_structured{getenv("KZGB_EVAL_STRUCTURED") ? atoi(getenv("KZGB_EVAL_STRUCTURED")) : 1};
+static std::atomic<int> g_eval_structured{1};
 void eval_set_structured(int on) { g_eval_structured.store(on != 0); }
 static constexpr int ZP_STRIDE = 32;  // Z_j slots per polynomial
 
