@@ -148,6 +148,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--blobs-per-step", type=int, default=16)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-msm-leg", action="store_true", help="skip the config-4 leg (2^26-point MSM by point range) of the default line")
     ap.add_argument("--window-bits", type=int, default=0, help="fixed-base window bits c (0 = the library's choice)")
     ap.add_argument("--option", action="append", default=[], metavar="NAME=VALUE", help="kzgb_set_option before the run (sweeps)")
     ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4", "c5"],
@@ -269,6 +270,16 @@ def main():
     assert cm1.raw == out_dev[0][:32] and pf1.raw == out_dev[1][:32]
 
     if rank != 0:
+        # the other ranks go straight to the config-4 leg (rank 0 joins after its single-GPU roofline measurements)
+        del host_blobs, dev_blobs
+        eng.close()
+        torch.cuda.empty_cache()
+        if not args.skip_msm_leg:
+            import bench_configs
+
+            margs = argparse.Namespace(**vars(args))
+            margs.log_n, margs.skip_cpu_baseline, margs.window_bits = 0, True, 0
+            bench_configs.measure_c4(margs, torch, dist, world, rank, local_rank, pkg)
         if world > 1:
             dist.destroy_process_group()
         return
@@ -288,16 +299,17 @@ def main():
     peak = imad.value / IMAD_PER_FQMUL / 1e9
     adds_per_launch = acc_adds.value / max(1, acc_n.value)
     avg_acc_ms = acc_ms.value / max(1, acc_n.value)
-    achieved = FQMUL_PER_MADD * adds_per_launch / (avg_acc_ms * 1e-3) / 1e9 if avg_acc_ms else 0.0
     # isolated (single stream, nothing else on the GPU) timing of the same kernel
     iso_total, iso_acc = C.c_double(0), C.c_double(0)
     eng.check(lib.kzgb_bench_msm(eng.h, n, 5, C.byref(iso_total), C.byref(iso_acc)))
     achieved_iso = FQMUL_PER_MADD * adds_per_launch / (iso_acc.value * 1e-3) / 1e9 if iso_acc.value else 0.0
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    traffic_src = None
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("k_accumulate_dram_bytes_per_launch")
+            tj = json.load(open(tpath))
+            traffic, traffic_src = tj.get("k_accumulate_dram_bytes_per_launch"), tj.get("source")
         except Exception:
             traffic = None
     # Fr NTT: the batched 2^16 transforms of config 3 (2 GiB, far beyond L2) are the HBM-bound case;
@@ -325,9 +337,16 @@ def main():
     roofline = {
         "kernel": "k_accumulate (MSM bucket accumulation, XYZZ += affine)", "bound": "integer-pipe (IMAD)",
         "achieved": achieved_iso, "peak": peak, "unit": "GFqmul/s", "frac": achieved_iso / peak if peak else None,
-        "traffic": traffic,
-        "achieved_in_pipeline": achieved, "frac_in_pipeline": achieved / peak if peak else None,
-        "launch_ms_isolated": iso_acc.value, "launch_ms_in_pipeline": avg_acc_ms, "msm_total_ms_isolated": iso_total.value,
+        "traffic": traffic, "traffic_source": traffic_src,
+        "launch_ms_isolated": iso_acc.value, "msm_total_ms_isolated": iso_total.value,
+        "launch_ms_in_pipeline_overlapping": avg_acc_ms,
+        "in_pipeline_note": "inside the timed region the accumulate kernels of the 4 lanes run CONCURRENTLY (2.1 in flight on average, "
+                            "scripts/trace_pipeline.py), so their per-launch event times overlap and are not additive; the step-level figure is below",
+        "step": {"algorithmic_fqmul_per_step": FQMUL_PER_MADD * acc_adds.value / args.steps,
+                 "achieved": FQMUL_PER_MADD * acc_adds.value / (dev_ms * 1e-3) / 1e9,
+                 "frac": (FQMUL_PER_MADD * acc_adds.value / (dev_ms * 1e-3) / 1e9) / peak if peak else None,
+                 "note": "all point additions of the timed region (exact count read back from the device) x 10 Fq-mul / its duration: "
+                         "the fraction of the model roof the WHOLE pipeline runs at, sort / stitch / bucket reduction / evaluation kernels included"},
         "algorithmic_fqmul_per_launch": FQMUL_PER_MADD * adds_per_launch, "point_adds_per_launch": adds_per_launch,
         "executed_note": "algorithmic count (SURVEY 8d): 10 Fq-mul per XYZZ += affine; the kernel executes 10 products and 9 Montgomery reductions (Y3 is one reduction of a difference of two products)",
         "peak_source": "measured live: dependency-free IMAD chains / 136 IMAD per 8x32-bit Montgomery multiplication (SURVEY.md 8d model)",
@@ -362,6 +381,18 @@ def main():
                         "literal_g1_ifft_commit_s_at_2p12": lit12,
                         "literal_g1_ifft_commit_s_at_2p19_extrapolated": lit12 * (n * LOG_N) / (n12 * 12.0)}
 
+    # config-4 leg: the second half of BASELINE's metric ("G1 MSM Mpts/s at 1/2/4/8") on the same line
+    msm_leg = None
+    del host_blobs, dev_blobs
+    eng.close()
+    torch.cuda.empty_cache()
+    if not args.skip_msm_leg:
+        import bench_configs
+
+        margs = argparse.Namespace(**vars(args))
+        margs.log_n, margs.skip_cpu_baseline, margs.window_bits = 0, True, 0
+        msm_leg = bench_configs.measure_c4(margs, torch, dist, world, rank, local_rank, pkg)
+
     line = {
         "metric": "blob commits+proofs/s (2^19 Fr, 16 MiB)", "value": value, "unit": "blobs/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
@@ -377,6 +408,7 @@ def main():
                 "ms_per_step": e2e_ms / args.steps, "wall_ms_per_step": e2e_wall / args.steps},
         "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "roofline_ntt": roofline_ntt,
         "cpu_baseline": cpu_baseline,
+        "extra": {"msm_mpts": msm_leg},
         "wall_ms_per_step": dev_wall / args.steps, "setup_s": setup_s,
         "single_blob_latency_ms": {"value": single_blob_ms, "note": "one 16 MiB blob through kzgb_commit_and_prove_blobs from host memory; "
                                    "bounded below by the sequential SHA-256 of the 16 MiB Fiat-Shamir transcript on one host core (~9 ms), "

@@ -194,26 +194,6 @@ int kzgb_g1_to_gnark_be(const uint64_t xy[8], uint8_t inf, uint8_t out32[32]);
 /* helpers::validate_g1_point (helpers.rs:694-708) for `n` points on the GPU. */
 int kzgb_validate_g1_points(kzgb_ctx* ctx, const uint64_t* xy, const uint8_t* inf, size_t n);
 
-/* ---- measurement hooks (bench.py) ---------------------------------------------------------- */
-/* Runs an integer-pipe microbenchmark and returns achieved operations per second.
- * kind 0: IMAD, 1: IMAD.WIDE, 2: carry-chained IMAD.WIDE.X, 3: Fq Montgomery multiplications. */
-int kzgb_microbench(kzgb_ctx* ctx, int kind, double* ops_per_second);
-/* Times `reps` back-to-back SRS MSMs of n points on device-resident scalars with CUDA events on the
- * context's stream; returns mean milliseconds per MSM of the whole pipeline and of the bucket
- * accumulation kernel alone. */
-int kzgb_bench_msm(kzgb_ctx* ctx, size_t n, int reps, double* ms_total, double* ms_accumulate);
-/* Times `reps` (I)NTTs of `batch` transforms of size 2^logn back to back on device-resident data
- * (alternating forward / inverse) with CUDA events; returns mean milliseconds per batched call. */
-int kzgb_bench_ntt(kzgb_ctx* ctx, int logn, size_t batch, int reps, double* ms_per_call);
-/* Number of kernels this library has launched since it was loaded. */
-uint64_t kzgb_launch_count(const kzgb_ctx* ctx);
-/* Device-side stopwatch (CUDA events) spanning every stream of the context: all work queued between
- * begin and end lies inside the measured interval. */
-int kzgb_timer_begin(kzgb_ctx* ctx);
-int kzgb_timer_end(kzgb_ctx* ctx, double* ms_out);
-/* Bucket-accumulation kernel statistics since the last reset: summed CUDA-event duration of the
- * launches (each bracketed on its own stream), launch count, and point additions performed. */
-int kzgb_stats(kzgb_ctx* ctx, double* acc_ms, uint64_t* acc_launches, uint64_t* acc_point_adds, int reset);
 /* Process-wide switches that never change results, only which exact code path produces them:
  *   "fs_device"            -1 auto (default), 0 host SHA-256 pool, 1 device kernel for the per-blob
  *                          Fiat-Shamir challenges of kzgb_verify_batch_rlc (auto: >= 256 blobs of <= 2^13 Fr)
@@ -238,6 +218,9 @@ int kzgb_stats(kzgb_ctx* ctx, double* acc_ms, uint64_t* acc_launches, uint64_t* 
  *   "l2_fetch_64"          1 (default): contexts that own their stream set the device's L2 fetch granularity to 64 B
  *                          (random 64-byte gathers) and restore it when the last of them is destroyed
  *   "batch_keep_mib"       blob staging memory kept between batch calls (default 4096)
+ *   "pipelined_upload"     1 (default): kzgb_msm_srs / kzgb_msm_srs_range calls of >= 2^22 points over a window table upload
+ *                          their host scalars in 4 or 8 chunks, each chunk's sort + bucket accumulation overlapping the next
+ *                          chunk's copy (bucket sums folded, one reduction); 0: one copy, then one MSM
  *   "fs_quad"              1 (default): four lanes per blob in the device-side Fiat-Shamir hashing
  * The library reads NO environment variables of its own (torchrun's LOCAL_WORLD_SIZE is consulted for "lane_wait" auto).
  * Unknown names return KZGB_ERR_GENERIC. */

@@ -7,6 +7,7 @@
 // the Fiat-Shamir transcripts (SHA-256 of a 16 MiB blob is ~9 ms of inherently serial CPU work,
 // several times the GPU time of the same blob, so it must overlap).
 #include <algorithm>
+#include <chrono>
 #include <condition_variable>
 #include <cstdio>
 #include <cstring>
@@ -17,6 +18,7 @@
 #include <vector>
 
 #include "../../include/kzg_bn254_b200.h"
+#include "../../include/kzg_bn254_b200_bench.h"
 #include "kzgb_internal.hpp"
 #include "sha256.hpp"
 
@@ -51,7 +53,7 @@ struct Lane {
                                     // slip in between its blocks instead of queueing behind the whole grid
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool own_stream = false;
-    DevBuf bytes, evals, work, ntt_scratch, eval_scratch, msm_ws, small, bases;
+    DevBuf bytes, evals, work, ntt_scratch, eval_scratch, msm_ws, small, bases, bucket_total;
     XYZZ* h_sets = nullptr;   // pinned
     uint32_t* h_entries = nullptr;  // pinned: length of the sorted list of the MSM in flight (= its point additions)
     Fr* h_fr = nullptr;       // pinned, 16 elements
@@ -89,6 +91,17 @@ struct kzgb_ctx {
     int logN = 0;
     // timer
     cudaEvent_t t0 = nullptr, t1 = nullptr;
+    // upload stream + double-buffer fences of msm_srs_host_pipelined
+    cudaStream_t copy_st = nullptr;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+    // timeline trace (kzgb_trace_begin / kzgb_trace_end, include/kzg_bn254_b200_bench.h): device events and host time
+    // stamps of every MSM of every lane, for reading pipeline stalls without a system profiler
+    struct TraceRec { int lane, kind; cudaEvent_t ev; double host_ms; };
+    std::atomic<bool> trace_on{false};
+    std::mutex trace_mu;
+    std::vector<TraceRec> trace;
+    cudaEvent_t trace_base = nullptr;
+    std::chrono::steady_clock::time_point trace_host0;
 };
 
 namespace {
@@ -111,6 +124,7 @@ std::atomic<int> g_hash_threads{0};     // host SHA-256 pool threads per batch c
 std::atomic<int> g_lane_wait{-1};       // -1 auto, 0 spin on the stream, 1 poll with short sleeps
 std::atomic<int> g_stream_priority{1};  // 1: bucket accumulation on a low-priority stream of its own
 std::atomic<int> g_l2_fetch_64{1};
+std::atomic<int> g_pipelined_upload{1};   // 1: host scalars of MSMs of >= 2^22 points over a window table are uploaded in overlapped chunks
 std::atomic<long> g_batch_keep_mib{4096};  // blob staging buffer of kzgb_commit_and_prove_blobs kept between calls up to this size      // 1: contexts that own their stream set the L2 fetch granularity to 64 B
 int fail(kzgb_ctx* c, int code, const std::string& msg) {
     if (c) { std::lock_guard<std::mutex> lk(g_err_mu); c->err = msg; }
@@ -277,7 +291,7 @@ int lane_init(kzgb_ctx* c, Lane& L, cudaStream_t st) {
 }
 void lane_destroy(Lane& L) {
     L.bytes.release(); L.evals.release(); L.work.release(); L.ntt_scratch.release();
-    L.eval_scratch.release(); L.msm_ws.release(); L.small.release(); L.bases.release();
+    L.eval_scratch.release(); L.msm_ws.release(); L.small.release(); L.bases.release(); L.bucket_total.release();
     if (L.h_sets) cudaFreeHost(L.h_sets);
     if (L.h_fr) cudaFreeHost(L.h_fr);
     if (L.h_entries) cudaFreeHost(L.h_entries);
@@ -306,6 +320,29 @@ void lane_collect_acc(Lane& L) {
         if (cudaEventElapsedTime(&ms, L.ev0, L.ev1) == cudaSuccess) { L.acc_ms += ms; L.acc_launches++; L.acc_adds += *L.h_entries; }
         L.ev_pending = false;
     }
+}
+
+// ---------------------------------------------------------------- timeline trace
+// kinds: 0 sort begins, 1 accumulate begins, 2 accumulate ends, 3 MSM ends (device events on the lane's streams);
+//        10 host: MSM enqueued, 11 host: lane woke up with the result, 12 host: result finished (affine, serialised)
+int lane_index(kzgb_ctx* c, const Lane& L) { return (int)(&L - &c->lanes[0]); }
+cudaEvent_t trace_mark(kzgb_ctx* c, const Lane& L, int kind, cudaStream_t st) {
+    if (!c->trace_on.load()) return nullptr;
+    cudaEvent_t ev = nullptr;
+    if (st) { if (cudaEventCreate(&ev) != cudaSuccess) return nullptr; cudaEventRecord(ev, st); }
+    double host = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - c->trace_host0).count();
+    std::lock_guard<std::mutex> lk(c->trace_mu);
+    c->trace.push_back({lane_index(c, L), kind, ev, host});
+    return ev;
+}
+// an event the caller records itself (accumulate begin / end inside msm_launch)
+cudaEvent_t trace_event(kzgb_ctx* c, const Lane& L, int kind) {
+    if (!c->trace_on.load()) return nullptr;
+    cudaEvent_t ev = nullptr;
+    if (cudaEventCreate(&ev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lk(c->trace_mu);
+    c->trace.push_back({lane_index(c, L), kind, ev, -1.0});
+    return ev;
 }
 
 // ---------------------------------------------------------------- twiddles
@@ -503,8 +540,12 @@ int msm_enqueue(kzgb_ctx* c, Lane& L, const Fr* d_scalars, bool canonical, size_
     MsmWorkspace ws;
     msm_workspace_carve(p, L.msm_ws.p, &ws);
     lane_collect_acc(L);
-    msm_launch(p, ws, d_scalars, canonical, table, L.st, L.ev0, L.ev1, L.st_acc, L.ev_fork, L.ev_join);
-    L.ev_pending = true;
+    trace_mark(c, L, 0, L.st);
+    cudaEvent_t tr1 = trace_event(c, L, 1), tr2 = trace_event(c, L, 2);
+    msm_launch(p, ws, d_scalars, canonical, table, L.st, tr1 ? tr1 : L.ev0, tr2 ? tr2 : L.ev1, L.st_acc, L.ev_fork, L.ev_join);
+    trace_mark(c, L, 3, L.st);
+    trace_mark(c, L, 10, nullptr);
+    L.ev_pending = !tr1;
     CK(c, cudaMemcpyAsync(L.h_entries, ws.hist + p.nbuckets, 4, cudaMemcpyDeviceToHost, L.st));
     CK(c, cudaMemcpyAsync(L.h_sets, ws.set_sums, sizeof(XYZZ) * p.sets, cudaMemcpyDeviceToHost, L.st));
     job->plan = p;
@@ -536,6 +577,7 @@ int lane_wait(kzgb_ctx* c, Lane& L) {
 int msm_finish(kzgb_ctx* c, Lane& L, const MsmJob& job, Affine* out) {
     if (!job.active) { aff_set_inf(*out); return KZGB_OK; }
     { int rc = lane_wait(c, L); if (rc) return rc; }
+    trace_mark(c, L, 11, nullptr);
     lane_collect_acc(L);
     const MsmPlan& p = job.plan;
     XYZZ acc = L.h_sets[p.sets - 1];
@@ -544,6 +586,7 @@ int msm_finish(kzgb_ctx* c, Lane& L, const MsmJob& job, Affine* out) {
         xyzz_add(acc, L.h_sets[w]);
     }
     xyzz_to_affine(*out, acc);
+    trace_mark(c, L, 12, nullptr);
     return KZGB_OK;
 }
 
@@ -553,6 +596,59 @@ int msm_blocking(kzgb_ctx* c, Lane& L, const Fr* d_scalars, bool canonical, size
     int rc = msm_enqueue(c, L, d_scalars, canonical, first, n, var_bases, &job);
     if (rc) return rc;
     return msm_finish(c, L, job, out);
+}
+
+// A large fixed-base MSM whose scalars live in HOST memory (KZG::commit_coeff_form on a 2^26-coefficient polynomial,
+// prover/src/kzg.rs:107-125): uploading 32 n bytes first and only then sorting leaves the GPU idle for the length of
+// the copy (2 GiB at n = 2^26: ~40 ms in front of a 150 ms MSM).  Here the points are cut into S sub-ranges; the upload
+// of sub-range k+1 runs on a copy stream while sub-range k is sorted and accumulated (double-buffered staging), the
+// bucket sums of the sub-ranges are folded into one array (k_merge_buckets: one XYZZ addition per bucket and
+// sub-range) and reduced ONCE.  Only the first sub-range's upload is exposed.
+// Returns KZGB_OK with *done = false when the shape does not qualify (no table over the range, or too small to matter).
+int msm_srs_host_pipelined(kzgb_ctx* c, Lane& L, const uint64_t* scalars, size_t first, size_t n, Affine* out, bool* done) {
+    *done = false;
+    if (n < ((size_t)1 << 22) || !g_pipelined_upload.load()) return KZGB_OK;
+    if (!(c->wtable && first >= c->wt_first && first + n <= c->wt_first + c->wt_n)) return KZGB_OK;
+    const size_t S = n >= ((size_t)1 << 24) ? 8 : 4;
+    const size_t per = ((n + S - 1) / S + 31) & ~(size_t)31;
+    if ((uint64_t)per * ((255 + c->wt_c - 1) / c->wt_c) >= 0xfff00000ull) return KZGB_OK;
+    if (!c->copy_st) {
+        CK(c, cudaStreamCreateWithFlags(&c->copy_st, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; k++) {
+            CK(c, cudaEventCreateWithFlags(&c->ev_copied[k], cudaEventDisableTiming));
+            CK(c, cudaEventCreateWithFlags(&c->ev_consumed[k], cudaEventDisableTiming));
+        }
+    }
+    const MsmPlan p0 = msm_make_plan((uint32_t)per, c->wt_c, true, (uint32_t)c->wt_n, (uint32_t)(first - c->wt_first));
+    CK(c, L.msm_ws.reserve(msm_workspace_bytes(p0)));
+    CK(c, L.work.reserve(2 * per * sizeof(Fr)));
+    CK(c, L.bucket_total.reserve((size_t)p0.nbuckets * sizeof(XYZZ)));
+    MsmWorkspace ws;
+    msm_workspace_carve(p0, L.msm_ws.p, &ws);
+    Fr* stage[2] = {(Fr*)L.work.p, (Fr*)L.work.p + per};
+    XYZZ* total = (XYZZ*)L.bucket_total.p;
+    CK(c, cudaEventRecord(c->ev_consumed[0], L.st));  // the staging buffers are free once earlier work on the lane is done
+    CK(c, cudaEventRecord(c->ev_consumed[1], L.st));
+    size_t k = 0;
+    for (size_t off = 0; off < n; off += per, k++) {
+        const size_t cnt = std::min(per, n - off);
+        const int b = (int)(k & 1);
+        CK(c, cudaStreamWaitEvent(c->copy_st, c->ev_consumed[b], 0));
+        CK(c, cudaMemcpyAsync(stage[b], scalars + 4 * off, cnt * sizeof(Fr), cudaMemcpyHostToDevice, c->copy_st));
+        CK(c, cudaEventRecord(c->ev_copied[b], c->copy_st));
+        CK(c, cudaStreamWaitEvent(L.st, c->ev_copied[b], 0));
+        const MsmPlan p = msm_make_plan((uint32_t)cnt, c->wt_c, true, (uint32_t)c->wt_n, (uint32_t)(first + off - c->wt_first));
+        msm_launch_buckets(p, ws, stage[b], false, c->wtable, L.st, nullptr, nullptr, L.st_acc, L.ev_fork, L.ev_join);
+        CK(c, cudaEventRecord(c->ev_consumed[b], L.st));
+        if (k == 0) CK(c, cudaMemcpyAsync(total, ws.buckets, (size_t)p0.nbuckets * sizeof(XYZZ), cudaMemcpyDeviceToDevice, L.st));
+        else msm_merge_buckets(total, ws.buckets, p0.nbuckets, L.st);
+    }
+    msm_launch_reduce(p0, ws, total, L.st);
+    CK(c, cudaMemcpyAsync(L.h_sets, ws.set_sums, sizeof(XYZZ), cudaMemcpyDeviceToHost, L.st));
+    { int rc = lane_wait(c, L); if (rc) return rc; }
+    xyzz_to_affine(*out, L.h_sets[0]);
+    *done = true;
+    return KZGB_OK;
 }
 
 // `batch` independent fixed-base MSMs of n_per scalars each in ONE set of launches (one bucket set per
@@ -578,8 +674,12 @@ int msm_enqueue_batched(kzgb_ctx* c, Lane& L, const Fr* d_scalars, size_t n_per,
     MsmWorkspace ws;
     msm_workspace_carve(p, L.msm_ws.p, &ws);
     lane_collect_acc(L);
-    msm_launch(p, ws, d_scalars, false, table, L.st, L.ev0, L.ev1, L.st_acc, L.ev_fork, L.ev_join);
-    L.ev_pending = true;
+    trace_mark(c, L, 0, L.st);
+    cudaEvent_t tr1 = trace_event(c, L, 1), tr2 = trace_event(c, L, 2);
+    msm_launch(p, ws, d_scalars, false, table, L.st, tr1 ? tr1 : L.ev0, tr2 ? tr2 : L.ev1, L.st_acc, L.ev_fork, L.ev_join);
+    trace_mark(c, L, 3, L.st);
+    trace_mark(c, L, 10, nullptr);
+    L.ev_pending = !tr1;
     CK(c, cudaMemcpyAsync(L.h_entries, ws.hist + p.nbuckets, 4, cudaMemcpyDeviceToHost, L.st));
     CK(c, cudaMemcpyAsync(L.h_sets, ws.set_sums, sizeof(XYZZ) * p.sets, cudaMemcpyDeviceToHost, L.st));
     job->plan = p;
@@ -857,6 +957,10 @@ void kzgb_ctx_destroy(kzgb_ctx* c) {
     c->batch_bytes.release();
     if (c->t0) cudaEventDestroy(c->t0);
     if (c->t1) cudaEventDestroy(c->t1);
+    if (c->copy_st) cudaStreamDestroy(c->copy_st);
+    for (int k = 0; k < 2; k++) { if (c->ev_copied[k]) cudaEventDestroy(c->ev_copied[k]); if (c->ev_consumed[k]) cudaEventDestroy(c->ev_consumed[k]); }
+    if (c->trace_base) cudaEventDestroy(c->trace_base);
+    for (auto& r : c->trace) if (r.ev) cudaEventDestroy(r.ev);
     if (c->set_l2_limit) l2_limit_release(c->device);
     cudaSetDevice(prev);
     delete c;
@@ -1053,9 +1157,14 @@ int kzgb_msm_srs_range(kzgb_ctx* c, const uint64_t* scalars, size_t first, size_
     if (first > c->srs_n || n > c->srs_n - first) return fail(c, KZGB_ERR_SERIALIZATION, "polynomial length is not correct");
     Affine r;
     if (n == 0) { aff_set_inf(r); affine_to_abi(r, out_xy, out_inf); return KZGB_OK; }
-    CK(c, L.work.reserve(n * sizeof(Fr)));
-    CK(c, cudaMemcpyAsync(L.work.p, scalars, n * sizeof(Fr), cudaMemcpyHostToDevice, L.st));
-    int rc = msm_blocking(c, L, (Fr*)L.work.p, false, first, n, nullptr, &r);
+    bool done = false;
+    int rc = msm_srs_host_pipelined(c, L, scalars, first, n, &r, &done);  // large MSMs over a window table: upload overlapped
+    if (rc) return rc;
+    if (!done) {
+        CK(c, L.work.reserve(n * sizeof(Fr)));
+        CK(c, cudaMemcpyAsync(L.work.p, scalars, n * sizeof(Fr), cudaMemcpyHostToDevice, L.st));
+        rc = msm_blocking(c, L, (Fr*)L.work.p, false, first, n, nullptr, &r);
+    }
     if (rc) return rc;
     affine_to_abi(r, out_xy, out_inf);
     return KZGB_OK;
@@ -1942,6 +2051,38 @@ int kzgb_timer_end(kzgb_ctx* c, double* ms_out) {
     *ms_out = ms;
     return KZGB_OK;
 }
+int kzgb_trace_begin(kzgb_ctx* c) {
+    Guard g(c);
+    for (int i = 0; i < c->n_lanes; i++) CK(c, cudaStreamSynchronize(c->lanes[i].st));
+    for (auto& r : c->trace) if (r.ev) cudaEventDestroy(r.ev);
+    c->trace.clear();
+    if (!c->trace_base) CK(c, cudaEventCreate(&c->trace_base));
+    CK(c, cudaEventRecord(c->trace_base, c->lanes[0].st));
+    CK(c, cudaEventSynchronize(c->trace_base));
+    c->trace_host0 = std::chrono::steady_clock::now();
+    c->trace_on.store(true);
+    return KZGB_OK;
+}
+// out: 4 doubles per record (lane, kind, device ms since begin or -1, host ms since begin or -1)
+int kzgb_trace_end(kzgb_ctx* c, double* out, size_t capacity_records, size_t* n_records) {
+    Guard g(c);
+    c->trace_on.store(false);
+    for (int i = 0; i < c->n_lanes; i++) {
+        CK(c, cudaStreamSynchronize(c->lanes[i].st));
+        if (c->lanes[i].st_acc) CK(c, cudaStreamSynchronize(c->lanes[i].st_acc));
+    }
+    size_t n = 0;
+    for (auto& r : c->trace) {
+        float ms = -1.f;
+        if (r.ev && cudaEventElapsedTime(&ms, c->trace_base, r.ev) != cudaSuccess) { ms = -1.f; cudaGetLastError(); }
+        if (out && n < capacity_records) { out[4 * n] = r.lane; out[4 * n + 1] = r.kind; out[4 * n + 2] = ms; out[4 * n + 3] = r.host_ms; }
+        n++;
+        if (r.ev) cudaEventDestroy(r.ev);
+    }
+    c->trace.clear();
+    if (n_records) *n_records = n;
+    return KZGB_OK;
+}
 int kzgb_stats(kzgb_ctx* c, double* acc_ms, uint64_t* acc_launches, uint64_t* acc_point_adds, int reset) {
     Guard g(c);
     double ms = 0; uint64_t nl = 0, na = 0;
@@ -1969,6 +2110,7 @@ int kzgb_set_option(const char* name, long value) {
     if (!strcmp(name, "lane_wait")) { g_lane_wait.store(value < 0 ? -1 : (value ? 1 : 0)); return KZGB_OK; }
     if (!strcmp(name, "stream_priority")) { g_stream_priority.store(value != 0); return KZGB_OK; }
     if (!strcmp(name, "l2_fetch_64")) { g_l2_fetch_64.store(value != 0); return KZGB_OK; }
+    if (!strcmp(name, "pipelined_upload")) { g_pipelined_upload.store(value != 0); return KZGB_OK; }
     if (!strcmp(name, "batch_keep_mib")) { g_batch_keep_mib.store(value < 0 ? 0 : value); return KZGB_OK; }
     if (!strcmp(name, "fs_quad")) { fs_set_quad((int)value); return KZGB_OK; }
     if (!strcmp(name, "group_members")) { g_group_members.store(value < 1 ? 1 : (int)value); return KZGB_OK; }
@@ -1977,6 +2119,8 @@ int kzgb_set_option(const char* name, long value) {
     if (!strcmp(name, "lagrange_budget_mib")) { g_lagrange_budget_mib.store(value < 0 ? 0 : value); return KZGB_OK; }
     if (!strcmp(name, "acc_waves")) { msm_set_acc_waves((int)value); return KZGB_OK; }
     if (!strcmp(name, "msm_debug_sync")) { msm_set_debug_sync((int)value); return KZGB_OK; }
+    if (!strcmp(name, "acc_regs")) { msm_set_experiment((int)value, -1); return KZGB_OK; }
+    if (!strcmp(name, "sort_block")) { msm_set_experiment(-1, (int)value); return KZGB_OK; }
     return KZGB_ERR_GENERIC;
 }
 

@@ -55,6 +55,7 @@ MsmPlan msm_make_plan(uint32_t n, int c, bool fixed_base, uint32_t table_stride,
 // waves of accumulate blocks (4 blocks of 128 threads per SM and wave) the sorted list is cut into; default 4
 void msm_set_acc_waves(int waves);
 void msm_set_debug_sync(int on);
+void msm_set_experiment(int acc_regs, int sort_block);
 
 // scalars: n Fr (Montgomery unless scalars_canonical).  Result: ws.set_sums[0..sets) on the device.
 // The optional events bracket the bucket-accumulation kernel (roofline timing).
@@ -64,6 +65,15 @@ void msm_launch(const MsmPlan& p, const MsmWorkspace& ws, const Fr* scalars, boo
                 cudaEvent_t ev_join = nullptr);
 // st_acc (optional): a second, lower-priority stream for the bucket accumulation, fenced against `st`
 // with ev_fork / ev_join.
+// The two halves of msm_launch: sort + accumulate + stitch (ws.buckets = the sum of every bucket), and the
+// bucket reduction of any bucket array of the plan's shape.  Large MSMs whose scalars arrive from the host in
+// chunks run the first half per chunk, fold the bucket sums together (msm_merge_buckets) and reduce once.
+void msm_launch_buckets(const MsmPlan& p, const MsmWorkspace& ws, const Fr* scalars, bool scalars_canonical,
+                        const Affine* table, cudaStream_t st, cudaEvent_t ev_acc_begin = nullptr,
+                        cudaEvent_t ev_acc_end = nullptr, cudaStream_t st_acc = nullptr, cudaEvent_t ev_fork = nullptr,
+                        cudaEvent_t ev_join = nullptr);
+void msm_launch_reduce(const MsmPlan& p, const MsmWorkspace& ws, const XYZZ* buckets, cudaStream_t st);
+void msm_merge_buckets(XYZZ* dst, const XYZZ* src, uint32_t nbuckets, cudaStream_t st);
 
 // ---- SRS ------------------------------------------------------------------------
 // gnark big-endian compressed points -> affine Montgomery (n < 2^30 per launch).  err[0] must be preset to

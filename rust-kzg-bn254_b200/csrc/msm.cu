@@ -211,9 +211,9 @@ __device__ __forceinline__ bool xyzz_madd_relaxed_nonempty(XYZZ& acc, const Affi
 // Thread t owns sorted entries [t*chunk, (t+1)*chunk).  A bucket run that lies entirely inside the chunk is
 // written to buckets[b]; the run cut by the chunk's start goes to partial[2t], the one cut by its end to
 // partial[2t+1] (k_bucket_fix adds them up).
-__global__ void __launch_bounds__(128, 4) k_accumulate(const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ offsets,
-                                                        const Affine* __restrict__ table, uint32_t nb, uint32_t acc_threads,
-                                                        uint32_t chunk, XYZZ* __restrict__ buckets, XYZZ* __restrict__ partial) {
+__device__ __forceinline__ void accumulate_body(const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ offsets,
+                                                const Affine* __restrict__ table, uint32_t nb, uint32_t acc_threads,
+                                                uint32_t chunk, XYZZ* __restrict__ buckets, XYZZ* __restrict__ partial) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= acc_threads) return;
     const uint32_t M = offsets[nb];
@@ -256,6 +256,19 @@ __global__ void __launch_bounds__(128, 4) k_accumulate(const uint32_t* __restric
     }
     bool complete = (run_begin >= start) && (next <= end);
     flush(complete ? &buckets[b] : (run_begin <= start) ? &partial[2 * t] : &partial[2 * t + 1]);
+}
+__global__ void __launch_bounds__(128, 4) k_accumulate(const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ offsets,
+                                                        const Affine* __restrict__ table, uint32_t nb, uint32_t acc_threads,
+                                                        uint32_t chunk, XYZZ* __restrict__ buckets, XYZZ* __restrict__ partial) {
+    accumulate_body(sorted, offsets, table, nb, acc_threads, chunk, buckets, partial);
+}
+// EXPERIMENT (option "acc_regs"): the same body under a hard register cap, so that four blocks leave part of the
+// register file free and the short sort kernels of the other lanes can be resident NEXT TO the accumulation
+template <int MAXR>
+__global__ void __maxnreg__(MAXR) k_accumulate_capped(const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ offsets,
+                                                       const Affine* __restrict__ table, uint32_t nb, uint32_t acc_threads,
+                                                       uint32_t chunk, XYZZ* __restrict__ buckets, XYZZ* __restrict__ partial) {
+    accumulate_body(sorted, offsets, table, nb, acc_threads, chunk, buckets, partial);
 }
 
 // Buckets whose entries span more than LONG_SPAN chunks (hot buckets: equal scalars, a top window with a
@@ -545,6 +558,11 @@ __global__ void __launch_bounds__(32) k_reduce_final(const XYZZ* __restrict__ gr
 
 // ---------------------------------------------------------------------------------
 static std::atomic<int> g_acc_waves{4};
+static std::atomic<int> g_acc_regs{0}, g_sort_block{256};
+void msm_set_experiment(int acc_regs, int sort_block) {
+    if (acc_regs >= 0) g_acc_regs.store(acc_regs);
+    if (sort_block == 64 || sort_block == 128 || sort_block == 256) g_sort_block.store(sort_block);
+}
 static std::atomic<int> g_debug_sync{0};  // option "msm_debug_sync": synchronise and report after every kernel of msm_launch
 void msm_set_debug_sync(int on) { g_debug_sync.store(on); }
 #define KZ_DBG(name)                                                                                         \
@@ -617,14 +635,39 @@ void msm_workspace_carve(const MsmPlan& p, void* base, MsmWorkspace* ws) {
     ws->long_list = (uint32_t*)c;
 }
 
+// dst[k] += src[k]: bucket sums of a further point sub-range folded into the running totals (msm_launch_buckets
+// of the chunks of one large MSM whose scalars arrive piecewise, capi.cu msm_host_scalars_pipelined)
+__global__ void __launch_bounds__(128) k_merge_buckets(XYZZ* __restrict__ dst, const XYZZ* __restrict__ src, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    XYZZ b = xyzz_load(&src[i]);
+    if (xyzz_is_inf(b)) return;
+    XYZZ a = xyzz_load(&dst[i]);
+    xyzz_add(a, b);
+    xyzz_store(&dst[i], a);
+}
+void msm_merge_buckets(XYZZ* dst, const XYZZ* src, uint32_t nbuckets, cudaStream_t st) {
+    k_merge_buckets<<<(nbuckets + 127) / 128, 128, 0, st>>>(dst, src, nbuckets);
+    g_launch_count++;
+}
+
 void msm_launch(const MsmPlan& p, const MsmWorkspace& ws, const Fr* scalars, bool scalars_canonical,
                 const Affine* table, cudaStream_t st, cudaEvent_t ev_acc_begin, cudaEvent_t ev_acc_end,
                 cudaStream_t st_acc, cudaEvent_t ev_fork, cudaEvent_t ev_join) {
+    msm_launch_buckets(p, ws, scalars, scalars_canonical, table, st, ev_acc_begin, ev_acc_end, st_acc, ev_fork, ev_join);
+    msm_launch_reduce(p, ws, ws.buckets, st);
+}
+
+// sort + accumulate + stitch: afterwards ws.buckets holds the sum of every bucket (identity where empty)
+void msm_launch_buckets(const MsmPlan& p, const MsmWorkspace& ws, const Fr* scalars, bool scalars_canonical,
+                        const Affine* table, cudaStream_t st, cudaEvent_t ev_acc_begin, cudaEvent_t ev_acc_end,
+                        cudaStream_t st_acc, cudaEvent_t ev_fork, cudaEvent_t ev_join) {
     const bool split = st_acc && ev_fork && ev_join;
     cudaStream_t sa = split ? st_acc : st;
     cudaMemsetAsync(ws.hist, 0, ((size_t)p.nbuckets + 1) * 4, st);
-    uint32_t gb = (p.n + 255) / 256;
-    if (p.n) { k_digits_hist<<<gb, 256, 0, st>>>(scalars, scalars_canonical, p, ws.canon, ws.hist); g_launch_count += 2; }
+    const uint32_t sb = (uint32_t)g_sort_block.load();
+    uint32_t gb = (p.n + sb - 1) / sb;
+    if (p.n) { k_digits_hist<<<gb, sb, 0, st>>>(scalars, scalars_canonical, p, ws.canon, ws.hist); g_launch_count += 2; }
     {
         uint32_t ntiles = (p.nbuckets + SCAN_TILE - 1) / SCAN_TILE;
         k_scan_tiles<<<ntiles, SCAN_THREADS, 0, st>>>(ws.hist, ws.cursor, p.nbuckets, ws.tile_tot, ntiles == 1);
@@ -635,12 +678,22 @@ void msm_launch(const MsmPlan& p, const MsmWorkspace& ws, const Fr* scalars, boo
             g_launch_count += 2;
         }
     }
-    if (p.n) k_scatter<<<gb, 256, 0, st>>>(ws.canon, p, ws.cursor, ws.sorted);
+    if (p.n) k_scatter<<<gb, sb, 0, st>>>(ws.canon, p, ws.cursor, ws.sorted);
     KZ_DBG("sort");
     if (split) { cudaEventRecord(ev_fork, st); cudaStreamWaitEvent(sa, ev_fork, 0); }
     if (ev_acc_begin) cudaEventRecord(ev_acc_begin, sa);
-    k_accumulate<<<(p.acc_threads + 127) / 128, 128, 0, sa>>>(ws.sorted, ws.hist, table, p.nbuckets, p.acc_threads, p.chunk,
-                                                              ws.buckets, ws.partial);
+    {
+        const dim3 ga((p.acc_threads + 127) / 128);
+#define KZ_ACC(K) K<<<ga, 128, 0, sa>>>(ws.sorted, ws.hist, table, p.nbuckets, p.acc_threads, p.chunk, ws.buckets, ws.partial)
+        switch (g_acc_regs.load()) {
+            case 120: KZ_ACC(k_accumulate_capped<120>); break;
+            case 112: KZ_ACC(k_accumulate_capped<112>); break;
+            case 104: KZ_ACC(k_accumulate_capped<104>); break;
+            case 96: KZ_ACC(k_accumulate_capped<96>); break;
+            default: KZ_ACC(k_accumulate); break;
+        }
+#undef KZ_ACC
+    }
     if (ev_acc_end) cudaEventRecord(ev_acc_end, sa);
     if (split) { cudaEventRecord(ev_join, sa); cudaStreamWaitEvent(st, ev_join, 0); }
     KZ_DBG("accumulate");
@@ -654,14 +707,20 @@ void msm_launch(const MsmPlan& p, const MsmWorkspace& ws, const Fr* scalars, boo
                                                                   ws.long_list + 1, long_cap);
     }
     KZ_DBG("bucket_fix");
-    k_reduce_lines<<<dim3((unsigned)lines_per_set(p), (unsigned)p.sets), LINE_THREADS, 0, st>>>(ws.buckets, p.a_bits, p.h_bits, ws.line_sums);
+    g_launch_count += 3;  // accumulate, bucket_fix, bucket_fix_long
+}
+
+// bucket sums -> ws.set_sums (one XYZZ point per bucket set)
+void msm_launch_reduce(const MsmPlan& p, const MsmWorkspace& ws, const XYZZ* buckets, cudaStream_t st) {
+    cudaStream_t sa = st;
+    k_reduce_lines<<<dim3((unsigned)lines_per_set(p), (unsigned)p.sets), LINE_THREADS, 0, st>>>(buckets, p.a_bits, p.h_bits, ws.line_sums);
     KZ_DBG("reduce_lines");
     k_reduce_groups<<<dim3((unsigned)p.ngroups, (unsigned)p.sets), GROUP_THREADS, 0, st>>>(ws.line_sums, p.a_bits, p.h_bits, p.ngroups,
                                                                                           ws.group_sums);
     KZ_DBG("reduce_groups");
     k_reduce_final<<<p.sets, 32, 0, st>>>(ws.group_sums, p.ngroups, ws.set_sums);
     KZ_DBG("reduce_final");
-    g_launch_count += 6;  // accumulate, bucket_fix, bucket_fix_long, reduce_lines, reduce_groups, reduce_final
+    g_launch_count += 3;  // reduce_lines, reduce_groups, reduce_final
 }
 
 }  // namespace kzgb

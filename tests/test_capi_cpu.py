@@ -1,5 +1,5 @@
 """No-GPU checks of the C-ABI library: it loads, exports every symbol include/kzg_bn254_b200.h
-declares, the host-only entry points agree with the oracle, and a context cannot be created
+(and the measurement header kzg_bn254_b200_bench.h) declares, the host-only entry points agree with the oracle, and a context cannot be created
 without a GPU (no silent CPU fallback)."""
 import ctypes as C
 import os
@@ -19,6 +19,7 @@ def pkg():
 
 def test_header_symbols_exported(pkg):
     hdr = open(os.path.join(ROOT, "include", "kzg_bn254_b200.h")).read()
+    hdr += open(os.path.join(ROOT, "include", "kzg_bn254_b200_bench.h")).read()  # measurement hooks, same library
     declared = set(re.findall(r"\b(kzgb_[a-z0-9_]+)\s*\(", hdr))
     assert len(declared) >= 35
     lib = pkg._capi.lib

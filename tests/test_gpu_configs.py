@@ -243,3 +243,119 @@ def test_ntt_linearity_2p19(pkg):
     for i in list(range(0, n, n // 64)) + [1, 2, 3, n - 1]:
         a, b, c = (pkg.fr_from_mont_bytes(o_[32 * i : 32 * i + 32])[0] for o_ in outs)
         assert c == (a + 3 * b) % o.R
+
+
+# ---------------------------------------------------------------------------------------------------------
+# BASELINE configs[2], [3] (one GPU's worth) and [4] at their FULL sizes, through size-independent properties
+# ---------------------------------------------------------------------------------------------------------
+def _raw_batch(lib, eng, host, count, nbytes):
+    """kzgb_commit_and_prove_blobs on `count` blobs laid out back to back in a pinned torch tensor."""
+    lens = (C.c_size_t * count)(*[nbytes] * count)
+    ptrs = (C.c_void_p * count)(*[host[i].data_ptr() for i in range(count)])
+    cm, pf = C.create_string_buffer(32 * count), C.create_string_buffer(32 * count)
+    eng.check(lib.kzgb_commit_and_prove_blobs(eng.h, ptrs, lens, count, cm, pf))
+    return cm.raw, pf.raw
+
+
+def test_config3_full_size_1024_blobs_2p16(pkg):
+    """configs[2] at full size: 1024 blobs x 2^16 Fr (2 GiB) through the grouped small-blob pipeline.  The second half
+    of the batch repeats the first (equal inputs at different positions of different groups must give equal bytes),
+    six blobs are checked against the closed forms commitment = p(tau) G and proof = ((p(tau) - y)/(tau - z)) G with
+    z recomputed from the real transcript, and the whole batch is run twice (idempotence of the resident tables)."""
+    import numpy as np
+    import torch
+
+    n, count = 1 << 16, 1024
+    eng = pkg.Engine(0)
+    srs = pkg.SRS.synthetic(n, TAU, engine=eng)
+    rng = np.random.default_rng(2016)
+    host = torch.empty((count, n * 32), dtype=torch.uint8).pin_memory()
+    half = rng.integers(0, 256, size=(count // 2, n, 32), dtype=np.uint8)
+    half[:, :, 0] = 0
+    host[: count // 2] = torch.from_numpy(half.reshape(count // 2, -1))
+    host[count // 2 :] = host[: count // 2]
+    cm, pf = _raw_batch(pkg.lib, eng, host, count, n * 32)
+    assert cm[: 32 * 512] == cm[32 * 512 :] and pf[: 32 * 512] == pf[32 * 512 :]
+    assert len({cm[32 * i : 32 * i + 32] for i in range(512)}) == 512
+    for i in (0, 1, 63, 64, 300, 511):
+        data = bytes(host[i].numpy().tobytes())
+        evals = [int.from_bytes(data[32 * k : 32 * k + 32], "big") for k in range(n)]
+        ptau = _barycentric(evals, TAU)
+        c = o.g1_mul(o.G1_GEN, ptau)
+        assert cm[32 * i : 32 * i + 32] == o.g1_serialize_compressed(c)
+        z = o.hash_to_field_element(o.FIAT_SHAMIR_PROTOCOL_DOMAIN + n.to_bytes(8, "big") + data + o.g1_serialize_compressed(c))
+        y = _barycentric(evals, z)
+        q = (ptau - y) * pow(TAU - z, -1, o.R) % o.R
+        assert pf[32 * i : 32 * i + 32] == o.g1_serialize_compressed(o.g1_mul(o.G1_GEN, q))
+    assert _raw_batch(pkg.lib, eng, host, count, n * 32) == (cm, pf)
+    eng.close()
+
+
+def test_config5_full_size_4096_pairs(pkg):
+    """configs[4] at full size: verify_blob_kzg_proof_batch's front half + RLC over 4096 (blob, commitment, proof)
+    triples of 2^12-Fr blobs.  The commitments and proofs come from the GPU prover; the two RLC outputs must satisfy
+    what the final pairing checks, rhs = tau * lhs (batch.rs:253-254 with [tau]G2), the device-hashed and host-hashed
+    challenge paths must agree, and one tampered proof among the 4096 must break the relation."""
+    import numpy as np
+    import torch
+
+    n, m = 1 << 12, 4096
+    eng = pkg.Engine(0)
+    srs = pkg.SRS.synthetic(n, TAU, engine=eng)
+    rng = np.random.default_rng(4096)
+    arr = rng.integers(0, 256, size=(m, n, 32), dtype=np.uint8)
+    arr[:, :, 0] = 0
+    host = torch.from_numpy(arr.reshape(m, -1)).pin_memory()
+    cm, pf = _raw_batch(pkg.lib, eng, host, m, n * 32)
+    cpts = [o.g1_deserialize_compressed(cm[32 * i : 32 * i + 32]) for i in range(m)]
+    ppts = [o.g1_deserialize_compressed(pf[32 * i : 32 * i + 32]) for i in range(m)]
+    cxy, cinf = pkg.g1_to_abi(cpts)
+    lens = (C.c_size_t * m)(*[n * 32] * m)
+    ptrs = (C.c_void_p * m)(*[host[i].data_ptr() for i in range(m)])
+
+    def rlc(proofs):
+        pxy, pinf = pkg.g1_to_abi(proofs)
+        lhs, rhs = C.create_string_buffer(64), C.create_string_buffer(64)
+        li, ri = C.c_uint8(0), C.c_uint8(0)
+        eng.check(pkg.lib.kzgb_verify_batch_rlc(eng.h, ptrs, lens, m, cxy, cinf, pxy, pinf, lhs, C.byref(li), rhs, C.byref(ri)))
+        return pkg.g1_from_abi(lhs.raw, bytes([li.value]))[0], pkg.g1_from_abi(rhs.raw, bytes([ri.value]))[0]
+
+    lhs, rhs = rlc(ppts)
+    assert lhs is not None and o.g1_mul(lhs, TAU) == rhs
+    try:
+        pkg.lib.kzgb_set_option(b"fs_device", 0)  # host SHA-256 pool instead of the device kernel
+        assert rlc(ppts) == (lhs, rhs)
+    finally:
+        pkg.lib.kzgb_set_option(b"fs_device", -1)
+    bad = list(ppts)
+    bad[2777] = o.g1_add(bad[2777], o.G1_GEN)
+    lhs2, rhs2 = rlc(bad)
+    assert o.g1_mul(lhs2, TAU) != rhs2
+    eng.close()
+
+
+def test_fixed_base_msm_2p24_closed_form(pkg):
+    """One quarter of config 4's point count on one GPU with its window table (the library picks c = 22:
+    12 windows x 2^24 points x 64 B = 12 GiB): scalars a^i => MSM = ((a tau)^N - 1)/(a tau - 1) G; the host-scalar
+    entry point (chunked upload) must return the same point as the device-resident one."""
+    import torch
+
+    N = 1 << 24
+    a = 0x1D5F3C29A7B4E6081122334455667788990AABBCCDDEEFF0123456789ABCDEF1 % o.R
+    at = a * TAU % o.R
+    expect = o.g1_mul(o.G1_GEN, (pow(at, N, o.R) - 1) * pow(at - 1, -1, o.R) % o.R)
+    eng = pkg.Engine(0)
+    srs = pkg.SRS.synthetic(N, TAU, engine=eng)
+    srs.precompute(N, 0)
+    cb, cw, ct = C.c_int(0), C.c_int(0), C.c_size_t(0)
+    pkg.lib.kzgb_msm_config(eng.h, C.byref(cb), C.byref(cw), C.byref(ct))
+    assert ct.value == N and cb.value >= 20
+    scal = torch.empty(N * 32, dtype=torch.uint8, device="cuda")
+    eng.check(pkg.lib.kzgb_fr_powers_dev(eng.h, pkg.fr_to_mont_bytes([a]), 0, N, scal.data_ptr()))
+    out, inf = C.create_string_buffer(64), C.c_uint8(0)
+    eng.check(pkg.lib.kzgb_msm_srs_range_dev(eng.h, scal.data_ptr(), 0, N, out, C.byref(inf)))
+    assert pkg.g1_from_abi(out.raw, bytes([inf.value]))[0] == expect
+    host = scal.cpu()
+    eng.check(pkg.lib.kzgb_msm_srs_range(eng.h, host.data_ptr(), 0, N, out, C.byref(inf)))
+    assert pkg.g1_from_abi(out.raw, bytes([inf.value]))[0] == expect
+    eng.close()
