@@ -225,6 +225,19 @@ int kzgb_validate_g1_points(kzgb_ctx* ctx, const uint64_t* xy, const uint8_t* in
  * The library reads NO environment variables of its own (torchrun's LOCAL_WORLD_SIZE is consulted for "lane_wait" auto).
  * Unknown names return KZGB_ERR_GENERIC. */
 int kzgb_set_option(const char* name, long value);
+/* ---- single-proof verification up to the pairing (verifier/src/verify.rs) ---------------------------------------------
+ * verify_proof (verify.rs:10-75), the G1 side: commitment and proof validated (validate_g1_point, :18-22; BN254 G1 has
+ * cofactor 1, so on-curve is the subgroup check), out = C - [y] G1 (:37-42).  The caller's reference code computes
+ * [tau - z] G2 and runs pairings_verify(out, G2, proof, [tau - z] G2) (:44-74).  Err KZGB_ERR_NOT_ON_CURVE. */
+int kzgb_verify_proof_g1(kzgb_ctx* ctx, const uint64_t c_xy[8], uint8_t c_inf, const uint64_t proof_xy[8], uint8_t proof_inf,
+                         const uint64_t y_mont[4], uint64_t out_xy[8], uint8_t* out_inf);
+/* verify_blob_kzg_proof (verify.rs:77-115) up to the pairing: validation, z = compute_challenge(blob, C), y = p(z)
+ * (barycentric evaluation on the GPU), then kzgb_verify_proof_g1.  z_out / y_out (Montgomery, may be NULL) are what the
+ * caller needs for [tau - z] G2. */
+int kzgb_verify_blob_proof_g1(kzgb_ctx* ctx, const uint8_t* blob, size_t len, const uint64_t c_xy[8], uint8_t c_inf,
+                              const uint64_t proof_xy[8], uint8_t proof_inf, uint64_t out_xy[8], uint8_t* out_inf,
+                              uint64_t z_out[4], uint64_t y_out[4]);
+
 /* ---- multi-GPU: one handle over several GPUs of one box ------------------------------------
  * The path shards by blob (batches) and by point range (one large MSM) and has no exchange step besides adding
  * G partial sums of 64 bytes, which happens on the host: one process, one host thread per GPU for the duration of

@@ -610,6 +610,30 @@ def evaluate_polynomial_in_evaluation_form(polynomial: PolynomialEvalForm, z: in
     return fr_from_mont_bytes(out.raw)[0]
 
 
+def verify_proof_g1(commitment: Affine, proof: Affine, value_fr: int, engine: Optional[Engine] = None) -> Affine:
+    """verifier/src/verify.rs:10-42: validates both points and returns ``commitment - [value] G1``, the first argument of the
+    final ``pairings_verify`` (which, with ``[tau - z] G2``, stays in the reference's code)."""
+    e = engine or default_engine()
+    cxy, cinf = g1_to_abi([commitment])
+    pxy, pinf = g1_to_abi([proof])
+    out = C.create_string_buffer(64)
+    inf = C.c_uint8(0)
+    e.check(lib.kzgb_verify_proof_g1(e.h, cxy, cinf[0], pxy, pinf[0], fr_to_mont_bytes([value_fr]), out, C.byref(inf)))
+    return g1_from_abi(out.raw, bytes([inf.value]))[0]
+
+
+def verify_blob_kzg_proof_g1(blob: "Blob", commitment: Affine, proof: Affine, engine: Optional[Engine] = None) -> Tuple[Affine, int, int]:
+    """verifier/src/verify.rs:77-115 up to the pairing: returns ``(commitment - [y] G1, z, y)``."""
+    e = engine or default_engine()
+    cxy, cinf = g1_to_abi([commitment])
+    pxy, pinf = g1_to_abi([proof])
+    out = C.create_string_buffer(64)
+    inf = C.c_uint8(0)
+    z, y = C.create_string_buffer(32), C.create_string_buffer(32)
+    e.check(lib.kzgb_verify_blob_proof_g1(e.h, blob.blob_data, len(blob.blob_data), cxy, cinf[0], pxy, pinf[0], out, C.byref(inf), z, y))
+    return g1_from_abi(out.raw, bytes([inf.value]))[0], fr_from_mont_bytes(z.raw)[0], fr_from_mont_bytes(y.raw)[0]
+
+
 def verify_blob_kzg_proof_batch_rlc(
     blobs: Sequence[Blob], commitments: Sequence[Affine], proofs: Sequence[Affine], engine: Optional[Engine] = None
 ) -> Tuple[Affine, Affine]:

@@ -85,6 +85,8 @@ SIGNATURES = {
     "kzgb_stats": (C.c_int, [ctx_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_int]),
     "kzgb_set_option": (C.c_int, [C.c_char_p, C.c_long]),
     "kzgb_msm_config": (C.c_int, [ctx_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
+    "kzgb_verify_proof_g1": (C.c_int, [ctx_p, buf, C.c_uint8, buf, C.c_uint8, buf, buf, u8p]),
+    "kzgb_verify_blob_proof_g1": (C.c_int, [ctx_p, buf, C.c_size_t, buf, C.c_uint8, buf, C.c_uint8, buf, u8p, buf, buf]),
     "kzgb_trace_begin": (C.c_int, [ctx_p]),
     "kzgb_trace_end": (C.c_int, [ctx_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "kzgb_srs_precompute_range": (C.c_int, [ctx_p, C.c_size_t, C.c_size_t, C.c_int]),

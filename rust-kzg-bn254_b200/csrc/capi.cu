@@ -91,6 +91,12 @@ struct kzgb_ctx {
     int logN = 0;
     // timer
     cudaEvent_t t0 = nullptr, t1 = nullptr;
+    // device-side hashing of long Fiat-Shamir transcripts (fs.cu k_fs_midstate_long): its stream, the mapped host block the
+    // kernel reports through ([state 8 x cap | done cap | cancel 1] words) and the device-side argument arrays
+    cudaStream_t hash_st = nullptr;
+    cudaEvent_t ev_hash_uploaded = nullptr;
+    uint32_t* fsl_host = nullptr;
+    DevBuf fsl_args;
     // upload stream + double-buffer fences of msm_srs_host_pipelined
     cudaStream_t copy_st = nullptr;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
@@ -124,6 +130,7 @@ std::atomic<int> g_hash_threads{0};     // host SHA-256 pool threads per batch c
 std::atomic<int> g_lane_wait{-1};       // -1 auto, 0 spin on the stream, 1 poll with short sleeps
 std::atomic<int> g_stream_priority{1};  // 1: bucket accumulation on a low-priority stream of its own
 std::atomic<int> g_l2_fetch_64{1};
+std::atomic<int> g_device_hash{-1};        // blobs of a large-blob batch whose transcript is hashed on the device: -1 auto, 0 none, k > 0 the last k
 std::atomic<int> g_pipelined_upload{1};   // 1: host scalars of MSMs of >= 2^22 points over a window table are uploaded in overlapped chunks
 std::atomic<long> g_batch_keep_mib{4096};  // blob staging buffer of kzgb_commit_and_prove_blobs kept between calls up to this size      // 1: contexts that own their stream set the L2 fetch granularity to 64 B
 int fail(kzgb_ctx* c, int code, const std::string& msg) {
@@ -958,6 +965,10 @@ void kzgb_ctx_destroy(kzgb_ctx* c) {
     if (c->t0) cudaEventDestroy(c->t0);
     if (c->t1) cudaEventDestroy(c->t1);
     if (c->copy_st) cudaStreamDestroy(c->copy_st);
+    if (c->hash_st) cudaStreamDestroy(c->hash_st);
+    if (c->ev_hash_uploaded) cudaEventDestroy(c->ev_hash_uploaded);
+    if (c->fsl_host) cudaFreeHost(c->fsl_host);
+    c->fsl_args.release();
     for (int k = 0; k < 2; k++) { if (c->ev_copied[k]) cudaEventDestroy(c->ev_copied[k]); if (c->ev_consumed[k]) cudaEventDestroy(c->ev_consumed[k]); }
     if (c->trace_base) cudaEventDestroy(c->trace_base);
     for (auto& r : c->trace) if (r.ev) cudaEventDestroy(r.ev);
@@ -1481,7 +1492,117 @@ int kzgb_compute_blob_proof(kzgb_ctx* c, const uint8_t* blob, size_t len, const 
     return KZGB_OK;
 }
 
+// ------------------------------------------------------------------------------- single-proof verification, G1 side
+// [k] G on the host (one 254-bit double-and-add on the 4x64 host field: ~0.1 ms, below the latency of any launch)
+static void g1_generator_mul(XYZZ& out, const Fr& k_mont) {
+    Fr k; fe_from_mont(k, k_mont);
+    Affine G;
+    fe_one(G.x); fe_dbl(G.y, G.x);
+    XYZZ acc; xyzz_set_inf(acc);
+    for (int i = 255; i >= 0; i--) {
+        xyzz_dbl(acc, acc);
+        if ((k.l[i >> 5] >> (i & 31)) & 1u) xyzz_madd(acc, G);
+    }
+    out = acc;
+}
+// verify_proof (verifier/src/verify.rs:10-75), everything that lives in G1: both points validated (:18-22), then
+// commit_minus_value = C - [y] G1 (:37-42).  [tau - z] G2 and the pairing stay in the reference's code.
+int kzgb_verify_proof_g1(kzgb_ctx* c, const uint64_t c_xy[8], uint8_t c_inf, const uint64_t proof_xy[8], uint8_t proof_inf,
+                         const uint64_t y_mont[4], uint64_t out_xy[8], uint8_t* out_inf) {
+    Affine C = affine_from_abi(c_xy, c_inf), P = affine_from_abi(proof_xy, proof_inf);
+    if (!aff_on_curve(C) || !aff_on_curve(P)) return fail(c, KZGB_ERR_NOT_ON_CURVE, "G1 point not on curve");
+    Fr y, ny;
+    memcpy(y.l, y_mont, 32);
+    fe_neg(ny, y);
+    XYZZ acc;
+    g1_generator_mul(acc, ny);  // -[y] G
+    xyzz_madd(acc, C);
+    Affine r;
+    xyzz_to_affine(r, acc);
+    affine_to_abi(r, out_xy, out_inf);
+    return KZGB_OK;
+}
+// verify_blob_kzg_proof (verifier/src/verify.rs:77-115) up to the pairing: validation, z = compute_challenge(blob, C) on the
+// host SHA-256 while the blob is uploaded and converted, y = p(z) on the GPU (no quotient), then kzgb_verify_proof_g1.
+int kzgb_verify_blob_proof_g1(kzgb_ctx* c, const uint8_t* blob, size_t len, const uint64_t c_xy[8], uint8_t c_inf,
+                              const uint64_t proof_xy[8], uint8_t proof_inf, uint64_t out_xy[8], uint8_t* out_inf,
+                              uint64_t z_out[4], uint64_t y_out[4]) {
+    Affine C = affine_from_abi(c_xy, c_inf), P = affine_from_abi(proof_xy, proof_inf);
+    if (!aff_on_curve(C) || !aff_on_curve(P)) return fail(c, KZGB_ERR_NOT_ON_CURVE, "G1 point not on curve");
+    if (len == 0) return fail(c, KZGB_ERR_GENERIC, "Length of data after padding is 0");  // helpers.rs:554-558 via :482
+    const size_t n = blob_poly_len(len);
+    if (n > ((size_t)1 << 28)) return fail(c, KZGB_ERR_GENERIC, "Input size exceeds maximum polynomial size");
+    Fr y;
+    {
+        Guard g(c);
+        Lane& L = c->lanes[0];
+        const int logn = log2_exact(n);
+        int rc = ensure_twiddles(c, logn);
+        if (rc) return rc;
+        rc = blob_to_evals(c, L, blob, nullptr, len, n);
+        if (rc) return rc;
+        Sha256 sh;
+        challenge_midstate(sh, blob, len, n);
+        L.h_fr[0] = challenge_finish(sh, C);
+        CK(c, L.eval_scratch.reserve(eval_quotient_scratch_elems((uint32_t)n, 1) * sizeof(Fr)));
+        CK(c, L.small.reserve(64 * sizeof(Fr)));
+        bool in_domain = false;
+        L.h_fr[1] = eval_tinv(L.h_fr[0], logn, &in_domain);
+        Fr* d_z = (Fr*)L.small.p;
+        CK(c, cudaMemcpyAsync(d_z, &L.h_fr[0], 2 * sizeof(Fr), cudaMemcpyHostToDevice, L.st));
+        Fr ninv = ninv_mont(logn);
+        eval_quotient_launch((Fr*)L.evals.p, (uint32_t)n, logn, 1, d_z, d_z + 1, c->tw, c->logN, &ninv, (Fr*)L.eval_scratch.p,
+                             nullptr, d_z + 2, L.st, !in_domain);
+        CK(c, cudaMemcpyAsync(&L.h_fr[3], d_z + 2, sizeof(Fr), cudaMemcpyDeviceToHost, L.st));
+        CK(c, cudaStreamSynchronize(L.st));
+        CK(c, cudaGetLastError());
+        y = L.h_fr[3];
+        if (z_out) memcpy(z_out, L.h_fr[0].l, 32);
+        if (y_out) memcpy(y_out, y.l, 32);
+    }
+    return kzgb_verify_proof_g1(c, c_xy, c_inf, proof_xy, proof_inf, (const uint64_t*)y.l, out_xy, out_inf);
+}
+
 // ------------------------------------------------------------------------------- blob batches
+constexpr size_t FSL_CAP = 4096;  // transcripts one batch call can hand to the device
+// How many blobs at the END of a large-blob batch get their transcript hashed by the device (k_fs_midstate_long) instead
+// of the host pool.  One transcript is ~0.25 s of one warp however fast the GPU is (SHA-256 is sequential per message),
+// against ~9 ms of a SHA-NI core -- so the device only helps when (a) the host cannot keep up with the GPU (8 ranks on 32
+// hardware threads: 38 GB/s of SHA-256 against 47 GB/s of blobs) and (b) the batch is long enough for 0.25 s to hide
+// behind the commitments of the other blobs.  The model below picks the k that minimises the predicted step time.
+size_t device_hash_share(const size_t* lens, size_t count) {
+    const int opt = g_device_hash.load();
+    if (opt == 0 || count < 2) return 0;
+    // eligible tail: blobs of exactly 32 * 2^j bytes, j >= 10
+    size_t eligible = 0;
+    while (eligible < count && eligible < FSL_CAP) {
+        const size_t len = lens[count - 1 - eligible], n = len / 32;
+        if (len % 32 || n < 1024 || (n & (n - 1))) break;
+        eligible++;
+    }
+    if (opt > 0) return std::min<size_t>((size_t)opt, eligible);
+    if (!eligible) return 0;
+    double bytes = 0;
+    for (size_t i = 0; i < count; i++) bytes += (double)lens[i];
+    const double per_blob = bytes / (double)count;
+    unsigned hw = std::thread::hardware_concurrency();
+    if (hw == 0) hw = 8;
+    int procs = g_group_members.load();
+    if (const char* w = getenv("LOCAL_WORLD_SIZE")) { int v = atoi(w); if (v > procs) procs = v; }
+    const double host_rate = 1.2e9 * std::max(1.0, std::min<double>((double)hash_pool_threads(), (double)hw / procs));  // B/s, with HT siblings
+    const double t_gpu = 2.9e-3 * per_blob / (double)(16u << 20);  // commit + proof of one blob
+    const double t_dev = 0.45 * per_blob / (double)(16u << 20);    // one transcript on one warp, next to the MSMs
+    double best = std::max(count * t_gpu, bytes / host_rate);
+    size_t best_k = 0;
+    for (size_t k = 1; k <= eligible; k++) {
+        // a hashing warp costs about 16% of a blob's MSM work in integer-pipe time
+        const double t = std::max({(count + 0.16 * k) * t_gpu, (double)(count - k) * per_blob / host_rate, t_dev + k * t_gpu * 0.5});
+        if (t < best * 0.97) { best = t; best_k = k; }
+    }
+    return best_k;
+}
+
+
 static int batch_impl(kzgb_ctx* c, const uint8_t* const* blobs_dev, const uint8_t* const* blobs_host, const size_t* lens,
                       size_t count, uint8_t* commitments32, uint8_t* proofs32) {
     if (count == 0) return KZGB_OK;
@@ -1540,11 +1661,104 @@ static int batch_impl(kzgb_ctx* c, const uint8_t* const* blobs_dev, const uint8_
         if (!lag_ok && !(c->wtable && c->wt_first == 0 && n <= c->wt_n)) { groups.clear(); break; }
     }
 
-    // host hashing pool: transcript midstates (everything but the commitment)
+    // Blob bytes stay resident on the device between a blob's commit and its proof (one H2D per blob).
+    std::vector<size_t> byte_off(count, 0);
+    bool resident = false;
+    if (!blobs_dev && groups.empty()) {
+        size_t total = 0;
+        for (size_t i = 0; i < count; i++) { byte_off[i] = total; total += (lens[i] + 255) & ~(size_t)255; }
+        if (total <= ((size_t)16 << 30) && c->batch_bytes.reserve(total) == cudaSuccess) resident = true;
+        else cudaGetLastError();
+    }
+
+    // Transcript midstates (everything but the commitment): a pool of host threads from the front of the batch and, when
+    // the host cannot keep up with the GPU, one warp per transcript on the device for the blobs at its end
+    // (device_hash_share).  Whoever delivers a midstate first installs it; the lanes take proofs as they become ready.
     std::vector<Sha256> mid(count);
     std::vector<uint8_t> ready(count, 0);
     std::mutex mu;
     std::condition_variable cv;
+    bool failed = false;
+    const size_t dev_k = (groups.empty() && (blobs_dev || resident)) ? device_hash_share(lens, count) : 0;
+    const size_t dev_first = count - dev_k;
+    std::atomic<bool> dev_failed{false}, dev_stop{false};
+    volatile uint32_t* fsl_done = nullptr;
+    uint32_t* fsl_state = nullptr;
+    volatile uint32_t* fsl_cancel = nullptr;
+    if (dev_k) {
+        cudaError_t e = cudaSuccess;
+        if (!c->hash_st) {
+            int lo = 0, hi = 0;
+            cudaDeviceGetStreamPriorityRange(&lo, &hi);
+            e = cudaStreamCreateWithPriority(&c->hash_st, cudaStreamNonBlocking, hi);  // its few blocks must become resident at once
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_hash_uploaded, cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaHostAlloc((void**)&c->fsl_host, (9 * FSL_CAP + 16) * 4, cudaHostAllocMapped);
+        }
+        if (e == cudaSuccess) e = c->fsl_args.reserve(FSL_CAP * 16);
+        if (e == cudaSuccess) {
+            fsl_state = c->fsl_host;
+            fsl_done = c->fsl_host + 8 * FSL_CAP;
+            fsl_cancel = c->fsl_host + 9 * FSL_CAP;
+            for (size_t j = 0; j < dev_k; j++) fsl_done[j] = 0;
+            *fsl_cancel = 0;
+            std::vector<const uint8_t*> ptrs(dev_k);
+            std::vector<uint32_t> ns(dev_k);
+            for (size_t j = 0; j < dev_k && e == cudaSuccess; j++) {
+                const size_t i = dev_first + j;
+                ns[j] = (uint32_t)(lens[i] / 32);
+                if (blobs_dev) ptrs[j] = blobs_dev[i];
+                else {  // host blobs: the device's share goes up first, on the hashing stream
+                    uint8_t* slot = (uint8_t*)c->batch_bytes.p + byte_off[i];
+                    e = cudaMemcpyAsync(slot, blobs_host[i], lens[i], cudaMemcpyHostToDevice, c->hash_st);
+                    ptrs[j] = slot;
+                }
+            }
+            const uint8_t** d_ptrs = (const uint8_t**)c->fsl_args.p;
+            uint32_t* d_ns = (uint32_t*)((char*)c->fsl_args.p + FSL_CAP * 8);
+            if (e == cudaSuccess) e = cudaEventRecord(c->ev_hash_uploaded, c->hash_st);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(d_ptrs, ptrs.data(), dev_k * 8, cudaMemcpyHostToDevice, c->hash_st);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(d_ns, ns.data(), dev_k * 4, cudaMemcpyHostToDevice, c->hash_st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(c->hash_st);  // the argument vectors die with this scope
+            if (e == cudaSuccess) {
+                fs_midstate_long_launch(d_ptrs, d_ns, (uint32_t)dev_k, fsl_state, (uint32_t*)fsl_done, (const uint32_t*)fsl_cancel, c->hash_st);
+                e = cudaGetLastError();
+            }
+        }
+        if (e != cudaSuccess) { cudaGetLastError(); dev_failed.store(true); }  // the host pool takes the whole batch
+    }
+    // the last 32-byte chunk of a blob of exactly 32 n bytes, reduced mod r as to_fr_array does
+    auto install_device_midstate = [&](size_t i, const uint32_t* st) {
+        const size_t n = lens[i] / 32;
+        Sha256 sh;
+        sh.reset();
+        memcpy(sh.h, st, 32);
+        sh.total = 32 * (uint64_t)n;  // tag (24) + u64 (8) + chunks 0 .. n-2
+        const uint8_t* ch = blobs_host[i] + 32 * (n - 1);
+        if (ch[0] < 0x30 || memcmp(ch, FR_MOD_BE, 32) < 0) sh.update(ch, 32);
+        else { Fr v = fr_from_be_bytes(ch); uint8_t red[32]; fe_to_be_bytes(v, red); sh.update(red, 32); }
+        std::lock_guard<std::mutex> lk(mu);
+        if (!ready[i]) { mid[i] = sh; ready[i] = 1; }
+    };
+    std::thread dev_poller;
+    if (dev_k && !dev_failed.load()) {
+        dev_poller = std::thread([&]() {
+            std::vector<uint8_t> seen(dev_k, 0);
+            size_t remaining = dev_k;
+            while (remaining && !dev_stop.load()) {
+                bool any = false;
+                for (size_t j = 0; j < dev_k; j++) {
+                    if (seen[j] || !fsl_done[j]) continue;
+                    std::atomic_thread_fence(std::memory_order_acquire);
+                    uint32_t st[8];
+                    for (int w = 0; w < 8; w++) st[w] = fsl_state[8 * j + w];
+                    install_device_midstate(dev_first + j, st);
+                    seen[j] = 1; remaining--; any = true;
+                }
+                if (any) cv.notify_all();
+                else { struct timespec ts = {0, 100000}; nanosleep(&ts, nullptr); }
+            }
+        });
+    }
     std::atomic<size_t> next_hash{0};
     size_t n_hash = std::max<size_t>(1, std::min<size_t>(count, hash_pool_threads()));
     std::vector<std::thread> hashers;
@@ -1553,15 +1767,31 @@ static int batch_impl(kzgb_ctx* c, const uint8_t* const* blobs_dev, const uint8_
             for (;;) {
                 size_t i = next_hash.fetch_add(1);
                 if (i >= count) return;
-                challenge_midstate(mid[i], blobs_host[i], lens[i], blob_poly_len(lens[i]));
-                { std::lock_guard<std::mutex> lk(mu); ready[i] = 1; }
+                if (i >= dev_first) {  // the device's share: only if the device path failed
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&] { return ready[i] != 0 || failed || dev_failed.load() || dev_stop.load(); });
+                    if (ready[i] || failed || dev_stop.load()) continue;
+                }
+                Sha256 sh;
+                challenge_midstate(sh, blobs_host[i], lens[i], blob_poly_len(lens[i]));
+                { std::lock_guard<std::mutex> lk(mu); if (!ready[i]) { mid[i] = sh; ready[i] = 1; } }
                 cv.notify_all();
             }
         });
     }
+    // every exit path below: stop the device hashing, then wait for it (it reads the blob bytes)
+    struct DevHashJoin {
+        std::thread& poller; std::atomic<bool>& stop; volatile uint32_t* cancel; cudaStream_t st; std::condition_variable& cv;
+        ~DevHashJoin() {
+            stop.store(true);
+            if (cancel) *cancel = 1;
+            cv.notify_all();
+            if (poller.joinable()) poller.join();
+            if (st) cudaStreamSynchronize(st);
+        }
+    } dev_hash_join{dev_poller, dev_stop, fsl_cancel, dev_k ? c->hash_st : nullptr, cv};
 
     std::vector<int> lane_rc(n_lanes, KZGB_OK);
-    bool failed = false;
     struct LanesRunning {  // from here on the lane threads only READ the context's tables (msm_enqueue builds none)
         kzgb_ctx* c;
         explicit LanesRunning(kzgb_ctx* ctx) : c(ctx) { c->lanes_running.store(true); }
@@ -1663,16 +1893,6 @@ static int batch_impl(kzgb_ctx* c, const uint8_t* const* blobs_dev, const uint8_
         return KZGB_OK;
     }
 
-    // Blob bytes stay resident on the device between a blob's commit and its proof (one H2D per blob).
-    std::vector<size_t> byte_off(count, 0);
-    bool resident = false;
-    if (!blobs_dev) {
-        size_t total = 0;
-        for (size_t i = 0; i < count; i++) { byte_off[i] = total; total += (lens[i] + 255) & ~(size_t)255; }
-        if (total <= ((size_t)16 << 30) && c->batch_bytes.reserve(total) == cudaSuccess) resident = true;
-        else cudaGetLastError();
-    }
-
     // Task scheduler.  commit(i) needs nothing; proof(i) needs commit(i) and the transcript midstate of
     // blob i (host SHA-256, ~9 ms for 16 MiB).  A lane takes the lowest ready proof, else the next
     // commit, so the GPU never idles behind the hashing pool.
@@ -1709,7 +1929,10 @@ static int batch_impl(kzgb_ctx* c, const uint8_t* const* blobs_dev, const uint8_
             int r = KZGB_OK;
             if (!dev_bytes && resident) {
                 uint8_t* slot = (uint8_t*)c->batch_bytes.p + byte_off[i];
-                if (!is_proof && len) {
+                if (i >= dev_first && !dev_failed.load()) {  // went up on the hashing stream
+                    if (!is_proof && cudaStreamWaitEvent(L.st, c->ev_hash_uploaded, 0) != cudaSuccess)
+                        r = fail(c, KZGB_ERR_DEVICE, "CUDA error: cudaStreamWaitEvent failed");
+                } else if (!is_proof && len) {
                     if (cudaMemcpyAsync(slot, blobs_host[i], len, cudaMemcpyHostToDevice, L.st) != cudaSuccess)
                         r = fail(c, KZGB_ERR_DEVICE, "CUDA error: H2D copy of a blob failed");
                 }
@@ -2110,6 +2333,7 @@ int kzgb_set_option(const char* name, long value) {
     if (!strcmp(name, "lane_wait")) { g_lane_wait.store(value < 0 ? -1 : (value ? 1 : 0)); return KZGB_OK; }
     if (!strcmp(name, "stream_priority")) { g_stream_priority.store(value != 0); return KZGB_OK; }
     if (!strcmp(name, "l2_fetch_64")) { g_l2_fetch_64.store(value != 0); return KZGB_OK; }
+    if (!strcmp(name, "device_hash")) { g_device_hash.store(value < 0 ? -1 : (int)value); return KZGB_OK; }
     if (!strcmp(name, "pipelined_upload")) { g_pipelined_upload.store(value != 0); return KZGB_OK; }
     if (!strcmp(name, "batch_keep_mib")) { g_batch_keep_mib.store(value < 0 ? 0 : value); return KZGB_OK; }
     if (!strcmp(name, "fs_quad")) { fs_set_quad((int)value); return KZGB_OK; }

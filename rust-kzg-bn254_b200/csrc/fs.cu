@@ -226,6 +226,111 @@ __global__ void __launch_bounds__(128) k_fs_challenges_quad(const Fr* __restrict
     if (in_domain_out) in_domain_out[k] = (in_domain || force_flag) ? 1u : 0u;
 }
 
+// ---- one WARP per LONG transcript (16 MiB blobs) -----------------------------------------------------------------
+// SHA-256 of one message cannot be spread over threads: block b needs the state after block b - 1, about 64 x 16
+// dependent instructions, which makes a 16 MiB transcript ~150-250 ms of one warp against 9 ms of a SHA-NI core.  As
+// LATENCY that is useless, as THROUGHPUT it is nearly free: a warp takes 1/2368 of the GPU's issue slots, so dozens of
+// transcripts can be hashed next to the MSMs -- which is what a box with 8 GPUs and 32 host threads needs, where the
+// hosts' aggregate SHA-256 rate (38 GB/s) is below what the GPUs consume (8 x 350 blobs/s x 16 MiB = 47 GB/s).
+// Per iteration the 32 lanes each load one of 32 consecutive 64-byte blocks straight from the resident blob BYTES
+// (the transcript hashes the canonical big-endian evaluations, which ARE the blob's bytes; a chunk >= r is reduced in
+// place, helpers.rs:32-34) and expand its message schedule W_t + K_t into registers; then the 32 x 64 rounds run on
+// the whole warp in lockstep, round inputs pulled from lane j by shuffles -- only the chaining state is sequential.
+// Output: the MIDSTATE after tag || u64_be(n) || chunks 0 .. n-2 (the host appends chunk n-1, which shares its block with
+// the commitment, and the commitment itself: challenge_finish).  Messages: blobs of exactly 32 n bytes, n = 2^k >= 4.
+// done[k] (mapped host memory) is set to 1 when state[8k .. 8k+8) is final; *cancel != 0 makes every warp stop early.
+__device__ __forceinline__ void fs_reduce_chunk_be(uint32_t* w) {  // w[0..8): big-endian words of a 256-bit value -> value mod r
+    const uint32_t rm[8] = FR_MOD_LIMBS;                           // little-endian limbs of r
+    if (w[0] < 0x30644e72u) return;                                // below r's top word: canonical (the common case)
+    for (int it = 0; it < 6; it++) {
+        bool ge = true;                                            // w >= r ?
+        for (int j = 0; j < 8; j++) {
+            uint32_t a = w[j], b = rm[7 - j];
+            if (a != b) { ge = a > b; break; }
+        }
+        if (!ge) return;
+        uint32_t borrow = 0;
+        for (int j = 7; j >= 0; j--) {
+            uint64_t d = (uint64_t)w[j] - rm[7 - j] - borrow;
+            w[j] = (uint32_t)d;
+            borrow = (uint32_t)(d >> 63);
+        }
+    }
+}
+static constexpr int FSL_WARPS = 4;  // messages per block: 4 warps x ~128 registers = the footprint of ONE accumulate block
+__global__ void __launch_bounds__(32 * FSL_WARPS) k_fs_midstate_long(const uint8_t* const* __restrict__ blobs, const uint32_t* __restrict__ ns,
+                                                                      uint32_t count, uint32_t* __restrict__ state,
+                                                                      volatile uint32_t* __restrict__ done, const volatile uint32_t* __restrict__ cancel) {
+    const uint32_t k = blockIdx.x * FSL_WARPS + (threadIdx.x >> 5);
+    if (k >= count) return;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n = ns[k];
+    const uint4* src = reinterpret_cast<const uint4*>(blobs[k]);  // 16-byte units; chunk i = units 2i, 2i + 1
+    uint32_t h[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+    uint32_t w[16];
+    auto load_chunk = [&](uint32_t* dst, uint32_t chunk) {
+        uint4 u0 = __ldg(src + 2 * (size_t)chunk), u1 = __ldg(src + 2 * (size_t)chunk + 1);
+        dst[0] = __byte_perm(u0.x, 0, 0x0123); dst[1] = __byte_perm(u0.y, 0, 0x0123);
+        dst[2] = __byte_perm(u0.z, 0, 0x0123); dst[3] = __byte_perm(u0.w, 0, 0x0123);
+        dst[4] = __byte_perm(u1.x, 0, 0x0123); dst[5] = __byte_perm(u1.y, 0, 0x0123);
+        dst[6] = __byte_perm(u1.z, 0, 0x0123); dst[7] = __byte_perm(u1.w, 0, 0x0123);
+        fs_reduce_chunk_be(dst);
+    };
+    {   // block 0: "EIGENDA_FSBLOBVERIFY_V1_" || u64_be(n) || chunk 0   (every lane redundantly: keeps the warp converged)
+        w[0] = 0x45494745; w[1] = 0x4e44415f; w[2] = 0x4653424c; w[3] = 0x4f425645; w[4] = 0x52494659; w[5] = 0x5f56315f;
+        w[6] = 0; w[7] = n;
+        load_chunk(w + 8, 0);
+        sha256_block(h, w);
+    }
+    const uint32_t middle = n / 2 - 1;  // blocks b = 1 .. middle hold chunks 2b - 1, 2b
+    for (uint32_t b0 = 1; b0 <= middle; b0 += 32) {
+        if (((b0 >> 5) & 63u) == 0) {  // every 2048 blocks (128 KiB): one lane looks, the warp decides together
+            uint32_t stop = lane == 0 ? *cancel : 0u;
+            if (__shfl_sync(0xffffffffu, stop, 0)) return;
+        }
+        const uint32_t b = b0 + lane;
+        uint32_t wk[64];
+        if (b <= middle) {
+            load_chunk(w, 2 * b - 1);
+            load_chunk(w + 8, 2 * b);
+            sha256_schedule_k(wk, w);
+        } else {
+#pragma unroll
+            for (int t = 0; t < 64; t++) wk[t] = 0;
+        }
+        const uint32_t cnt = min(32u, middle - b0 + 1);
+        uint32_t a = h[0], bb = h[1], c = h[2], d = h[3], e = h[4], ff = h[5], g = h[6], hh = h[7];
+#pragma unroll 1
+        for (uint32_t j = 0; j < cnt; j++) {
+#pragma unroll
+            for (int t = 0; t < 64; t++) {
+                const uint32_t x = __shfl_sync(0xffffffffu, wk[t], j);
+                const uint32_t pre = hh + x, dp = d + pre;  // off the critical path: hh and d are known rounds ahead
+                const uint32_t S1 = rotr(e, 6) ^ rotr(e, 11) ^ rotr(e, 25);
+                const uint32_t ch = (e & ff) ^ (~e & g);
+                const uint32_t S0 = rotr(a, 2) ^ rotr(a, 13) ^ rotr(a, 22);
+                const uint32_t mj = (a & bb) ^ (a & c) ^ (bb & c);
+                const uint32_t t1 = pre + S1 + ch;
+                hh = g; g = ff; ff = e; e = dp + S1 + ch; d = c; c = bb; bb = a; a = t1 + S0 + mj;
+            }
+            h[0] += a; h[1] += bb; h[2] += c; h[3] += d; h[4] += e; h[5] += ff; h[6] += g; h[7] += hh;
+            a = h[0]; bb = h[1]; c = h[2]; d = h[3]; e = h[4]; ff = h[5]; g = h[6]; hh = h[7];
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) state[8 * (size_t)k + j] = h[j];
+        __threadfence_system();
+        done[k] = 1u;
+    }
+}
+void fs_midstate_long_launch(const uint8_t* const* blobs_dev, const uint32_t* ns_dev, uint32_t count, uint32_t* state_mapped,
+                             uint32_t* done_mapped, const uint32_t* cancel_mapped, cudaStream_t st) {
+    if (!count) return;
+    k_fs_midstate_long<<<(count + FSL_WARPS - 1) / FSL_WARPS, 32 * FSL_WARPS, 0, st>>>(blobs_dev, ns_dev, count, state_mapped, done_mapped, cancel_mapped);
+    g_launch_count++;
+}
+
 // tests: flag every polynomial as "z in the domain" so the device-side choice takes the generic inverses everywhere
 static std::atomic<int> g_fs_force_flag{0};
 void fs_set_force_flag(int on) { g_fs_force_flag.store(on != 0); }

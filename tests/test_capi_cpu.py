@@ -63,6 +63,27 @@ def test_fiat_shamir_challenge_matches_oracle(pkg):
     assert e.value.variant == "NotOnCurveError"
 
 
+def test_verify_proof_g1_side_matches_oracle(pkg):
+    """verifier/src/verify.rs:18-42 on the host side of the library (no GPU needed): C - [y] G1, and the validation errors."""
+    import ctypes as C
+
+    pts = g.srs_points_string()
+    for y in (0, 1, 5, o.R - 1, 0x1234567890ABCDEF1234567890ABCDEF1234567890ABCDEF):
+        cxy, cinf = pkg.g1_to_abi([pts[7]])
+        pxy, pinf = pkg.g1_to_abi([pts[9]])
+        out, inf = C.create_string_buffer(64), C.c_uint8(0)
+        assert pkg.lib.kzgb_verify_proof_g1(None, cxy, cinf[0], pxy, pinf[0], pkg.fr_to_mont_bytes([y]), out, C.byref(inf)) == 0
+        want = o.g1_add(pts[7], o.g1_neg(o.g1_mul(o.G1_GEN, y)))
+        assert pkg.g1_from_abi(out.raw, bytes([inf.value]))[0] == want
+    # C = [y] G -> the identity; a point off the curve -> NotOnCurveError
+    cxy, cinf = pkg.g1_to_abi([o.g1_mul(o.G1_GEN, 77)])
+    out, inf = C.create_string_buffer(64), C.c_uint8(0)
+    assert pkg.lib.kzgb_verify_proof_g1(None, cxy, cinf[0], pxy, pinf[0], pkg.fr_to_mont_bytes([77]), out, C.byref(inf)) == 0 and inf.value == 1
+    bad, binf = pkg.g1_to_abi([(1, 3)])
+    assert pkg.lib.kzgb_verify_proof_g1(None, bad, binf[0], pxy, pinf[0], pkg.fr_to_mont_bytes([1]), out, C.byref(inf)) == -5
+    assert pkg.lib.kzgb_verify_proof_g1(None, cxy, cinf[0], bad, binf[0], pkg.fr_to_mont_bytes([1]), out, C.byref(inf)) == -5
+
+
 def test_host_side_containers(pkg):
     assert pkg.pad_payload(b"hi") == o.pad_payload(b"hi")
     b = pkg.Blob.from_raw_data(g.gettysburg())

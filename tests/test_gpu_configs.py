@@ -94,6 +94,15 @@ def test_config1_gpu_prover_verified_by_the_pairing(pkg):
     assert o.verify_blob_kzg_proof(o.Blob(other), c2, pi2, g2_tau)
     assert not o.verify_blob_kzg_proof(bo, c, pi2, g2_tau)
     assert not o.verify_blob_kzg_proof(bo, c2, pi, g2_tau)
+    # verify_blob_kzg_proof with its G1 side on the GPU (verify.rs:77-115): challenge, evaluation, C - [y] G1; the G2 side and
+    # the pairing on the oracle: e(C - y G1, G2) == e(proof, [tau - z] G2)
+    cmv, z, y = pkg.verify_blob_kzg_proof_g1(blob, c, pi, eng)
+    assert z == o.compute_challenge(bo, c) and y == o.evaluate_polynomial_in_evaluation_form(bo.to_polynomial_eval_form(), z)
+    x_minus_z = o.g2_add(g2_tau, o.g2_neg(o.g2_mul(o.G2_GEN, z)))
+    assert o.pairings_verify(cmv, o.G2_GEN, pi, x_minus_z)
+    cmv_bad, z2, _ = pkg.verify_blob_kzg_proof_g1(blob, c, pi2, eng)
+    assert z2 == z and not o.pairings_verify(cmv_bad, o.G2_GEN, pi2, x_minus_z)
+    assert pkg.verify_proof_g1(c, pi, y, eng) == cmv
     lhs, rhs = pkg.verify_blob_kzg_proof_batch_rlc([blob, blob2], [c, c2], [pi, pi2], eng)
     assert o.pairings_verify(lhs, g2_tau, rhs, o.G2_GEN)
     lhs_bad, rhs_bad = pkg.verify_blob_kzg_proof_batch_rlc([blob, blob2], [c, c2], [pi2, pi], eng)

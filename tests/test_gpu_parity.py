@@ -410,6 +410,68 @@ def test_batch_groups_of_equal_size_blobs(pkg, ref_srs, ref_srs_points):
         assert first[1][i] == o.g1_serialize_compressed(ko.compute_blob_proof(bo, c, ref_srs_points))
 
 
+def test_device_hashed_transcripts_equal_host_hashed(pkg):
+    """Long-transcript hashing on the device (fs.cu k_fs_midstate_long, one warp per blob, from the resident blob bytes)
+    forced on for the tail of a batch: same commitments and proofs as the host SHA-256 pool and as the oracle's
+    compute_challenge.  Covers chunks >= r inside a blob and in its last chunk (reduced in place, helpers.rs:32-34),
+    blobs that do not qualify (ragged length -> host), host-buffer and device-resident entry points, every split."""
+    import ctypes as C
+
+    import torch
+
+    rnd = random.Random(77)
+    n = 1 << 11
+    TAU = o.SYNTH_TAU
+    datas = []
+    for k in range(6):
+        chunks = [rnd.randrange(o.R).to_bytes(32, "big") for _ in range(n)]
+        if k == 1:
+            chunks[5] = (o.R + 12345).to_bytes(32, "big")          # >= r in the middle
+            chunks[2 * 700] = b"\xff" * 32                          # the largest 256-bit value
+        if k == 2:
+            chunks[n - 1] = (2 * o.R + 7).to_bytes(32, "big")      # >= r in the chunk the host appends
+            chunks[0] = (o.R).to_bytes(32, "big")                  # exactly r in block 0
+        datas.append(b"".join(chunks))
+    datas.insert(0, datas[0][: 32 * n - 40])                        # ragged: ends the eligible tail, stays on the host pool
+    blobs = [pkg.Blob.from_unchecked(d) for d in datas]
+    lib = pkg.lib
+    eng = pkg.Engine(0)
+    srs = pkg.SRS.synthetic(n, TAU, engine=eng)
+    outs = {}
+    try:
+        lib.kzgb_set_option(b"group", 0)  # small blobs through the large-blob pipeline (where device hashing lives)
+        for k in (0, 1, 4, 7):
+            lib.kzgb_set_option(b"device_hash", k)
+            outs[k] = pkg.KZG.commit_and_prove_blobs(blobs, srs)
+        # device-resident entry point
+        dev = [torch.frombuffer(bytearray(d), dtype=torch.uint8).cuda() for d in datas]
+        cnt = len(datas)
+        keep = [C.create_string_buffer(d, len(d)) for d in datas]
+        hp = (C.c_void_p * cnt)(*[C.cast(kb, C.c_void_p).value for kb in keep])
+        dp = (C.c_void_p * cnt)(*[t.data_ptr() for t in dev])
+        lens = (C.c_size_t * cnt)(*[len(d) for d in datas])
+        cm, pf = C.create_string_buffer(32 * cnt), C.create_string_buffer(32 * cnt)
+        lib.kzgb_set_option(b"device_hash", 4)
+        eng.check(lib.kzgb_commit_and_prove_blobs_dev(eng.h, dp, hp, lens, cnt, cm, pf))
+        outs["dev"] = ([cm.raw[32 * i : 32 * i + 32] for i in range(cnt)], [pf.raw[32 * i : 32 * i + 32] for i in range(cnt)])
+    finally:
+        lib.kzgb_set_option(b"group", -1)
+        lib.kzgb_set_option(b"device_hash", -1)
+    for k, v in outs.items():
+        assert v == outs[0], k
+    # z of the device-hashed blobs against the oracle's transcript: proof = ((p(tau) - y)/(tau - z)) G needs the right z
+    for i in (2, 3):  # the blobs with chunks >= r
+        bo = o.Blob.from_unchecked(datas[i])
+        c = o.g1_deserialize_compressed(outs[0][0][i])
+        z = o.compute_challenge(bo, c)
+        poly = bo.to_polynomial_eval_form()
+        y = o.evaluate_polynomial_in_evaluation_form(poly, z)
+        ptau = o.evaluate_polynomial_in_evaluation_form(poly, TAU)
+        assert c == o.g1_mul(o.G1_GEN, ptau)
+        q = (ptau - y) * pow(TAU - z, -1, o.R) % o.R
+        assert outs[7][1][i] == o.g1_serialize_compressed(o.g1_mul(o.G1_GEN, q))
+
+
 def test_verify_batch_rlc(pkg, ref_srs, ref_srs_points):
     """verifier/src/batch.rs:16-249 up to the pairing: both G1 outputs equal the oracle's."""
     rnd = random.Random(8)
