@@ -221,6 +221,12 @@ int kzgb_validate_g1_points(kzgb_ctx* ctx, const uint64_t* xy, const uint8_t* in
  *   "pipelined_upload"     1 (default): kzgb_msm_srs / kzgb_msm_srs_range calls of >= 2^22 points over a window table upload
  *                          their host scalars in 4 or 8 chunks, each chunk's sort + bucket accumulation overlapping the next
  *                          chunk's copy (bucket sums folded, one reduction); 0: one copy, then one MSM
+ *   "ntt_kernel"           Fr (I)NTT implementation: 0 passes through shared-memory tiles, 1 warp-resident passes (registers, warp
+ *                          shuffles, bulk asynchronous tile loads), -1 (default) by shape (1 for large batches of transforms of
+ *                          <= 2^13, where it is 27 % faster; 0 elsewhere, where it is up to 12 % faster) -- same results
+ *   "device_hash"          -1 (default): kzgb_commit_and_prove_blobs decides how many transcripts of a large-blob batch are
+ *                          hashed on the device next to the host SHA-256 pool (none unless the host cannot keep up and the
+ *                          batch is ~170+ blobs of 16 MiB deep); 0: none; k > 0: the last k eligible blobs
  *   "fs_quad"              1 (default): four lanes per blob in the device-side Fiat-Shamir hashing
  * The library reads NO environment variables of its own (torchrun's LOCAL_WORLD_SIZE is consulted for "lane_wait" auto).
  * Unknown names return KZGB_ERR_GENERIC. */

@@ -97,6 +97,9 @@ void ntt_twiddles_launch(Fr* tw, int logN, const Fr* omega_mont_host, cudaStream
 void ntt_launch(Fr* data, int logn, uint32_t batch, bool inverse, const Fr* tw, int logN, const Fr* ninv_mont_host,
                 Fr* scratch, cudaStream_t st);
 
+// 0: shared-memory tile passes (default), 1: warp-resident passes (registers + shuffles + bulk copy)
+void ntt_set_kernel(int which);
+
 // ---- G1 inverse NTT (KZG::g1_ifft, prover/src/kzg.rs:263-285) --------------------------
 // srs: 2^logn affine points; work: 2^logn XYZZ scratch; out: 2^logn affine points (natural order).
 // ninv_canon_host: 1/n as a CANONICAL (non-Montgomery) scalar.

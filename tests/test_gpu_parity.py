@@ -159,8 +159,16 @@ def test_to_fr_array_kat(pkg, eng):
     assert pkg.to_byte_array(frs, 100, eng) == o.to_byte_array(frs, 100)
 
 
-@pytest.mark.parametrize("logn", [0, 1, 2, 3, 5, 9, 10, 11, 12, 13])
-def test_ntt_matches_oracle(pkg, eng, logn):
+@pytest.fixture(params=[0, 1], ids=["smem-tiles", "warp-resident"])
+def ntt_kernel(pkg, request):
+    """Both Fr NTT implementations (ntt.cu: shared-memory tile passes, and the register / warp-shuffle / bulk-copy passes)."""
+    pkg.lib.kzgb_set_option(b"ntt_kernel", request.param)
+    yield request.param
+    pkg.lib.kzgb_set_option(b"ntt_kernel", -1)
+
+
+@pytest.mark.parametrize("logn", [0, 1, 2, 3, 4, 5, 7, 8, 9, 10, 11, 12, 13])
+def test_ntt_matches_oracle(pkg, eng, logn, ntt_kernel):
     rnd = random.Random(100 + logn)
     n = 1 << logn
     v = [rnd.randrange(o.R) for _ in range(n)]
@@ -168,8 +176,8 @@ def test_ntt_matches_oracle(pkg, eng, logn):
     assert pkg._ntt(v, True, eng) == o.ifft(v)
 
 
-@pytest.mark.parametrize("logn", [16, 19, 21])
-def test_ntt_roundtrip_large(pkg, eng, logn):
+@pytest.mark.parametrize("logn", [16, 17, 19, 21])
+def test_ntt_roundtrip_large(pkg, eng, logn, ntt_kernel):
     """FFT o IFFT identity (primitives/tests/polynomial_test.rs:47-64) at bench sizes, plus a
     delta-function known answer: fft(e_1)[i] = w^i."""
     import ctypes as C
