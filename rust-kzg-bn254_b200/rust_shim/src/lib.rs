@@ -3,8 +3,17 @@
 //! prover/src/kzg.rs:25-309 and prover/src/srs.rs:10-49 of the reference line by line.
 //!
 //! `KZG` derives PartialEq + Clone over `expanded_roots_of_unity` and `SRS` has pub fields in the
-//! reference, so no device handle is stored inside them: contexts live in a process-global registry
-//! keyed by the address/length of the `SRS.g1` slice.
+//! reference, so no device handle can be stored inside them.  The GPU side of an `SRS` -- a `kzgb_group` over every
+//! visible GPU, holding the decompressed points, window tables and Lagrange tables -- lives in a process-global
+//! registry instead:
+//!   * the key is the (address, length) of the `SRS.g1` slice, the value carries a CONTENT fingerprint (length and 64
+//!     sampled points) that is checked on every hit, so an allocation reused by a different SRS never resolves to
+//!     the old tables;
+//!   * `impl Drop for SRS` removes the entry, which frees the group (HBM tables included) when the last call using it
+//!     returns; the registry also holds at most `MAX_RESIDENT_SRS` groups, least recently used evicted first;
+//!   * the registry lock is held only for the lookup -- calls on different SRS run concurrently, calls on one SRS are
+//!     serialised inside the library;
+//!   * every return code of context creation and SRS upload is checked and surfaces as `KzgError`.
 mod ffi;
 
 use ark_bn254::{Fq, Fr, G1Affine};
@@ -16,19 +25,110 @@ use rust_kzg_bn254_primitives::{
     helpers,
     polynomial::{PolynomialCoeffForm, PolynomialEvalForm},
 };
-use std::{borrow::Cow, collections::HashMap, ffi::CStr, ffi::CString, sync::Mutex};
+use std::{
+    borrow::Cow,
+    collections::HashMap,
+    ffi::CStr,
+    ffi::CString,
+    sync::{Arc, Mutex},
+};
 
 const _: () = assert!(core::mem::size_of::<Fr>() == 32 && core::mem::size_of::<Fq>() == 32);
 
-struct Ctx(*mut ffi::kzgb_ctx);
-unsafe impl Send for Ctx {}
-impl Drop for Ctx {
+/// Groups kept resident at once (each holds an SRS plus its tables on every GPU).
+const MAX_RESIDENT_SRS: usize = 4;
+/// Polynomials at least this long are committed over all GPUs of the group (point-range sharding).
+const GROUP_MSM_MIN_LEN: usize = 1 << 22;
+
+/// One `kzgb_group` (all visible GPUs).  Single-polynomial calls run on member 0; blob batches and very large
+/// coefficient-form commitments are spread over the members by the library.
+struct Gpu {
+    group: *mut ffi::kzgb_group,
+    fingerprint: u64,
+}
+unsafe impl Send for Gpu {}
+unsafe impl Sync for Gpu {} // every entry point of the library locks its context / group internally
+impl Drop for Gpu {
     fn drop(&mut self) {
-        unsafe { ffi::kzgb_ctx_destroy(self.0) }
+        unsafe { ffi::kzgb_group_destroy(self.group) }
+    }
+}
+impl Gpu {
+    fn ctx0(&self) -> *mut ffi::kzgb_ctx {
+        unsafe { ffi::kzgb_group_ctx(self.group, 0) }
+    }
+    fn members(&self) -> usize {
+        unsafe { ffi::kzgb_group_size(self.group) as usize }
     }
 }
 
-static REGISTRY: Mutex<Option<HashMap<(usize, usize), Ctx>>> = Mutex::new(None);
+struct Entry {
+    gpu: Arc<Gpu>,
+    last_use: u64,
+}
+struct Registry {
+    map: HashMap<(usize, usize), Entry>,
+    clock: u64,
+}
+static REGISTRY: Mutex<Option<Registry>> = Mutex::new(None);
+
+/// Length and 64 evenly spaced points (x and y limbs) folded with FNV-1a: cheap enough for every call, and enough to
+/// tell two SRS of equal length apart (they differ in every point beyond the generator).
+fn fingerprint(g1: &[G1Affine]) -> u64 {
+    let mut h: u64 = 0xcbf29ce484222325 ^ g1.len() as u64;
+    let mut mix = |w: u64| {
+        h ^= w;
+        h = h.wrapping_mul(0x100000001b3);
+    };
+    if g1.is_empty() {
+        return h;
+    }
+    for k in 0..64usize {
+        let p = &g1[(k * (g1.len() - 1)) / 63];
+        if p.is_zero() {
+            mix(u64::MAX);
+        } else {
+            for w in p.x.0 .0.iter().chain(p.y.0 .0.iter()) {
+                mix(*w);
+            }
+        }
+    }
+    h
+}
+
+fn group_err(group: *mut ffi::kzgb_group, rc: i32) -> KzgError {
+    let msg = unsafe { CStr::from_ptr(ffi::kzgb_group_last_error(group)) }.to_string_lossy().into_owned();
+    match rc {
+        ffi::KZGB_ERR_SRS_CAPACITY => KzgError::GenericError(msg),
+        ffi::KZGB_ERR_SERIALIZATION => KzgError::SerializationError(msg),
+        ffi::KZGB_ERR_NOT_ON_CURVE => KzgError::NotOnCurveError(msg),
+        ffi::KZGB_ERR_DESERIALIZATION => KzgError::DeserializationError(msg),
+        _ => KzgError::GenericError(msg),
+    }
+}
+
+/// A group over every visible GPU; the caller loads an SRS into it.
+fn new_group() -> Result<*mut ffi::kzgb_group, KzgError> {
+    let mut group = std::ptr::null_mut();
+    let rc = unsafe { ffi::kzgb_group_create(&mut group, std::ptr::null(), 0) };
+    if rc != 0 || group.is_null() {
+        return Err(KzgError::GenericError(format!("no usable CUDA device (kzgb_group_create: {rc})")));
+    }
+    Ok(group)
+}
+
+/// Registers `gpu` for the slice `g1`, evicting the least recently used group beyond `MAX_RESIDENT_SRS`.
+fn register(g1: &[G1Affine], gpu: Arc<Gpu>) {
+    let mut guard = REGISTRY.lock().unwrap();
+    let reg = guard.get_or_insert_with(|| Registry { map: HashMap::new(), clock: 0 });
+    reg.clock += 1;
+    let now = reg.clock;
+    reg.map.insert((g1.as_ptr() as usize, g1.len()), Entry { gpu, last_use: now });
+    while reg.map.len() > MAX_RESIDENT_SRS {
+        let oldest = *reg.map.iter().min_by_key(|(_, e)| e.last_use).map(|(k, _)| k).unwrap();
+        reg.map.remove(&oldest); // the group itself is freed when the last Arc (a call in flight) goes
+    }
+}
 
 fn to_err(ctx: *mut ffi::kzgb_ctx, rc: i32, poly_len: usize, srs_len: usize) -> KzgError {
     let msg = unsafe { CStr::from_ptr(ffi::kzgb_last_error(ctx)) }.to_string_lossy().into_owned();
@@ -82,27 +182,41 @@ pub struct SRS<'a> {
 }
 
 impl SRS<'_> {
-    /// prover/src/srs.rs:35-49: the file is read in one piece and decompressed on the GPU.
+    /// prover/src/srs.rs:35-49: the file is streamed to GPU 0 in chunks and decompressed there, the points are replicated
+    /// to the other GPUs device to device, and read back once to fill the reference's `pub g1` field.
     pub fn new(path_to_g1_points: &str, order: u32, points_to_load: u32) -> Result<Self, KzgError> {
-        let mut ctx = std::ptr::null_mut();
-        if unsafe { ffi::kzgb_ctx_create(&mut ctx, 0, std::ptr::null_mut()) } != 0 {
-            return Err(KzgError::GenericError("no usable CUDA device".into()));
-        }
-        let cpath = CString::new(path_to_g1_points).unwrap();
-        let rc = unsafe { ffi::kzgb_srs_load_file(ctx, cpath.as_ptr(), order, points_to_load) };
+        let group = new_group()?;
+        let cpath = CString::new(path_to_g1_points).map_err(|_| KzgError::GenericError("path contains a NUL byte".into()))?;
+        let rc = unsafe { ffi::kzgb_group_srs_load_file(group, cpath.as_ptr(), order, points_to_load) };
         if rc != 0 {
-            let e = to_err(ctx, rc, 0, 0);
-            unsafe { ffi::kzgb_ctx_destroy(ctx) };
+            let e = group_err(group, rc);
+            unsafe { ffi::kzgb_group_destroy(group) };
             return Err(e);
         }
-        let n = unsafe { ffi::kzgb_srs_len(ctx) };
+        let ctx0 = unsafe { ffi::kzgb_group_ctx(group, 0) };
+        let n = unsafe { ffi::kzgb_srs_len(ctx0) };
         let mut xy = vec![0u64; 8 * n];
         let mut inf = vec![0u8; n];
-        unsafe { ffi::kzgb_srs_get_affine_mont(ctx, 0, n, xy.as_mut_ptr(), inf.as_mut_ptr()) };
+        let rc = unsafe { ffi::kzgb_srs_get_affine_mont(ctx0, 0, n, xy.as_mut_ptr(), inf.as_mut_ptr()) };
+        if rc != 0 {
+            let e = to_err(ctx0, rc, 0, n);
+            unsafe { ffi::kzgb_group_destroy(group) };
+            return Err(e);
+        }
         let g1: Vec<G1Affine> = (0..n).map(|i| unpack_point(xy[8 * i..8 * i + 8].try_into().unwrap(), inf[i])).collect();
-        let key = (g1.as_ptr() as usize, g1.len());
-        REGISTRY.lock().unwrap().get_or_insert_with(HashMap::new).insert(key, Ctx(ctx));
+        register(&g1, Arc::new(Gpu { group, fingerprint: fingerprint(&g1) }));
         Ok(Self { g1: Cow::Owned(g1), order })
+    }
+}
+
+/// Frees the GPU side with the SRS it belongs to (the key is the slice's address: it must not outlive the slice).
+impl Drop for SRS<'_> {
+    fn drop(&mut self) {
+        if let Ok(mut guard) = REGISTRY.lock() {
+            if let Some(reg) = guard.as_mut() {
+                reg.map.remove(&(self.g1.as_ptr() as usize, self.g1.len()));
+            }
+        }
     }
 }
 
@@ -112,10 +226,9 @@ impl SRS<'_> {
     /// instead of on the first commit of that size (the cached form of the `g1_ifft` that
     /// `KZG::commit_eval_form` runs on every call in the reference, prover/src/kzg.rs:98).
     pub fn prepare_lagrange(&self, n: usize) -> Result<(), KzgError> {
-        with_ctx(self, |ctx| {
-            let rc = unsafe { ffi::kzgb_srs_prepare_lagrange(ctx, n) };
-            if rc != 0 { Err(to_err(ctx, rc, n, self.g1.len())) } else { Ok(()) }
-        })
+        let gpu = gpu_for(self)?;
+        let rc = unsafe { ffi::kzgb_group_srs_prepare_lagrange(gpu.group, n) };
+        if rc != 0 { Err(group_err(gpu.group, rc)) } else { Ok(()) }
     }
     /// Writes the decompressed points so that a later process can skip the per-point square root
     /// (`kzgb_srs_load_cache` checks every point to be on the curve instead).
@@ -128,19 +241,48 @@ impl SRS<'_> {
     }
 }
 
-fn with_ctx<T>(srs: &SRS, f: impl FnOnce(*mut ffi::kzgb_ctx) -> T) -> T {
+/// The GPU side of `srs`: looked up under the registry lock, used WITHOUT it.  A hit whose fingerprint does not match
+/// the slice's content (the allocation was reused by another SRS built through the pub fields) is replaced.
+fn gpu_for(srs: &SRS) -> Result<Arc<Gpu>, KzgError> {
     let key = (srs.g1.as_ptr() as usize, srs.g1.len());
-    let mut reg = REGISTRY.lock().unwrap();
-    let map = reg.get_or_insert_with(HashMap::new);
-    let ctx = map.entry(key).or_insert_with(|| {
-        // an SRS built by the caller (pub fields): upload its points once
-        let mut ctx = std::ptr::null_mut();
-        unsafe { ffi::kzgb_ctx_create(&mut ctx, 0, std::ptr::null_mut()) };
-        let (xy, inf) = pack_points(&srs.g1);
-        unsafe { ffi::kzgb_srs_load_affine_mont(ctx, xy.as_ptr(), inf.as_ptr(), srs.g1.len()) };
-        Ctx(ctx)
-    });
-    f(ctx.0)
+    let fp = fingerprint(&srs.g1);
+    {
+        let mut guard = REGISTRY.lock().unwrap();
+        let reg = guard.get_or_insert_with(|| Registry { map: HashMap::new(), clock: 0 });
+        reg.clock += 1;
+        let now = reg.clock;
+        match reg.map.get_mut(&key) {
+            Some(e) if e.gpu.fingerprint == fp => {
+                e.last_use = now;
+                return Ok(e.gpu.clone());
+            }
+            Some(_) => {
+                reg.map.remove(&key); // stale: same address and length, different points
+            }
+            None => {}
+        }
+    }
+    // an SRS built by the caller (pub fields, Cow::Borrowed): upload its points once, outside the lock
+    if srs.g1.is_empty() {
+        return Err(KzgError::GenericError("empty SRS".into()));
+    }
+    let group = new_group()?;
+    let (xy, inf) = pack_points(&srs.g1);
+    let rc = unsafe { ffi::kzgb_group_srs_load_affine_mont(group, xy.as_ptr(), inf.as_ptr(), srs.g1.len()) };
+    if rc != 0 {
+        let e = group_err(group, rc);
+        unsafe { ffi::kzgb_group_destroy(group) };
+        return Err(e);
+    }
+    let gpu = Arc::new(Gpu { group, fingerprint: fp });
+    register(&srs.g1, gpu.clone());
+    Ok(gpu)
+}
+
+/// Runs `f` on member 0's context of the SRS's group (single-polynomial entry points).
+fn with_ctx<T>(srs: &SRS, f: impl FnOnce(*mut ffi::kzgb_ctx) -> Result<T, KzgError>) -> Result<T, KzgError> {
+    let gpu = gpu_for(srs)?;
+    f(gpu.ctx0())
 }
 
 #[derive(Debug, PartialEq, Clone, Default)]
@@ -174,10 +316,18 @@ impl KZG {
     pub fn commit_coeff_form(&self, polynomial: &PolynomialCoeffForm, srs: &SRS) -> Result<G1Affine, KzgError> {
         let (mut xy, mut inf) = ([0u64; 8], 0u8);
         let cf = polynomial.coeffs();
-        with_ctx(srs, |ctx| {
-            let rc = unsafe { ffi::kzgb_commit_coeff(ctx, fr_words(cf), cf.len(), xy.as_mut_ptr(), &mut inf) };
-            if rc != 0 { Err(to_err(ctx, rc, cf.len(), srs.g1.len())) } else { Ok(unpack_point(&xy, inf)) }
-        })
+        let gpu = gpu_for(srs)?;
+        if gpu.members() > 1 && cf.len() >= GROUP_MSM_MIN_LEN {
+            // one MSM cut by point range over every GPU, partial sums added on the host (kzg.rs:107-125 at 2^26 coefficients)
+            if cf.len() > srs.g1.len() {
+                return Err(KzgError::SerializationError("polynomial length is not correct".to_string()));
+            }
+            let rc = unsafe { ffi::kzgb_group_msm_srs(gpu.group, fr_words(cf), cf.len(), xy.as_mut_ptr(), &mut inf) };
+            return if rc != 0 { Err(group_err(gpu.group, rc)) } else { Ok(unpack_point(&xy, inf)) };
+        }
+        let ctx = gpu.ctx0();
+        let rc = unsafe { ffi::kzgb_commit_coeff(ctx, fr_words(cf), cf.len(), xy.as_mut_ptr(), &mut inf) };
+        if rc != 0 { Err(to_err(ctx, rc, cf.len(), srs.g1.len())) } else { Ok(unpack_point(&xy, inf)) }
     }
     pub fn commit_blob(&self, blob: &Blob, srs: &SRS) -> Result<G1Affine, KzgError> {
         let (mut xy, mut inf) = ([0u64; 8], 0u8);
@@ -263,17 +413,18 @@ impl KZG {
         let lens: Vec<usize> = blobs.iter().map(|b| b.data().len()).collect();
         let mut commitments = vec![0u8; 32 * blobs.len()];
         let mut proofs = vec![0u8; 32 * blobs.len()];
-        with_ctx(srs, |ctx| {
-            let rc = unsafe {
-                ffi::kzgb_commit_and_prove_blobs(ctx, ptrs.as_ptr(), lens.as_ptr(), blobs.len(), commitments.as_mut_ptr(), proofs.as_mut_ptr())
-            };
-            if rc != 0 {
-                return Err(to_err(ctx, rc, 0, srs.g1.len()));
-            }
-            Ok((0..blobs.len())
-                .map(|i| (commitments[32 * i..32 * i + 32].try_into().unwrap(), proofs[32 * i..32 * i + 32].try_into().unwrap()))
-                .collect())
-        })
+        let gpu = gpu_for(srs)?;
+        // contiguous shares of the batch, one per GPU of the box (kzgb_group_commit_and_prove_blobs)
+        let rc = unsafe {
+            ffi::kzgb_group_commit_and_prove_blobs(gpu.group, ptrs.as_ptr(), lens.as_ptr(), blobs.len(), commitments.as_mut_ptr(),
+                                                   proofs.as_mut_ptr())
+        };
+        if rc != 0 {
+            return Err(group_err(gpu.group, rc));
+        }
+        Ok((0..blobs.len())
+            .map(|i| (commitments[32 * i..32 * i + 32].try_into().unwrap(), proofs[32 * i..32 * i + 32].try_into().unwrap()))
+            .collect())
     }
 }
 
@@ -284,13 +435,20 @@ impl KZG {
 pub mod backend {
     use super::*;
 
+    struct Ctx(*mut ffi::kzgb_ctx);
+    unsafe impl Send for Ctx {}
+    impl Drop for Ctx {
+        fn drop(&mut self) {
+            unsafe { ffi::kzgb_ctx_destroy(self.0) }
+        }
+    }
     static DEFAULT_CTX: Mutex<Option<Ctx>> = Mutex::new(None);
 
     fn with_default_ctx<T>(f: impl FnOnce(*mut ffi::kzgb_ctx) -> T) -> Result<T, KzgError> {
         let mut guard = DEFAULT_CTX.lock().unwrap();
         if guard.is_none() {
             let mut ctx = std::ptr::null_mut();
-            if unsafe { ffi::kzgb_ctx_create(&mut ctx, 0, std::ptr::null_mut()) } != 0 {
+            if unsafe { ffi::kzgb_ctx_create(&mut ctx, 0, std::ptr::null_mut()) } != 0 || ctx.is_null() {
                 return Err(KzgError::GenericError("no usable CUDA device".into()));
             }
             *guard = Some(Ctx(ctx));
