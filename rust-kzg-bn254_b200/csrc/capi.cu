@@ -16,6 +16,9 @@
 #include <string>
 #include <thread>
 #include <vector>
+#include <sys/resource.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 #include "../../include/kzg_bn254_b200.h"
 #include "../../include/kzg_bn254_b200_bench.h"
@@ -131,6 +134,8 @@ std::atomic<int> g_lane_wait{-1};       // -1 auto, 0 spin on the stream, 1 poll
 std::atomic<int> g_stream_priority{1};  // 1: bucket accumulation on a low-priority stream of its own
 std::atomic<int> g_l2_fetch_64{1};
 std::atomic<int> g_device_hash{-1};        // blobs of a large-blob batch whose transcript is hashed on the device: -1 auto, 0 none, k > 0 the last k
+std::atomic<int> g_hash_nice{1};          // 1: the SHA-256 pool threads of a batch call run at the lowest nice level
+std::atomic<int> g_hash_mb{-1};            // AVX-512 multi-buffer SHA-256 for deep large-blob batches: -1 auto, 0 never, 1 whenever a group of 16 forms
 std::atomic<int> g_pipelined_upload{1};   // 1: host scalars of MSMs of >= 2^22 points over a window table are uploaded in overlapped chunks
 std::atomic<long> g_batch_keep_mib{4096};  // blob staging buffer of kzgb_commit_and_prove_blobs kept between calls up to this size      // 1: contexts that own their stream set the L2 fetch granularity to 64 B
 int fail(kzgb_ctx* c, int code, const std::string& msg) {
@@ -1565,23 +1570,25 @@ int kzgb_verify_blob_proof_g1(kzgb_ctx* c, const uint8_t* blob, size_t len, cons
 
 // ------------------------------------------------------------------------------- blob batches
 constexpr size_t FSL_CAP = 4096;  // transcripts one batch call can hand to the device
-// How many blobs at the END of a large-blob batch get their transcript hashed by the device (k_fs_midstate_long) instead
-// of the host pool.  One transcript is ~0.25 s of one warp however fast the GPU is (SHA-256 is sequential per message),
-// against ~9 ms of a SHA-NI core -- so the device only helps when (a) the host cannot keep up with the GPU (8 ranks on 32
-// hardware threads: 38 GB/s of SHA-256 against 47 GB/s of blobs) and (b) the batch is long enough for 0.25 s to hide
-// behind the commitments of the other blobs.  The model below picks the k that minimises the predicted step time.
-size_t device_hash_share(const size_t* lens, size_t count) {
-    const int opt = g_device_hash.load();
-    if (opt == 0 || count < 2) return 0;
-    // eligible tail: blobs of exactly 32 * 2^j bytes, j >= 10
-    size_t eligible = 0;
-    while (eligible < count && eligible < FSL_CAP) {
-        const size_t len = lens[count - 1 - eligible], n = len / 32;
-        if (len % 32 || n < 1024 || (n & (n - 1))) break;
-        eligible++;
-    }
-    if (opt > 0) return std::min<size_t>((size_t)opt, eligible);
-    if (!eligible) return 0;
+// Who hashes the Fiat-Shamir transcripts of a large-blob batch (everything but the commitment: challenge_midstate).
+//  * single stream: one SHA-NI thread per blob, ~9 ms per 16 MiB, the first challenges ready after 9 ms -- the default
+//    whenever the pool keeps up with the GPU (16 spare cores next to one GPU: 29 GB/s against 6 GB/s of blobs);
+//  * multi-buffer: groups of 16 equal-size blobs hashed in lockstep on AVX-512 (sha256_mb16_blocks), about twice the bytes
+//    per second of a core, the 16 midstates arrive together (~130 ms for 16 MiB blobs) -- for deep batches on a host
+//    whose single-stream pool is slower than the GPU (8 ranks on 32 hardware threads: 38 GB/s against 47 GB/s);
+//  * device: the last k blobs on the GPU next to the MSMs, one warp (0.45 s, 16 % of a blob's MSM work in issue slots) or
+//    one lane (0.9 s: a warp instruction occupies the 16-wide integer ALU for two cycles and the lane does schedule and
+//    rounds alone; half a percent) per transcript -- only a batch several hundred blobs deep hides that latency.
+struct HashPlan {
+    bool mb = false;        // multi-buffer groups on the host
+    size_t mb_threads = 0;  // host threads in multi-buffer mode
+    size_t dev_k = 0;       // transcripts hashed on the device (the last dev_k blobs)
+    bool dev_lanes = false; // k_fs_midstate_lanes instead of k_fs_midstate_long
+};
+bool hash_mb_eligible(size_t len) { const size_t n = len / 32; return len % 32 == 0 && n >= 1024 && (n & (n - 1)) == 0; }
+HashPlan hash_plan(const size_t* lens, size_t count, bool device_possible) {
+    HashPlan hp;
+    if (count < 2) return hp;
     double bytes = 0;
     for (size_t i = 0; i < count; i++) bytes += (double)lens[i];
     const double per_blob = bytes / (double)count;
@@ -1589,19 +1596,64 @@ size_t device_hash_share(const size_t* lens, size_t count) {
     if (hw == 0) hw = 8;
     int procs = g_group_members.load();
     if (const char* w = getenv("LOCAL_WORLD_SIZE")) { int v = atoi(w); if (v > procs) procs = v; }
-    const double host_rate = 1.2e9 * std::max(1.0, std::min<double>((double)hash_pool_threads(), (double)hw / procs));  // B/s, with HT siblings
-    const double t_gpu = 2.9e-3 * per_blob / (double)(16u << 20);  // commit + proof of one blob
-    const double t_dev = 0.45 * per_blob / (double)(16u << 20);    // one transcript on one warp, next to the MSMs
-    double best = std::max(count * t_gpu, bytes / host_rate);
-    size_t best_k = 0;
-    for (size_t k = 1; k <= eligible; k++) {
-        // a hashing warp costs about 16% of a blob's MSM work in integer-pipe time
-        const double t = std::max({(count + 0.16 * k) * t_gpu, (double)(count - k) * per_blob / host_rate, t_dev + k * t_gpu * 0.5});
-        if (t < best * 0.97) { best = t; best_k = k; }
+    const double share = std::max(1.0, (double)hw / procs);                                          // hardware threads of this context
+    const double rate_ni = 1.2e9 * std::max(1.0, std::min<double>((double)hash_pool_threads(), share));  // B/s, HT siblings both hashing
+    const double t_gpu = 2.75e-3 * per_blob / (double)(16u << 20);  // commit + proof of one blob
+    // eligible blobs: exactly 32 * 2^j bytes, j >= 10 (the multi-buffer and device kernels hash whole 64-byte blocks)
+    size_t eligible_total = 0, eligible_tail = 0;
+    for (size_t i = 0; i < count; i++) eligible_total += hash_mb_eligible(lens[i]);
+    while (eligible_tail < count && eligible_tail < FSL_CAP && hash_mb_eligible(lens[count - 1 - eligible_tail])) eligible_tail++;
+    const int mb_opt = g_hash_mb.load();
+    const bool ni_keeps_up = bytes / rate_ni <= 0.8 * count * t_gpu;
+    if (sha256_has_mb16() && mb_opt != 0 && eligible_total >= 16 && (mb_opt == 1 || (!ni_keeps_up && eligible_total >= 32))) {
+        hp.mb = true;
+        const int ht = g_hash_threads.load();
+        hp.mb_threads = (size_t)std::max(1.0, ht > 0 ? (double)ht : share);
     }
-    return best_k;
+    const int dev_opt = device_possible ? g_device_hash.load() : 0;
+    if (dev_opt > 0) { hp.dev_k = std::min<size_t>((size_t)dev_opt, eligible_tail); hp.dev_lanes = fs_midstate_lanes() != 0; return hp; }
+    if (dev_opt == 0 || !eligible_tail) return hp;
+    const double rate_host = hp.mb ? 1.6e9 * (double)hp.mb_threads : rate_ni;
+    double best = std::max(count * t_gpu, bytes / rate_host);
+    for (int lanes = 0; lanes < 2; lanes++) {
+        if (fs_midstate_lanes() >= 0 && lanes != fs_midstate_lanes()) continue;
+        const double t_dev = (lanes ? 0.95 : 0.45) * per_blob / (double)(16u << 20), dev_cost = lanes ? 0.006 : 0.16;
+        for (size_t k = 1; k <= eligible_tail; k++) {
+            // GPU busy time; host time for the front of the batch; the device's share lands at t_dev and its proofs follow
+            const double t = std::max({(count + dev_cost * k) * t_gpu, (double)(count - k) * per_blob / rate_host, t_dev + k * t_gpu * 0.5});
+            if (t < best * 0.97) { best = t; hp.dev_k = k; hp.dev_lanes = lanes != 0; }
+        }
+    }
+    return hp;
 }
-
+// a 32-byte big-endian value >= r inside a transcript block -> its canonical residue (to_fr_array, helpers.rs:32-34)
+void hash_fix_block(uint8_t block[64]) {
+    for (int h = 0; h < 64; h += 32) {
+        uint8_t* ch = block + h;
+        if (ch[0] < 0x30 || memcmp(ch, FR_MOD_BE, 32) < 0) continue;
+        Fr v = fr_from_be_bytes(ch);
+        fe_to_be_bytes(v, ch);
+    }
+}
+// Midstates of up to 16 blobs of exactly 32 n bytes each after tag || u64_be(n) || chunks 0 .. n-2 (all whole blocks),
+// hashed in lockstep; out[m] = 8 state words.  Unused slots repeat blob 0.
+void challenge_midstates_mb16(const uint8_t* const* blobs, size_t members, size_t n, uint32_t out[16][8]) {
+    static const uint32_t iv[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+    alignas(64) uint8_t first[16][64];
+    const uint8_t* p[16];
+    for (size_t m = 0; m < 16; m++) {
+        const uint8_t* blob = blobs[m < members ? m : 0];
+        memcpy(first[m], "EIGENDA_FSBLOBVERIFY_V1_", 24);
+        for (int i = 0; i < 8; i++) first[m][24 + i] = (uint8_t)((uint64_t)n >> (56 - 8 * i));
+        memcpy(first[m] + 32, blob, 32);
+        if (first[m][32] >= 0x30 && memcmp(first[m] + 32, FR_MOD_BE, 32) >= 0) { Fr v = fr_from_be_bytes(first[m] + 32); fe_to_be_bytes(v, first[m] + 32); }
+        memcpy(out[m], iv, 32);
+        p[m] = first[m];
+    }
+    sha256_mb16_blocks(out, p, 1, nullptr);
+    for (size_t m = 0; m < 16; m++) p[m] = blobs[m < members ? m : 0] + 32;  // block b >= 1 holds chunks 2b - 1, 2b
+    sha256_mb16_blocks(out, p, n / 2 - 1, hash_fix_block);
+}
 
 static int batch_impl(kzgb_ctx* c, const uint8_t* const* blobs_dev, const uint8_t* const* blobs_host, const size_t* lens,
                       size_t count, uint8_t* commitments32, uint8_t* proofs32) {
@@ -1679,7 +1731,8 @@ static int batch_impl(kzgb_ctx* c, const uint8_t* const* blobs_dev, const uint8_
     std::mutex mu;
     std::condition_variable cv;
     bool failed = false;
-    const size_t dev_k = (groups.empty() && (blobs_dev || resident)) ? device_hash_share(lens, count) : 0;
+    const HashPlan hplan = groups.empty() ? hash_plan(lens, count, blobs_dev || resident) : HashPlan();
+    const size_t dev_k = hplan.dev_k;
     const size_t dev_first = count - dev_k;
     std::atomic<bool> dev_failed{false}, dev_stop{false};
     volatile uint32_t* fsl_done = nullptr;
@@ -1720,7 +1773,7 @@ static int batch_impl(kzgb_ctx* c, const uint8_t* const* blobs_dev, const uint8_
             if (e == cudaSuccess) e = cudaMemcpyAsync(d_ns, ns.data(), dev_k * 4, cudaMemcpyHostToDevice, c->hash_st);
             if (e == cudaSuccess) e = cudaStreamSynchronize(c->hash_st);  // the argument vectors die with this scope
             if (e == cudaSuccess) {
-                fs_midstate_long_launch(d_ptrs, d_ns, (uint32_t)dev_k, fsl_state, (uint32_t*)fsl_done, (const uint32_t*)fsl_cancel, c->hash_st);
+                fs_midstate_long_launch(d_ptrs, d_ns, (uint32_t)dev_k, fsl_state, (uint32_t*)fsl_done, (const uint32_t*)fsl_cancel, hplan.dev_lanes, c->hash_st);
                 e = cudaGetLastError();
             }
         }
@@ -1759,14 +1812,38 @@ static int batch_impl(kzgb_ctx* c, const uint8_t* const* blobs_dev, const uint8_
             }
         });
     }
+    // Hash tasks in blob order: one blob on a single stream, or a group of up to 16 equal-size blobs in lockstep.
+    struct HashTask { size_t first, members; };
+    std::vector<HashTask> tasks;
+    for (size_t i = 0; i < count;) {
+        size_t j = i + 1;
+        if (hplan.mb && i < dev_first && hash_mb_eligible(lens[i])) {
+            while (j < dev_first && j - i < 16 && lens[j] == lens[i]) j++;
+            if (j - i < 8) j = i + 1;  // a group under half full hashes no faster than its members one by one
+        }
+        tasks.push_back({i, j - i});
+        i = j;
+    }
     std::atomic<size_t> next_hash{0};
-    size_t n_hash = std::max<size_t>(1, std::min<size_t>(count, hash_pool_threads()));
+    size_t n_hash = std::max<size_t>(1, std::min<size_t>(tasks.size(), hplan.mb ? hplan.mb_threads : hash_pool_threads()));
     std::vector<std::thread> hashers;
     for (size_t t = 0; t < n_hash; t++) {
         hashers.emplace_back([&]() {
+            // The pool is pure throughput work; the lane threads next to it are latency work (every microsecond a lane
+            // wakes up late is a microsecond its stream may run dry).  Where both share a few cores (8 ranks on 32
+            // hardware threads) the hashers yield to them: lowest nice level for this thread only.
+            if (g_hash_nice.load()) setpriority(PRIO_PROCESS, (id_t)syscall(SYS_gettid), 19);
             for (;;) {
-                size_t i = next_hash.fetch_add(1);
-                if (i >= count) return;
+                size_t ti = next_hash.fetch_add(1);
+                if (ti >= tasks.size()) return;
+                const size_t i = tasks[ti].first, members = tasks[ti].members;
+                if (members > 1) {
+                    uint32_t st[16][8];
+                    challenge_midstates_mb16(blobs_host + i, members, lens[i] / 32, st);
+                    for (size_t m = 0; m < members; m++) install_device_midstate(i + m, st[m]);
+                    cv.notify_all();
+                    continue;
+                }
                 if (i >= dev_first) {  // the device's share: only if the device path failed
                     std::unique_lock<std::mutex> lk(mu);
                     cv.wait(lk, [&] { return ready[i] != 0 || failed || dev_failed.load() || dev_stop.load(); });
@@ -1887,7 +1964,7 @@ static int batch_impl(kzgb_ctx* c, const uint8_t* const* blobs_dev, const uint8_
         for (int li = 1; li < n_lanes; li++) lane_threads.emplace_back(group_main, li);
         group_main(0);
         for (auto& t : lane_threads) t.join();
-        next_hash.store(count);
+        next_hash.store(tasks.size());
         for (auto& t : hashers) t.join();
         for (int li = 0; li < n_lanes; li++) if (lane_rc[li]) return lane_rc[li];
         return KZGB_OK;
@@ -1966,7 +2043,7 @@ static int batch_impl(kzgb_ctx* c, const uint8_t* const* blobs_dev, const uint8_
     for (int li = 1; li < n_lanes; li++) lane_threads.emplace_back(lane_main, li);
     lane_main(0);
     for (auto& t : lane_threads) t.join();
-    next_hash.store(count);
+    next_hash.store(tasks.size());
     for (auto& t : hashers) t.join();
     if (c->batch_bytes.cap > ((size_t)g_batch_keep_mib.load() << 20)) c->batch_bytes.release();  // bounded residency between calls
     for (int li = 0; li < n_lanes; li++) if (lane_rc[li]) return lane_rc[li];
@@ -2338,6 +2415,9 @@ int kzgb_set_option(const char* name, long value) {
     if (!strcmp(name, "batch_keep_mib")) { g_batch_keep_mib.store(value < 0 ? 0 : value); return KZGB_OK; }
     if (!strcmp(name, "ntt_kernel")) { ntt_set_kernel((int)value); return KZGB_OK; }
     if (!strcmp(name, "fs_quad")) { fs_set_quad((int)value); return KZGB_OK; }
+    if (!strcmp(name, "device_hash_lanes")) { fs_set_midstate_lanes((int)value); return KZGB_OK; }
+    if (!strcmp(name, "hash_nice")) { g_hash_nice.store(value != 0); return KZGB_OK; }
+    if (!strcmp(name, "hash_mb")) { g_hash_mb.store(value < 0 ? -1 : (value ? 1 : 0)); return KZGB_OK; }
     if (!strcmp(name, "group_members")) { g_group_members.store(value < 1 ? 1 : (int)value); return KZGB_OK; }
     if (!strcmp(name, "lagrange")) { g_lagrange.store(value != 0); return KZGB_OK; }
     if (!strcmp(name, "lagrange_after")) { g_lagrange_after.store(value < 1 ? 1 : (int)value); return KZGB_OK; }

@@ -324,10 +324,80 @@ __global__ void __launch_bounds__(32 * FSL_WARPS) k_fs_midstate_long(const uint8
         done[k] = 1u;
     }
 }
+// One LANE per transcript: 32 messages per warp, each lane with its own chaining state, schedule and rounds -- the
+// formulation whose cost per message is 1/32 of the warp-per-message kernel above (about 1.5 k instructions per 64-byte
+// block and lane, 4 x 10^8 warp instructions per 32 transcripts of 16 MiB = 1 % of what the MSMs of those blobs issue),
+// at the same latency: the rounds of one message are a dependent chain either way.  Each lane streams its own blob
+// (64 B per block, the next block's 64 B requested before the current one is compressed, an L2 prefetch four blocks
+// ahead); lanes whose transcript is shorter simply stop earlier.  One warp per block so that the warps spread over SMs.
+__global__ void __launch_bounds__(32) k_fs_midstate_lanes(const uint8_t* const* __restrict__ blobs, const uint32_t* __restrict__ ns,
+                                                           uint32_t count, uint32_t* __restrict__ state,
+                                                           volatile uint32_t* __restrict__ done, const volatile uint32_t* __restrict__ cancel) {
+    const uint32_t k = blockIdx.x * 32u + threadIdx.x;
+    const bool live = k < count;
+    const uint32_t n = live ? ns[k] : 0u;
+    const uint4* src = live ? reinterpret_cast<const uint4*>(blobs[k]) : nullptr;  // 16-byte units; chunk i = units 2i, 2i + 1
+    uint32_t h[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+    uint32_t w[16];
+    auto swap_chunk = [&](uint32_t* dst, const uint4& u0, const uint4& u1) {
+        dst[0] = __byte_perm(u0.x, 0, 0x0123); dst[1] = __byte_perm(u0.y, 0, 0x0123);
+        dst[2] = __byte_perm(u0.z, 0, 0x0123); dst[3] = __byte_perm(u0.w, 0, 0x0123);
+        dst[4] = __byte_perm(u1.x, 0, 0x0123); dst[5] = __byte_perm(u1.y, 0, 0x0123);
+        dst[6] = __byte_perm(u1.z, 0, 0x0123); dst[7] = __byte_perm(u1.w, 0, 0x0123);
+        fs_reduce_chunk_be(dst);
+    };
+    if (live) {  // block 0: "EIGENDA_FSBLOBVERIFY_V1_" || u64_be(n) || chunk 0
+        w[0] = 0x45494745; w[1] = 0x4e44415f; w[2] = 0x4653424c; w[3] = 0x4f425645; w[4] = 0x52494659; w[5] = 0x5f56315f;
+        w[6] = 0; w[7] = n;
+        swap_chunk(w + 8, __ldg(src), __ldg(src + 1));
+        sha256_block(h, w);
+    }
+    const uint32_t middle = live ? n / 2 - 1 : 0u;  // blocks b = 1 .. middle hold chunks 2b - 1, 2b = units 4b - 2 .. 4b + 1
+    uint32_t longest = middle;
+    for (int off = 16; off >= 1; off >>= 1) longest = max(longest, __shfl_xor_sync(0xffffffffu, longest, off));
+    uint4 cur[4];
+    if (1u <= middle) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) cur[j] = __ldg(src + 2 + j);
+    }
+#pragma unroll 1
+    for (uint32_t b = 1; b <= longest; b++) {
+        if ((b & 2047u) == 0) {  // every 128 KiB: one lane looks, the warp decides together
+            uint32_t stop = threadIdx.x == 0 ? *cancel : 0u;
+            if (__shfl_sync(0xffffffffu, stop, 0)) return;
+        }
+        uint4 nxt[4];
+        if (b + 1 <= middle) {
+            const uint4* q = src + 4 * (size_t)(b + 1) - 2;
+#pragma unroll
+            for (int j = 0; j < 4; j++) nxt[j] = __ldg(q + j);
+            if (b + 5 <= middle) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + 16));
+        }
+        if (b <= middle) {
+            swap_chunk(w, cur[0], cur[1]);
+            swap_chunk(w + 8, cur[2], cur[3]);
+            sha256_block(h, w);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) cur[j] = nxt[j];
+    }
+    if (live) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) state[8 * (size_t)k + j] = h[j];
+        __threadfence_system();
+        done[k] = 1u;
+    }
+}
+static std::atomic<int> g_fsl_lanes{-1};  // option "device_hash_lanes": 1 one lane per transcript, 0 one warp per transcript, -1 the caller's model decides
+void fs_set_midstate_lanes(int on) { g_fsl_lanes.store(on < 0 ? -1 : (on != 0)); }
+int fs_midstate_lanes() { return g_fsl_lanes.load(); }
 void fs_midstate_long_launch(const uint8_t* const* blobs_dev, const uint32_t* ns_dev, uint32_t count, uint32_t* state_mapped,
-                             uint32_t* done_mapped, const uint32_t* cancel_mapped, cudaStream_t st) {
+                             uint32_t* done_mapped, const uint32_t* cancel_mapped, bool lanes, cudaStream_t st) {
     if (!count) return;
-    k_fs_midstate_long<<<(count + FSL_WARPS - 1) / FSL_WARPS, 32 * FSL_WARPS, 0, st>>>(blobs_dev, ns_dev, count, state_mapped, done_mapped, cancel_mapped);
+    if (lanes)
+        k_fs_midstate_lanes<<<(count + 31) / 32, 32, 0, st>>>(blobs_dev, ns_dev, count, state_mapped, done_mapped, cancel_mapped);
+    else
+        k_fs_midstate_long<<<(count + FSL_WARPS - 1) / FSL_WARPS, 32 * FSL_WARPS, 0, st>>>(blobs_dev, ns_dev, count, state_mapped, done_mapped, cancel_mapped);
     g_launch_count++;
 }
 

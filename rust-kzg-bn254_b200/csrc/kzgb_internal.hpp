@@ -134,12 +134,14 @@ void eval_set_structured(int on);
 // domain).  commit32_dev: batch x 32 bytes, arkworks-compressed commitments.
 void fs_set_force_flag(int on);
 void fs_set_quad(int on);
-// Midstates of `count` long Fiat-Shamir transcripts on the device, one warp per message, from resident blob BYTES:
+void fs_set_midstate_lanes(int on);  // 1: one lane per long transcript, 0: one warp per transcript, -1 (default): by the batch's depth
+int fs_midstate_lanes();
+// Midstates of `count` long Fiat-Shamir transcripts on the device, one warp (or, lanes = true, one lane) per message, from resident blob BYTES:
 // state[8k..8k+8) = SHA-256 state after tag || u64_be(n) || chunks 0..n-2 of blob k (exactly 32 n bytes, n = ns[k] = 2^j >= 4).
 // state / done / cancel are device-visible pointers to MAPPED pinned host memory: done[k] becomes 1 when state k is final,
 // a non-zero *cancel stops the kernel early.
 void fs_midstate_long_launch(const uint8_t* const* blobs_dev, const uint32_t* ns_dev, uint32_t count, uint32_t* state_mapped,
-                             uint32_t* done_mapped, const uint32_t* cancel_mapped, cudaStream_t st);
+                             uint32_t* done_mapped, const uint32_t* cancel_mapped, bool lanes, cudaStream_t st);
 // in_domain_out (optional, batch words): 1 where z_k turned out to be a root of the domain.
 void fs_challenges_launch(const Fr* evals, uint32_t n, int logn, uint32_t batch, const uint8_t* commit32_dev,
                           const Fr* ninv_mont_host, Fr* z_out, Fr* tinv_out, cudaStream_t st, uint32_t* in_domain_out = nullptr);

@@ -91,6 +91,115 @@ bool sha256_has_shani() {
 #endif
 }
 
+#if defined(__x86_64__)
+// ---------------------------------------------------------------------------------------------------------------
+// Sixteen messages in lockstep, one per 32-bit lane of the AVX-512 registers ("multi-buffer" SHA-256).  A single SHA-NI
+// stream is bound by the latency chain of its 32 sha256rnds2 per block (1.8 GB/s on one core of this box, 2.4 GB/s per
+// core with both hardware threads hashing); here a round is 6 rotates + 4 ternary logic ops + 7 additions for SIXTEEN
+// blocks, so one core sustains about twice that -- at the price of latency: the sixteen digests arrive together.  Used by
+// the blob-batch pipeline when a deep batch meets a host whose SHA-NI pool cannot keep up with the GPU (capi.cu batch_impl).
+// ---------------------------------------------------------------------------------------------------------------
+#define KZ_MB_TARGET __attribute__((target("avx512f,avx512bw,avx512vl")))
+
+KZ_MB_TARGET static inline void transpose16(__m512i r[16]) {
+    __m512i t[16];
+    for (int i = 0; i < 16; i += 2) { t[i] = _mm512_unpacklo_epi32(r[i], r[i + 1]); t[i + 1] = _mm512_unpackhi_epi32(r[i], r[i + 1]); }
+    for (int i = 0; i < 16; i += 4) {
+        r[i] = _mm512_unpacklo_epi64(t[i], t[i + 2]); r[i + 1] = _mm512_unpackhi_epi64(t[i], t[i + 2]);
+        r[i + 2] = _mm512_unpacklo_epi64(t[i + 1], t[i + 3]); r[i + 3] = _mm512_unpackhi_epi64(t[i + 1], t[i + 3]);
+    }
+    // r[4q + j] now holds, in 128-bit lane L, words 4L + j of rows 4q .. 4q + 3
+    for (int j = 0; j < 4; j++) {
+        t[j] = _mm512_shuffle_i32x4(r[j], r[4 + j], 0x88);          // lanes 0, 2 of rows 0-3 | 4-7
+        t[4 + j] = _mm512_shuffle_i32x4(r[j], r[4 + j], 0xdd);      // lanes 1, 3
+        t[8 + j] = _mm512_shuffle_i32x4(r[8 + j], r[12 + j], 0x88);
+        t[12 + j] = _mm512_shuffle_i32x4(r[8 + j], r[12 + j], 0xdd);
+    }
+    for (int j = 0; j < 4; j++) {
+        r[j] = _mm512_shuffle_i32x4(t[j], t[8 + j], 0x88);          // word j       of rows 0 .. 15
+        r[8 + j] = _mm512_shuffle_i32x4(t[j], t[8 + j], 0xdd);      // word 8 + j
+        r[4 + j] = _mm512_shuffle_i32x4(t[4 + j], t[12 + j], 0x88); // word 4 + j
+        r[12 + j] = _mm512_shuffle_i32x4(t[4 + j], t[12 + j], 0xdd);// word 12 + j
+    }
+}
+
+KZ_MB_TARGET void sha256_mb16_blocks(uint32_t st[16][8], const uint8_t* const p[16], size_t nblk, void (*fix)(uint8_t block[64])) {
+    const __m512i BSWAP = _mm512_broadcast_i32x4(_mm_set_epi64x(0x0c0d0e0f08090a0bULL, 0x0405060700010203ULL));
+    const __m512i THIRTY = _mm512_set1_epi8(0x30);
+    __m512i s[16];
+    for (int m = 0; m < 16; m++) s[m] = _mm512_zextsi256_si512(_mm256_loadu_si256((const __m256i*)st[m]));
+    transpose16(s);  // s[j] = state word j of the 16 messages (j < 8)
+    __m512i a = s[0], b = s[1], c = s[2], d = s[3], e = s[4], f = s[5], g = s[6], h = s[7];
+    for (size_t k = 0; k < nblk; k++) {
+        __m512i w[16];
+        for (int m = 0; m < 16; m++) {
+            w[m] = _mm512_loadu_si512((const void*)(p[m] + 64 * k));
+            // a 32-byte chunk whose first byte is >= 0x30 may need the caller's fix-up (value >= r): rare, out of line
+            if (fix && _mm512_mask_cmpge_epu8_mask(0x0000000100000001ULL, w[m], THIRTY)) {
+                alignas(64) uint8_t tmp[64];
+                _mm512_store_si512((void*)tmp, w[m]);
+                fix(tmp);
+                w[m] = _mm512_load_si512((const void*)tmp);
+            }
+            if (k + 4 < nblk) _mm_prefetch((const char*)(p[m] + 64 * (k + 4)), _MM_HINT_T0);
+        }
+        transpose16(w);
+        for (int t = 0; t < 16; t++) w[t] = _mm512_shuffle_epi8(w[t], BSWAP);
+        const __m512i a0 = a, b0 = b, c0 = c, d0 = d, e0 = e, f0 = f, g0 = g, h0 = h;
+#define KZ_ROUND(A, B, C, D, E, F, G, H, T)                                                                                     \
+    do {                                                                                                                        \
+        __m512i S1 = _mm512_ternarylogic_epi32(_mm512_ror_epi32(E, 6), _mm512_ror_epi32(E, 11), _mm512_ror_epi32(E, 25), 0x96); \
+        __m512i t1 = _mm512_add_epi32(_mm512_add_epi32(H, S1), _mm512_add_epi32(_mm512_ternarylogic_epi32(E, F, G, 0xca),       \
+                                                                                 _mm512_add_epi32(w[(T) & 15], _mm512_set1_epi32((int)K256[T])))); \
+        __m512i S0 = _mm512_ternarylogic_epi32(_mm512_ror_epi32(A, 2), _mm512_ror_epi32(A, 13), _mm512_ror_epi32(A, 22), 0x96); \
+        D = _mm512_add_epi32(D, t1);                                                                                            \
+        H = _mm512_add_epi32(t1, _mm512_add_epi32(S0, _mm512_ternarylogic_epi32(A, B, C, 0xe8)));                               \
+    } while (0)
+#define KZ_SCHED(T)                                                                                                             \
+    do {                                                                                                                        \
+        const __m512i w15 = w[((T) + 1) & 15], w2 = w[((T) + 14) & 15];                                                         \
+        __m512i s0 = _mm512_ternarylogic_epi32(_mm512_ror_epi32(w15, 7), _mm512_ror_epi32(w15, 18), _mm512_srli_epi32(w15, 3), 0x96);   \
+        __m512i s1 = _mm512_ternarylogic_epi32(_mm512_ror_epi32(w2, 17), _mm512_ror_epi32(w2, 19), _mm512_srli_epi32(w2, 10), 0x96);    \
+        w[(T) & 15] = _mm512_add_epi32(_mm512_add_epi32(w[(T) & 15], s0), _mm512_add_epi32(w[((T) + 9) & 15], s1));             \
+    } while (0)
+#define KZ_ROUND8(T, SCHED)                                  \
+    do {                                                     \
+        if (SCHED) KZ_SCHED((T) + 0); KZ_ROUND(a, b, c, d, e, f, g, h, (T) + 0); \
+        if (SCHED) KZ_SCHED((T) + 1); KZ_ROUND(h, a, b, c, d, e, f, g, (T) + 1); \
+        if (SCHED) KZ_SCHED((T) + 2); KZ_ROUND(g, h, a, b, c, d, e, f, (T) + 2); \
+        if (SCHED) KZ_SCHED((T) + 3); KZ_ROUND(f, g, h, a, b, c, d, e, (T) + 3); \
+        if (SCHED) KZ_SCHED((T) + 4); KZ_ROUND(e, f, g, h, a, b, c, d, (T) + 4); \
+        if (SCHED) KZ_SCHED((T) + 5); KZ_ROUND(d, e, f, g, h, a, b, c, (T) + 5); \
+        if (SCHED) KZ_SCHED((T) + 6); KZ_ROUND(c, d, e, f, g, h, a, b, (T) + 6); \
+        if (SCHED) KZ_SCHED((T) + 7); KZ_ROUND(b, c, d, e, f, g, h, a, (T) + 7); \
+    } while (0)
+        KZ_ROUND8(0, 0); KZ_ROUND8(8, 0);
+        KZ_ROUND8(16, 1); KZ_ROUND8(24, 1); KZ_ROUND8(32, 1); KZ_ROUND8(40, 1); KZ_ROUND8(48, 1); KZ_ROUND8(56, 1);
+#undef KZ_ROUND8
+#undef KZ_SCHED
+#undef KZ_ROUND
+        a = _mm512_add_epi32(a, a0); b = _mm512_add_epi32(b, b0); c = _mm512_add_epi32(c, c0); d = _mm512_add_epi32(d, d0);
+        e = _mm512_add_epi32(e, e0); f = _mm512_add_epi32(f, f0); g = _mm512_add_epi32(g, g0); h = _mm512_add_epi32(h, h0);
+    }
+    s[0] = a; s[1] = b; s[2] = c; s[3] = d; s[4] = e; s[5] = f; s[6] = g; s[7] = h;
+    for (int j = 8; j < 16; j++) s[j] = _mm512_setzero_si512();
+    transpose16(s);  // s[m] = the 8 state words of message m (low half)
+    for (int m = 0; m < 16; m++) _mm256_storeu_si256((__m256i*)st[m], _mm512_castsi512_si256(s[m]));
+}
+#endif
+
+bool sha256_has_mb16() {
+#if defined(__x86_64__)
+    static const bool has = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512vl");
+    return has;
+#else
+    return false;
+#endif
+}
+#if !defined(__x86_64__)
+void sha256_mb16_blocks(uint32_t[16][8], const uint8_t* const[16], size_t, void (*)(uint8_t[64])) {}
+#endif
+
 static inline void blocks(uint32_t st[8], const uint8_t* p, size_t nblk) {
 #if defined(__x86_64__)
     if (sha256_has_shani()) { blocks_shani(st, p, nblk); return; }

@@ -32,4 +32,22 @@ void t_sha256_chunked(const uint8_t* d, size_t n, size_t step, uint8_t* out) {
     s.finish(out);
 }
 int t_has_shani() { return sha256_has_shani() ? 1 : 0; }
+int t_has_mb16() { return sha256_has_mb16() ? 1 : 0; }
+// 16 messages of nblk 64-byte blocks each, msgs = 16 x (64 nblk) bytes back to back; out = 16 x 8 state words after the blocks
+// (no padding: the raw compression chain).  flip != 0 installs a fix-up that xors 0xff into byte 1 of flagged chunks.
+static void flip_fix(uint8_t b[64]) { if (b[0] >= 0x30) b[1] ^= 0xff; if (b[32] >= 0x30) b[33] ^= 0xff; }
+void t_sha256_mb16(const uint8_t* msgs, size_t nblk, int flip, uint32_t* out) {
+    static const uint32_t iv[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+    uint32_t st[16][8];
+    const uint8_t* p[16];
+    for (int m = 0; m < 16; m++) { for (int j = 0; j < 8; j++) st[m][j] = iv[j]; p[m] = msgs + (size_t)m * 64 * nblk; }
+    sha256_mb16_blocks(st, p, nblk, flip ? flip_fix : nullptr);
+    for (int m = 0; m < 16; m++) for (int j = 0; j < 8; j++) out[8 * m + j] = st[m][j];
+}
+// the same chain through the single-stream implementation (update() without finish): state after nblk blocks
+void t_sha256_state(const uint8_t* msg, size_t nblk, uint32_t* out) {
+    Sha256 s;
+    s.update(msg, 64 * nblk);
+    for (int j = 0; j < 8; j++) out[j] = s.h[j];
+}
 }

@@ -451,6 +451,11 @@ def test_device_hashed_transcripts_equal_host_hashed(pkg):
         for k in (0, 1, 4, 7):
             lib.kzgb_set_option(b"device_hash", k)
             outs[k] = pkg.KZG.commit_and_prove_blobs(blobs, srs)
+        for lanes in (0, 1):  # one warp per transcript / one lane per transcript
+            lib.kzgb_set_option(b"device_hash_lanes", lanes)
+            lib.kzgb_set_option(b"device_hash", 5)
+            outs["lanes%d" % lanes] = pkg.KZG.commit_and_prove_blobs(blobs, srs)
+        lib.kzgb_set_option(b"device_hash_lanes", -1)
         # device-resident entry point
         dev = [torch.frombuffer(bytearray(d), dtype=torch.uint8).cuda() for d in datas]
         cnt = len(datas)
@@ -465,6 +470,7 @@ def test_device_hashed_transcripts_equal_host_hashed(pkg):
     finally:
         lib.kzgb_set_option(b"group", -1)
         lib.kzgb_set_option(b"device_hash", -1)
+        lib.kzgb_set_option(b"device_hash_lanes", -1)
     for k, v in outs.items():
         assert v == outs[0], k
     # z of the device-hashed blobs against the oracle's transcript: proof = ((p(tau) - y)/(tau - z)) G needs the right z
@@ -478,6 +484,57 @@ def test_device_hashed_transcripts_equal_host_hashed(pkg):
         assert c == o.g1_mul(o.G1_GEN, ptau)
         q = (ptau - y) * pow(TAU - z, -1, o.R) % o.R
         assert outs[7][1][i] == o.g1_serialize_compressed(o.g1_mul(o.G1_GEN, q))
+
+
+def test_multibuffer_hashed_transcripts_equal_single_stream(pkg):
+    """Host transcripts hashed 16 at a time on AVX-512 (sha256.cpp sha256_mb16_blocks via capi.cu challenge_midstates_mb16),
+    forced on: same commitments and proofs as the single-stream pool and as the oracle's compute_challenge.  37 blobs =
+    two full groups + a group of 5 that falls back to single streams; values >= r in block 0, in the middle, in the last
+    chunk (which the host appends after the lockstep part) and a ragged blob that splits a run."""
+    if not pkg.lib.kzgb_set_option(b"hash_mb", 1) == 0:
+        pytest.fail("option hash_mb missing")
+    rnd = random.Random(79)
+    n = 1 << 10
+    TAU = o.SYNTH_TAU
+    datas = []
+    for k in range(37):
+        chunks = [rnd.randrange(o.R).to_bytes(32, "big") for _ in range(n)]
+        if k == 3:
+            chunks[0] = (o.R + 5).to_bytes(32, "big")
+            chunks[77] = b"\xff" * 32
+            chunks[78] = (o.R).to_bytes(32, "big")
+        if k == 17:
+            chunks[n - 1] = (3 * o.R + 11).to_bytes(32, "big")
+            chunks[n - 2] = (o.R + 1).to_bytes(32, "big")
+        datas.append(b"".join(chunks))
+    datas[20] = datas[20][: 32 * n - 7]  # ragged: single stream, and it ends the run of equal sizes
+    blobs = [pkg.Blob.from_unchecked(d) for d in datas]
+    lib = pkg.lib
+    eng = pkg.Engine(0)
+    srs = pkg.SRS.synthetic(n, TAU, engine=eng)
+    try:
+        lib.kzgb_set_option(b"group", 0)
+        lib.kzgb_set_option(b"device_hash", 0)
+        lib.kzgb_set_option(b"hash_mb", 0)
+        single = pkg.KZG.commit_and_prove_blobs(blobs, srs)
+        lib.kzgb_set_option(b"hash_mb", 1)
+        multi = pkg.KZG.commit_and_prove_blobs(blobs, srs)
+        lib.kzgb_set_option(b"device_hash", 6)  # multi-buffer groups in front, the device's share behind
+        mixed = pkg.KZG.commit_and_prove_blobs(blobs, srs)
+    finally:
+        lib.kzgb_set_option(b"group", -1)
+        lib.kzgb_set_option(b"device_hash", -1)
+        lib.kzgb_set_option(b"hash_mb", -1)
+    assert multi == single and mixed == single
+    for i in (3, 17):
+        bo = o.Blob.from_unchecked(datas[i])
+        c = o.g1_deserialize_compressed(single[0][i])
+        z = o.compute_challenge(bo, c)
+        poly = bo.to_polynomial_eval_form()
+        y = o.evaluate_polynomial_in_evaluation_form(poly, z)
+        ptau = o.evaluate_polynomial_in_evaluation_form(poly, TAU)
+        q = (ptau - y) * pow(TAU - z, -1, o.R) % o.R
+        assert multi[1][i] == o.g1_serialize_compressed(o.g1_mul(o.G1_GEN, q))
 
 
 def test_verify_batch_rlc(pkg, ref_srs, ref_srs_points):

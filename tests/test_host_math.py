@@ -207,6 +207,33 @@ def test_sha256_matches_hashlib(hm):
                 assert out.raw == hashlib.sha256(data).digest()
 
 
+def test_sha256_multibuffer_matches_single_stream(hm):
+    """AVX-512 multi-buffer SHA-256 (16 messages in lockstep, sha256.cpp sha256_mb16_blocks): the chaining state after
+    nblk blocks of each of the 16 messages equals the single-stream implementation's (itself checked against hashlib
+    above), with and without the per-block fix-up hook (which must see exactly the blocks with a flagged chunk)."""
+    if not hm.t_has_mb16():
+        pytest.skip("no AVX-512 on this host")
+    rnd = random.Random(5)
+    for nblk in (1, 2, 3, 17, 64):
+        msgs = bytearray(rnd.getrandbits(8) for _ in range(16 * 64 * nblk))
+        out = (C.c_uint32 * 128)()
+        hm.t_sha256_mb16(bytes(msgs), nblk, 0, out)
+        for m in range(16):
+            one = (C.c_uint32 * 8)()
+            hm.t_sha256_state(bytes(msgs[m * 64 * nblk : (m + 1) * 64 * nblk]), nblk, one)
+            assert list(out[8 * m : 8 * m + 8]) == list(one), (nblk, m)
+        # fix-up hook: reference = apply the same rewrite to the message, then hash it plainly
+        hm.t_sha256_mb16(bytes(msgs), nblk, 1, out)
+        fixed = bytearray(msgs)
+        for off in range(0, len(fixed), 32):
+            if fixed[off] >= 0x30:
+                fixed[off + 1] ^= 0xFF
+        for m in range(16):
+            one = (C.c_uint32 * 8)()
+            hm.t_sha256_state(bytes(fixed[m * 64 * nblk : (m + 1) * 64 * nblk]), nblk, one)
+            assert list(out[8 * m : 8 * m + 8]) == list(one), ("fix", nblk, m)
+
+
 def test_safegcd_inverse_matches_bigint(hm):
     """fe_inv_fast (Bernstein-Yang division steps, 30-bit batches) against pow(a, -1, p): edge values,
     every bit length, random elements; 0 -> 0 like the Fermat inverse."""
