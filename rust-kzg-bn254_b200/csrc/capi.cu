@@ -60,7 +60,7 @@ struct Lane {
     XYZZ* h_sets = nullptr;   // pinned
     uint32_t* h_entries = nullptr;  // pinned: length of the sorted list of the MSM in flight (= its point additions)
     Fr* h_fr = nullptr;       // pinned, 16 elements
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_done = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_done = nullptr, ev_block = nullptr;
     bool ev_pending = false;
     double acc_ms = 0;        // summed duration of bucket-accumulation kernels
     uint64_t acc_launches = 0;
@@ -99,6 +99,7 @@ struct kzgb_ctx {
     cudaStream_t hash_st = nullptr;
     cudaEvent_t ev_hash_uploaded = nullptr;
     uint32_t* fsl_host = nullptr;
+    std::atomic<bool> lanes_block{false};  // lanes of the running large-blob batch sleep on a blocking event (lane_wait)
     DevBuf fsl_args;
     // upload stream + double-buffer fences of msm_srs_host_pipelined
     cudaStream_t copy_st = nullptr;
@@ -134,6 +135,7 @@ std::atomic<int> g_lane_wait{-1};       // -1 auto, 0 spin on the stream, 1 poll
 std::atomic<int> g_stream_priority{1};  // 1: bucket accumulation on a low-priority stream of its own
 std::atomic<int> g_l2_fetch_64{1};
 std::atomic<int> g_device_hash{-1};        // blobs of a large-blob batch whose transcript is hashed on the device: -1 auto, 0 none, k > 0 the last k
+std::atomic<int> g_hash_trace{0};         // option "hash_trace": 1 = every multi-buffer group reports its wall and CPU time on stderr
 std::atomic<int> g_hash_nice{1};          // 1: the SHA-256 pool threads of a batch call run at the lowest nice level
 std::atomic<int> g_hash_mb{-1};            // AVX-512 multi-buffer SHA-256 for deep large-blob batches: -1 auto, 0 never, 1 whenever a group of 16 forms
 std::atomic<int> g_pipelined_upload{1};   // 1: host scalars of MSMs of >= 2^22 points over a window table are uploaded in overlapped chunks
@@ -299,6 +301,7 @@ int lane_init(kzgb_ctx* c, Lane& L, cudaStream_t st) {
     CK(c, cudaEventCreate(&L.ev0));
     CK(c, cudaEventCreate(&L.ev1));
     CK(c, cudaEventCreateWithFlags(&L.ev_done, cudaEventDisableTiming));
+    CK(c, cudaEventCreateWithFlags(&L.ev_block, cudaEventDisableTiming | cudaEventBlockingSync));
     return KZGB_OK;
 }
 void lane_destroy(Lane& L) {
@@ -310,6 +313,7 @@ void lane_destroy(Lane& L) {
     if (L.ev0) cudaEventDestroy(L.ev0);
     if (L.ev1) cudaEventDestroy(L.ev1);
     if (L.ev_done) cudaEventDestroy(L.ev_done);
+    if (L.ev_block) cudaEventDestroy(L.ev_block);
     if (L.ev_fork) cudaEventDestroy(L.ev_fork);
     if (L.ev_join) cudaEventDestroy(L.ev_join);
     if (L.st_acc) cudaStreamDestroy(L.st_acc);
@@ -566,11 +570,16 @@ int msm_enqueue(kzgb_ctx* c, Lane& L, const Fr* d_scalars, bool canonical, size_
 }
 
 bool lane_wait_polls();
+int lane_wait_mode();
 // Wait for everything queued on the lane.  Spinning by default (a blocking-sync event costs ~0.3 ms per
 // MSM in wake-up latency).  When the ranks on this host have more lane threads than spare cores, spinning
 // lanes starve the SHA-256 pool (8 GPUs x 4 lanes on 32 cores): poll with short sleeps instead.
 int lane_wait(kzgb_ctx* c, Lane& L) {
-    if (lane_wait_polls()) {
+    const int mode = (g_lane_wait.load() < 0 && c->lanes_block.load()) ? 2 : lane_wait_mode();
+    if (mode == 2) {  // sleep in the driver until the GPU's interrupt: no CPU at all while waiting
+        CK(c, cudaEventRecord(L.ev_block, L.st));
+        CK(c, cudaEventSynchronize(L.ev_block));
+    } else if (mode == 1) {
         CK(c, cudaEventRecord(L.ev_done, L.st));
         for (;;) {
             cudaError_t q = cudaEventQuery(L.ev_done);
@@ -797,9 +806,11 @@ Fr challenge_finish(Sha256 sh, const Affine& commitment) {
     return fr_from_be_bytes(dg);  // hash_to_field_element (helpers.rs:382-390)
 }
 
-bool lane_wait_polls() {
+// 0: spin on the stream, 1: poll an event with short sleeps, 2: block on an event (option "lane_wait"; -1 = auto: spin
+// unless the lane threads of the ranks on this host outnumber half of its hardware threads, then poll)
+int lane_wait_mode() {
     const int opt = g_lane_wait.load();
-    if (opt >= 0) return opt == 1;
+    if (opt >= 0) return opt;
     static int mode = -1;
     if (mode < 0) {
         unsigned hw = std::thread::hardware_concurrency();
@@ -807,8 +818,9 @@ bool lane_wait_polls() {
         if (const char* w = getenv("LOCAL_WORLD_SIZE")) { int v = atoi(w); if (v > local) local = v; }  // torchrun: ranks on this host
         mode = ((unsigned)local * 4u > hw / 2u) ? 1 : 0;
     }
-    return mode == 1;
+    return mode;
 }
+bool lane_wait_polls() { return lane_wait_mode() != 0; }
 
 // Host threads for the SHA-256 pool of one context.  One transcript hash is sequential (~9 ms per 16 MiB
 // with SHA-NI).  Measured on the 8-GPU box (32 hardware threads): one thread per blob, even
@@ -1608,12 +1620,12 @@ HashPlan hash_plan(const size_t* lens, size_t count, bool device_possible) {
     if (sha256_has_mb16() && mb_opt != 0 && eligible_total >= 16 && (mb_opt == 1 || (!ni_keeps_up && eligible_total >= 32))) {
         hp.mb = true;
         const int ht = g_hash_threads.load();
-        hp.mb_threads = (size_t)std::max(1.0, ht > 0 ? (double)ht : share);
+        hp.mb_threads = (size_t)std::max(1.0, ht > 0 ? (double)ht : share - 1.0);  // one hardware thread of the share stays with the lanes
     }
     const int dev_opt = device_possible ? g_device_hash.load() : 0;
     if (dev_opt > 0) { hp.dev_k = std::min<size_t>((size_t)dev_opt, eligible_tail); hp.dev_lanes = fs_midstate_lanes() != 0; return hp; }
     if (dev_opt == 0 || !eligible_tail) return hp;
-    const double rate_host = hp.mb ? 1.6e9 * (double)hp.mb_threads : rate_ni;
+    const double rate_host = hp.mb ? 2.4e9 * (double)hp.mb_threads : rate_ni;
     double best = std::max(count * t_gpu, bytes / rate_host);
     for (int lanes = 0; lanes < 2; lanes++) {
         if (fs_midstate_lanes() >= 0 && lanes != fs_midstate_lanes()) continue;
@@ -1687,9 +1699,19 @@ static int batch_impl(kzgb_ctx* c, const uint8_t* const* blobs_dev, const uint8_
     }
     // lanes in flight: 3 keep the GPU full on 16 MiB blobs; small blobs are latency-bound per lane
     // (bucket reduction, host hand-offs), so they get more
+    // Large-blob batches: 6 lanes whose threads SLEEP on a blocking event while their MSM runs (measured against 4 spinning
+    // lanes: 355 -> 362 blobs/s with 16 cores, and the only form that leaves a rank of the 8-GPU box -- 4 hardware threads
+    // -- its cores for hashing: profiles/r02_host_hashing.txt).  The wake-up latency of a blocking event (~0.1-0.3 ms) hides
+    // behind the other lanes; single calls and the latency-bound small-blob groups keep spinning.
     const int lanes_env = g_lanes.load();
-    int want_lanes = lanes_env > 0 ? lanes_env : ((max_n >= ((size_t)1 << 18) && !lane_wait_polls()) ? 4 : 6);
+    const bool deep = groups.empty() && count >= 4;
+    int want_lanes = lanes_env > 0 ? lanes_env : ((max_n >= ((size_t)1 << 18) && !lane_wait_polls() && !deep) ? 4 : 6);
     if (!groups.empty() && lanes_env <= 0) want_lanes = 3;
+    struct LanesBlock {
+        kzgb_ctx* c;
+        LanesBlock(kzgb_ctx* ctx, bool on) : c(ctx) { c->lanes_block.store(on); }
+        ~LanesBlock() { c->lanes_block.store(false); }
+    } lanes_block(c, deep);
     int n_lanes = (int)std::min<size_t>(groups.empty() ? count : groups.size(), (size_t)std::min(want_lanes, MAX_LANES));
     int rc = ensure_lanes(c, n_lanes);
     if (rc) return rc;
@@ -1839,7 +1861,15 @@ static int batch_impl(kzgb_ctx* c, const uint8_t* const* blobs_dev, const uint8_
                 const size_t i = tasks[ti].first, members = tasks[ti].members;
                 if (members > 1) {
                     uint32_t st[16][8];
+                    struct timespec w0, w1, c0, c1;
+                    const bool trace = g_hash_trace.load() != 0;
+                    if (trace) { clock_gettime(CLOCK_MONOTONIC, &w0); clock_gettime(CLOCK_THREAD_CPUTIME_ID, &c0); }
                     challenge_midstates_mb16(blobs_host + i, members, lens[i] / 32, st);
+                    if (trace) {  // option "hash_trace": wall and CPU time of the group -- tells a descheduled pool from a slow one
+                        clock_gettime(CLOCK_MONOTONIC, &w1); clock_gettime(CLOCK_THREAD_CPUTIME_ID, &c1);
+                        fprintf(stderr, "[hash] group at blob %zu (%zu members): wall %.1f ms, cpu %.1f ms\n", i, members,
+                                (w1.tv_sec - w0.tv_sec) * 1e3 + (w1.tv_nsec - w0.tv_nsec) * 1e-6, (c1.tv_sec - c0.tv_sec) * 1e3 + (c1.tv_nsec - c0.tv_nsec) * 1e-6);
+                    }
                     for (size_t m = 0; m < members; m++) install_device_midstate(i + m, st[m]);
                     cv.notify_all();
                     continue;
@@ -2407,7 +2437,7 @@ int kzgb_set_option(const char* name, long value) {
     if (!strcmp(name, "group")) { g_group.store((int)value); return KZGB_OK; }
     if (!strcmp(name, "lanes")) { g_lanes.store(value < 0 ? 0 : (int)value); return KZGB_OK; }
     if (!strcmp(name, "hash_threads")) { g_hash_threads.store(value < 0 ? 0 : (int)value); return KZGB_OK; }
-    if (!strcmp(name, "lane_wait")) { g_lane_wait.store(value < 0 ? -1 : (value ? 1 : 0)); return KZGB_OK; }
+    if (!strcmp(name, "lane_wait")) { g_lane_wait.store(value < 0 ? -1 : (value > 2 ? 2 : (int)value)); return KZGB_OK; }
     if (!strcmp(name, "stream_priority")) { g_stream_priority.store(value != 0); return KZGB_OK; }
     if (!strcmp(name, "l2_fetch_64")) { g_l2_fetch_64.store(value != 0); return KZGB_OK; }
     if (!strcmp(name, "device_hash")) { g_device_hash.store(value < 0 ? -1 : (int)value); return KZGB_OK; }
@@ -2416,12 +2446,14 @@ int kzgb_set_option(const char* name, long value) {
     if (!strcmp(name, "ntt_kernel")) { ntt_set_kernel((int)value); return KZGB_OK; }
     if (!strcmp(name, "fs_quad")) { fs_set_quad((int)value); return KZGB_OK; }
     if (!strcmp(name, "device_hash_lanes")) { fs_set_midstate_lanes((int)value); return KZGB_OK; }
+    if (!strcmp(name, "hash_trace")) { g_hash_trace.store(value != 0); return KZGB_OK; }
     if (!strcmp(name, "hash_nice")) { g_hash_nice.store(value != 0); return KZGB_OK; }
     if (!strcmp(name, "hash_mb")) { g_hash_mb.store(value < 0 ? -1 : (value ? 1 : 0)); return KZGB_OK; }
     if (!strcmp(name, "group_members")) { g_group_members.store(value < 1 ? 1 : (int)value); return KZGB_OK; }
     if (!strcmp(name, "lagrange")) { g_lagrange.store(value != 0); return KZGB_OK; }
     if (!strcmp(name, "lagrange_after")) { g_lagrange_after.store(value < 1 ? 1 : (int)value); return KZGB_OK; }
     if (!strcmp(name, "lagrange_budget_mib")) { g_lagrange_budget_mib.store(value < 0 ? 0 : value); return KZGB_OK; }
+    if (!strcmp(name, "acc_prefetch")) { msm_set_acc_prefetch((int)value); return KZGB_OK; }
     if (!strcmp(name, "acc_waves")) { msm_set_acc_waves((int)value); return KZGB_OK; }
     if (!strcmp(name, "msm_debug_sync")) { msm_set_debug_sync((int)value); return KZGB_OK; }
     if (!strcmp(name, "acc_regs")) { msm_set_experiment((int)value, -1); return KZGB_OK; }

@@ -591,6 +591,11 @@ def test_msm_exceptional_pairs_exact(pkg, eng, ref_srs, ref_srs_points, waves):
         sc = [0x1234567890ABCDEF1234567890ABCDEF] * 2048
         assert kzg.commit_coeff_form(pkg.PolynomialCoeffForm(sc), ref_srs) == o.msm(ref_srs_points[:2048], sc)
         assert kzg.commit_coeff_form(pkg.PolynomialCoeffForm([0] * 64), ref_srs) is None
+        # many points, few distinct digits: hot buckets that span dozens of chunks of either tier
+        sc = [rnd.choice([3, 1 << 40, o.R - 2]) for _ in range(2048)]
+        assert kzg.commit_coeff_form(pkg.PolynomialCoeffForm(sc), ref_srs) == o.msm(ref_srs_points[:2048], sc)
+        sc = [rnd.randrange(o.R) for _ in range(2048)]
+        assert kzg.commit_coeff_form(pkg.PolynomialCoeffForm(sc), ref_srs) == o.msm(ref_srs_points[:2048], sc)
     finally:
         pkg.lib.kzgb_set_option(b"acc_waves", 4)
 
