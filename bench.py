@@ -49,32 +49,70 @@ def make_blob(n_elems: int, seed: int):
 
 
 class ClockSampler(threading.Thread):
-    def __init__(self, index: int):
-        super().__init__(daemon=True)
-        self.index = index
-        self.rows = []
-        self.stop_flag = False
+    """SM clocks and throttle reasons DURING the timed region.  NVML in-process (nvidia_ml_py: the library nvidia-smi itself
+    reads) when importable, the nvidia-smi binary otherwise -- a forked nvidia-smi costs ~0.15 CPU-seconds per call on an 8-GPU
+    box, which eight ranks cannot spare while they hash 47 GB/s of transcripts.  Only rank 0 samples, every GPU of the job."""
 
-    def run(self):
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
+    def __init__(self, indices):
+        super().__init__(daemon=True)
+        self.indices = [indices] if isinstance(indices, int) else list(indices)
+        self.rows = []  # (sm_mhz, max_mhz, [reason flags])
+        self.stop_flag = False
+        self.nvml = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handles = [pynvml.nvmlDeviceGetHandleByIndex(i) for i in self.indices]
+        except Exception:
+            self.nvml = None
+
+    def sample_nvml(self):
+        nv = self.nvml
+        bits = [nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else nv.nvmlClocksThrottleReasonHwSlowdown,
+                nv.nvmlClocksEventReasonHwThermalSlowdown if hasattr(nv, "nvmlClocksEventReasonHwThermalSlowdown") else nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                nv.nvmlClocksEventReasonSwThermalSlowdown if hasattr(nv, "nvmlClocksEventReasonSwThermalSlowdown") else nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                nv.nvmlClocksEventReasonSwPowerCap if hasattr(nv, "nvmlClocksEventReasonSwPowerCap") else nv.nvmlClocksThrottleReasonSwPowerCap]
+        for h in self.handles:
+            sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            try:
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+            except Exception:
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            self.rows.append((sm, mx, [bool(r & b) for b in bits]))
+
+    def sample_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", ",".join(map(str, self.indices))],
+                             capture_output=True, text=True, timeout=10).stdout.strip()
+        for line in out.splitlines():
+            r = [x.strip() for x in line.split(",")]
+            if len(r) >= 6 and r[0].isdigit() and r[1].isdigit():
+                self.rows.append((int(r[0]), int(r[1]), [r[2 + i].lower().startswith("active") for i in range(4)]))
+
+    def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                if self.nvml:
+                    self.sample_nvml()
+                else:
+                    self.sample_smi()
             except Exception:
                 pass
             time.sleep(0.2)
 
     def summary(self):
-        sm = [int(r[0]) for r in self.rows if r[0].isdigit()]
-        mx = [int(r[1]) for r in self.rows if r[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) >= 6 and r[2 + i].lower().startswith("active")})
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        sm = [r[0] for r in self.rows]
+        mx = [r[1] for r in self.rows]
+        reasons = sorted({self.NAMES[i] for r in self.rows for i in range(4) if r[2][i]})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_min_mhz": min(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm), "gpus_sampled": len(self.indices),
+                "source": "NVML in-process (nvidia_ml_py)" if self.nvml else "nvidia-smi"}
 
 
 def load_oracle_lib():
@@ -225,15 +263,22 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    import resource
+
+    cpu_used = []  # process CPU seconds (user + system, all threads) of each timed leg on this rank
+
     def timed(fn, steps):
         ms = C.c_double(0)
         barrier()
+        ru0 = resource.getrusage(resource.RUSAGE_SELF)
         w0 = time.perf_counter()
         eng.check(lib.kzgb_timer_begin(eng.h))
         for _ in range(steps):
             fn()
         eng.check(lib.kzgb_timer_end(eng.h, C.byref(ms)))
         wall = (time.perf_counter() - w0) * 1e3
+        ru1 = resource.getrusage(resource.RUSAGE_SELF)
+        cpu_used.append((ru1.ru_utime - ru0.ru_utime) + (ru1.ru_stime - ru0.ru_stime))
         barrier()
         t = torch.tensor([ms.value, wall], device="cuda", dtype=torch.float64)
         if world > 1:
@@ -243,8 +288,9 @@ def main():
     for _ in range(args.warmup):
         step_dev()
     lib.kzgb_stats(eng.h, None, None, None, 1)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler = ClockSampler(range(world) if rank == 0 else [])  # one node: the job's GPUs are 0 .. world-1
+    if rank == 0:
+        sampler.start()
     l0 = eng.launch_count()
     dev_ms, dev_wall = timed(step_dev, args.steps)
     launches = eng.launch_count() - l0
@@ -256,7 +302,8 @@ def main():
         step_e2e()
     e2e_ms, e2e_wall = timed(step_e2e, args.steps)
     sampler.stop_flag = True
-    sampler.join(timeout=2)
+    if rank == 0:
+        sampler.join(timeout=2)
     assert (cm.raw, pf.raw) == out_dev, "device-resident and host-buffer paths disagree"
 
     # the same pipeline fed 16 blobs per call (round 1's step; shallow batches leave fill / drain bubbles and cannot use the
@@ -432,6 +479,9 @@ def main():
         "cpu_baseline": cpu_baseline,
         "extra": {"msm_mpts": msm_leg, "batch16": batch16},
         "wall_ms_per_step": dev_wall / args.steps, "setup_s": setup_s,
+        "host_cpu_ms_per_blob": {"resident": 1e3 * cpu_used[0] / (B * args.steps), "e2e": 1e3 * cpu_used[1] / (B * args.steps),
+                                 "note": "rank 0's process CPU time (user + system, every thread: lanes, SHA-256 pool, driver) per blob inside the "
+                                         "timed legs; a 16 MiB transcript alone is 9.2 ms of a SHA-NI core or 4.4 ms of an AVX-512 multi-buffer thread"},
         "single_blob_latency_ms": {"value": single_blob_ms, "note": "one 16 MiB blob through kzgb_commit_and_prove_blobs from host memory; "
                                    "bounded below by the sequential SHA-256 of the 16 MiB Fiat-Shamir transcript on one host core (~9 ms), "
                                    "which overlaps the commitment MSM; GPU work is ~4.5 ms of it"},

@@ -212,8 +212,10 @@ int kzgb_validate_g1_points(kzgb_ctx* ctx, const uint64_t* xy, const uint8_t* in
  *   "lagrange_after", "lagrange_budget_mib"   the table policy described at kzgb_srs_prepare_lagrange
  *   "lanes"                lanes (host thread + streams) of the blob-batch pipelines, 0 = the library's choice
  *   "hash_threads"         host SHA-256 pool threads of a batch call, 0 = the library's choice
- *   "lane_wait"            -1 auto, 0 lanes spin on their stream, 1 lanes poll with short sleeps (when lane threads
- *                          outnumber spare cores)
+ *   "lane_wait"            how a lane thread waits for its MSM: 0 spins on the stream, 1 polls an event with short sleeps, 2 sleeps on a
+ *                          blocking event; -1 (default): deep large-blob batches (>= 32 blobs, or >= 4 when cores are plentiful) run 6
+ *                          lanes in mode 2, everything else spins -- or polls when the lane threads of the ranks on this host
+ *                          outnumber half of its hardware threads
  *   "stream_priority"      1 (default): bucket accumulation runs on a low-priority stream of its lane
  *   "l2_fetch_64"          1 (default): contexts that own their stream set the device's L2 fetch granularity to 64 B
  *                          (random 64-byte gathers) and restore it when the last of them is destroyed
@@ -224,11 +226,20 @@ int kzgb_validate_g1_points(kzgb_ctx* ctx, const uint64_t* xy, const uint8_t* in
  *   "ntt_kernel"           Fr (I)NTT implementation: 0 passes through shared-memory tiles, 1 warp-resident passes (registers, warp
  *                          shuffles, bulk asynchronous tile loads), -1 (default) by shape (1 for large batches of transforms of
  *                          <= 2^13, where it is 27 % faster; 0 elsewhere, where it is up to 12 % faster) -- same results
+ *   "hash_mb"              -1 (default): kzgb_commit_and_prove_blobs hashes the transcripts of a large-blob batch sixteen at a time on
+ *                          AVX-512 (multi-buffer SHA-256: ~2x the bytes per second of a core's SHA-NI, the 16 digests arrive together)
+ *                          when the single-stream pool of this context's share of the host is slower than the GPU and >= 32 blobs
+ *                          of exactly 32 * 2^j bytes are in the batch; 0: never; 1: whenever a group of >= 8 forms
+ *   "hash_nice"            1 (default): the SHA-256 pool threads of a batch call run at nice 19, so a waking lane thread preempts them
+ *   "hash_trace"           1: every multi-buffer group reports its wall and CPU time on stderr
  *   "device_hash"          -1 (default): kzgb_commit_and_prove_blobs decides how many transcripts of a large-blob batch are
- *                          hashed on the device next to the host SHA-256 pool (none unless the host cannot keep up and the
- *                          batch is ~170+ blobs of 16 MiB deep); 0: none; k > 0: the last k eligible blobs
+ *                          hashed on the device next to the host pool (none unless the host cannot keep up even with "hash_mb" and
+ *                          the batch is several hundred blobs deep); 0: none; k > 0: the last k eligible blobs
+ *   "device_hash_lanes"    device kernel for those: 0 one warp per transcript (0.45 s, 16 % of a blob's MSM work each), 1 one lane per
+ *                          transcript (0.9 s, 0.5 %), -1 (default): whichever the batch's depth favours
  *   "fs_quad"              1 (default): four lanes per blob in the device-side Fiat-Shamir hashing
- * The library reads NO environment variables of its own (torchrun's LOCAL_WORLD_SIZE is consulted for "lane_wait" auto).
+ * The library reads NO environment variables of its own (torchrun's LOCAL_WORLD_SIZE is consulted for the "lane_wait" and "hash_mb"
+ * auto decisions: how many ranks share this host's hardware threads).
  * Unknown names return KZGB_ERR_GENERIC. */
 int kzgb_set_option(const char* name, long value);
 /* ---- single-proof verification up to the pairing (verifier/src/verify.rs) ---------------------------------------------

@@ -54,7 +54,6 @@ void msm_workspace_carve(const MsmPlan& p, void* base, MsmWorkspace* ws);
 MsmPlan msm_make_plan(uint32_t n, int c, bool fixed_base, uint32_t table_stride, uint32_t base_offset, uint32_t batch = 0);
 // waves of accumulate blocks (4 blocks of 128 threads per SM and wave) the sorted list is cut into; default 4
 void msm_set_acc_waves(int waves);
-void msm_set_acc_prefetch(int on);
 void msm_set_debug_sync(int on);
 void msm_set_experiment(int acc_regs, int sort_block);
 

@@ -211,7 +211,6 @@ __device__ __forceinline__ bool xyzz_madd_relaxed_nonempty(XYZZ& acc, const Affi
 // Thread t owns sorted entries [t*chunk, (t+1)*chunk).  A bucket run that lies entirely inside the chunk is
 // written to buckets[b]; the run cut by the chunk's start goes to partial[2t], the one cut by its end to
 // partial[2t+1] (k_bucket_fix adds them up).
-template <bool PF>
 __device__ __forceinline__ void accumulate_body(const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ offsets,
                                                 const Affine* __restrict__ table, uint32_t nb, uint32_t acc_threads,
                                                 uint32_t chunk, XYZZ* __restrict__ buckets, XYZZ* __restrict__ partial) {
@@ -244,10 +243,6 @@ __device__ __forceinline__ void accumulate_body(const uint32_t* __restrict__ sor
     for (uint32_t pos = start; pos < end; pos++) {
         const uint32_t ref = sorted[pos];
         Affine q = aff_gather_ro(&table[ref & 0x7fffffffu]);
-        if (PF && pos + 1 < end) {  // the next point of this chunk: ask L2 for it now, a whole addition ahead of its use
-            const uint32_t nref = sorted[pos + 1];
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(table + (nref & 0x7fffffffu)));
-        }
         if (pos >= next) boundary(pos);
         if (aff_is_inf(q)) continue;  // an identity point in the table (SRS files may hold them)
         fq_cneg_ptx(q.y.l, q.y.l, ref & 0x80000000u);
@@ -265,13 +260,7 @@ __device__ __forceinline__ void accumulate_body(const uint32_t* __restrict__ sor
 __global__ void __launch_bounds__(128, 4) k_accumulate(const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ offsets,
                                                         const Affine* __restrict__ table, uint32_t nb, uint32_t acc_threads,
                                                         uint32_t chunk, XYZZ* __restrict__ buckets, XYZZ* __restrict__ partial) {
-    accumulate_body<false>(sorted, offsets, table, nb, acc_threads, chunk, buckets, partial);
-}
-// EXPERIMENT (option "acc_prefetch"): the same with an L2 prefetch of the next point of the chunk
-__global__ void __launch_bounds__(128, 4) k_accumulate_pf(const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ offsets,
-                                                           const Affine* __restrict__ table, uint32_t nb, uint32_t acc_threads,
-                                                           uint32_t chunk, XYZZ* __restrict__ buckets, XYZZ* __restrict__ partial) {
-    accumulate_body<true>(sorted, offsets, table, nb, acc_threads, chunk, buckets, partial);
+    accumulate_body(sorted, offsets, table, nb, acc_threads, chunk, buckets, partial);
 }
 // EXPERIMENT (option "acc_regs"): the same body under a hard register cap, so that four blocks leave part of the
 // register file free and the short sort kernels of the other lanes can be resident NEXT TO the accumulation
@@ -279,7 +268,7 @@ template <int MAXR>
 __global__ void __maxnreg__(MAXR) k_accumulate_capped(const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ offsets,
                                                        const Affine* __restrict__ table, uint32_t nb, uint32_t acc_threads,
                                                        uint32_t chunk, XYZZ* __restrict__ buckets, XYZZ* __restrict__ partial) {
-    accumulate_body<false>(sorted, offsets, table, nb, acc_threads, chunk, buckets, partial);
+    accumulate_body(sorted, offsets, table, nb, acc_threads, chunk, buckets, partial);
 }
 
 // Buckets whose entries span more than LONG_SPAN chunks (hot buckets: equal scalars, a top window with a
@@ -570,8 +559,6 @@ __global__ void __launch_bounds__(32) k_reduce_final(const XYZZ* __restrict__ gr
 // ---------------------------------------------------------------------------------
 static std::atomic<int> g_acc_waves{4};
 static std::atomic<int> g_acc_regs{0}, g_sort_block{256};
-static std::atomic<int> g_acc_prefetch{0};
-void msm_set_acc_prefetch(int on) { g_acc_prefetch.store(on != 0); }
 void msm_set_experiment(int acc_regs, int sort_block) {
     if (acc_regs >= 0) g_acc_regs.store(acc_regs);
     if (sort_block == 64 || sort_block == 128 || sort_block == 256) g_sort_block.store(sort_block);
@@ -703,7 +690,7 @@ void msm_launch_buckets(const MsmPlan& p, const MsmWorkspace& ws, const Fr* scal
             case 112: KZ_ACC(k_accumulate_capped<112>); break;
             case 104: KZ_ACC(k_accumulate_capped<104>); break;
             case 96: KZ_ACC(k_accumulate_capped<96>); break;
-            default: if (g_acc_prefetch.load()) KZ_ACC(k_accumulate_pf); else KZ_ACC(k_accumulate); break;
+            default: KZ_ACC(k_accumulate); break;
         }
 #undef KZ_ACC
     }
