@@ -1616,7 +1616,9 @@ HashPlan hash_plan(const size_t* lens, size_t count, bool device_possible) {
     for (size_t i = 0; i < count; i++) eligible_total += hash_mb_eligible(lens[i]);
     while (eligible_tail < count && eligible_tail < FSL_CAP && hash_mb_eligible(lens[count - 1 - eligible_tail])) eligible_tail++;
     const int mb_opt = g_hash_mb.load();
-    const bool ni_keeps_up = bytes / rate_ni <= 0.8 * count * t_gpu;
+    // "keeps up" = the single-stream pool needs at most half of this context's hardware threads for the duration of the GPU work:
+    // the other half belongs to the lanes and the driver (measured on 4 hardware threads per rank: 291 blobs/s single stream, 367 multi-buffer)
+    const bool ni_keeps_up = bytes / rate_ni <= 0.5 * count * t_gpu;
     if (sha256_has_mb16() && mb_opt != 0 && eligible_total >= 16 && (mb_opt == 1 || (!ni_keeps_up && eligible_total >= 32))) {
         hp.mb = true;
         const int ht = g_hash_threads.load();
