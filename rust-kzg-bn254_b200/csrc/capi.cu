@@ -1586,8 +1586,9 @@ constexpr size_t FSL_CAP = 4096;  // transcripts one batch call can hand to the 
 //  * single stream: one SHA-NI thread per blob, ~9 ms per 16 MiB, the first challenges ready after 9 ms -- the default
 //    whenever the pool keeps up with the GPU (16 spare cores next to one GPU: 29 GB/s against 6 GB/s of blobs);
 //  * multi-buffer: groups of 16 equal-size blobs hashed in lockstep on AVX-512 (sha256_mb16_blocks), about twice the bytes
-//    per second of a core, the 16 midstates arrive together (~130 ms for 16 MiB blobs) -- for deep batches on a host
-//    whose single-stream pool is slower than the GPU (8 ranks on 32 hardware threads: 38 GB/s against 47 GB/s);
+//    per second of a core, the 16 midstates arrive together (71-80 ms for 16 MiB blobs) -- for deep batches on a host
+//    whose single-stream pool is slower than the GPU (8 ranks on 32 hardware threads: 36 GB/s against 49 GB/s;
+//    profiles/r02_scale8.txt: 2184 -> 2857 blobs/s);
 //  * device: the last k blobs on the GPU next to the MSMs, one warp (0.45 s, 16 % of a blob's MSM work in issue slots) or
 //    one lane (0.9 s: a warp instruction occupies the 16-wide integer ALU for two cycles and the lane does schedule and
 //    rounds alone; half a percent) per transcript -- only a batch several hundred blobs deep hides that latency.
@@ -1702,8 +1703,8 @@ static int batch_impl(kzgb_ctx* c, const uint8_t* const* blobs_dev, const uint8_
     // lanes in flight: 3 keep the GPU full on 16 MiB blobs; small blobs are latency-bound per lane
     // (bucket reduction, host hand-offs), so they get more
     // Large-blob batches: 6 lanes whose threads SLEEP on a blocking event while their MSM runs (measured against 4 spinning
-    // lanes: 355 -> 362 blobs/s with 16 cores, and the only form that leaves a rank of the 8-GPU box -- 4 hardware threads
-    // -- its cores for hashing: profiles/r02_host_hashing.txt).  The wake-up latency of a blocking event (~0.1-0.3 ms) hides
+    // lanes: 342 -> 353 blobs/s e2e with 16 hardware threads, and the only form that leaves a rank of the 8-GPU box -- 4
+    // hardware threads -- its cores for hashing: profiles/r02_host_hashing.txt, r02_scale8.txt).  The wake-up latency of a blocking event (~0.1-0.3 ms) hides
     // behind the other lanes; single calls and the latency-bound small-blob groups keep spinning.
     const int lanes_env = g_lanes.load();
     // (a rank short of cores -- lane_wait auto = poll -- with a shallow batch is the exception: 4 polling lanes, measured 316
