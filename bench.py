@@ -58,6 +58,9 @@ class ClockSampler(threading.Thread):
     def __init__(self, indices):
         super().__init__(daemon=True)
         self.indices = [indices] if isinstance(indices, int) else list(indices)
+        # CUDA ordinals -> what NVML / nvidia-smi address: they enumerate every GPU of the box, whatever CUDA_VISIBLE_DEVICES says
+        vis = [t.strip() for t in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if t.strip()]
+        self.targets = [vis[i] if i < len(vis) else str(i) for i in self.indices]
         self.rows = []  # (sm_mhz, max_mhz, [reason flags])
         self.stop_flag = False
         self.nvml = None
@@ -65,8 +68,17 @@ class ClockSampler(threading.Thread):
             import pynvml
 
             pynvml.nvmlInit()
+            handles = []
+            for t in self.targets:
+                if t.isdigit():
+                    handles.append(pynvml.nvmlDeviceGetHandleByIndex(int(t)))
+                else:
+                    try:
+                        handles.append(pynvml.nvmlDeviceGetHandleByUUID(t))
+                    except TypeError:
+                        handles.append(pynvml.nvmlDeviceGetHandleByUUID(t.encode()))
+            self.handles = handles
             self.nvml = pynvml
-            self.handles = [pynvml.nvmlDeviceGetHandleByIndex(i) for i in self.indices]
         except Exception:
             self.nvml = None
 
@@ -88,7 +100,7 @@ class ClockSampler(threading.Thread):
     def sample_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", ",".join(map(str, self.indices))],
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", ",".join(self.targets)],
                              capture_output=True, text=True, timeout=10).stdout.strip()
         for line in out.splitlines():
             r = [x.strip() for x in line.split(",")]
