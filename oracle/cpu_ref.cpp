@@ -23,7 +23,6 @@
 #include <thread>
 #include <vector>
 
-#include "../rust-kzg-bn254_b200/csrc/sha256.hpp"  // SHA-256 only (checked against hashlib in tests)
 
 typedef unsigned __int128 u128;
 
@@ -383,6 +382,52 @@ bool lex_largest(const Fp& y_mont) {
     for (int i = 3; i >= 0; i--) if (c.v[i] != HALF[i]) return c.v[i] > HALF[i];
     return false;
 }
+// SHA-256 (FIPS 180-4), the oracle's OWN plain implementation: the product's sha256.cpp (SHA-NI, AVX-512 multi-buffer) is
+// one of the things this oracle checks, so nothing of it is linked here.  Checked against hashlib in tests/test_oracle_c.py.
+static inline uint32_t sha_rotr(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
+void oracle_sha256(const uint8_t* data, size_t len, uint8_t out[32]) {
+    static const uint32_t K[64] = {
+        0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5, 0xd807aa98, 0x12835b01, 0x243185be,
+        0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174, 0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa,
+        0x5cb0a9dc, 0x76f988da, 0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967, 0x27b70a85,
+        0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85, 0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3,
+        0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070, 0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f,
+        0x682e6ff3, 0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
+    uint32_t H[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+    // the message, a 0x80 byte, zeros up to 56 mod 64, the bit length as a big-endian u64
+    const size_t total = ((len + 8) / 64 + 1) * 64;
+    uint8_t tail[128];
+    const size_t tail_start = len / 64 * 64, tail_len = total - tail_start;
+    memset(tail, 0, sizeof tail);
+    memcpy(tail, data + tail_start, len - tail_start);
+    tail[len - tail_start] = 0x80;
+    const uint64_t bits = (uint64_t)len * 8;
+    for (int i = 0; i < 8; i++) tail[tail_len - 1 - i] = (uint8_t)(bits >> (8 * i));
+    for (size_t off = 0; off < total; off += 64) {
+        const uint8_t* blk = off < tail_start ? data + off : tail + (off - tail_start);
+        uint32_t w[64];
+        for (int t = 0; t < 16; t++) w[t] = ((uint32_t)blk[4 * t] << 24) | ((uint32_t)blk[4 * t + 1] << 16) | ((uint32_t)blk[4 * t + 2] << 8) | blk[4 * t + 3];
+        for (int t = 16; t < 64; t++) {
+            const uint32_t s0 = sha_rotr(w[t - 15], 7) ^ sha_rotr(w[t - 15], 18) ^ (w[t - 15] >> 3);
+            const uint32_t s1 = sha_rotr(w[t - 2], 17) ^ sha_rotr(w[t - 2], 19) ^ (w[t - 2] >> 10);
+            w[t] = w[t - 16] + s0 + w[t - 7] + s1;
+        }
+        uint32_t v[8];
+        memcpy(v, H, sizeof v);
+        for (int t = 0; t < 64; t++) {
+            const uint32_t S1 = sha_rotr(v[4], 6) ^ sha_rotr(v[4], 11) ^ sha_rotr(v[4], 25);
+            const uint32_t ch = (v[4] & v[5]) ^ (~v[4] & v[6]);
+            const uint32_t t1 = v[7] + S1 + ch + K[t] + w[t];
+            const uint32_t S0 = sha_rotr(v[0], 2) ^ sha_rotr(v[0], 13) ^ sha_rotr(v[0], 22);
+            const uint32_t mj = (v[0] & v[1]) ^ (v[0] & v[2]) ^ (v[1] & v[2]);
+            for (int i = 7; i > 0; i--) v[i] = v[i - 1];
+            v[4] += t1;
+            v[0] = t1 + S0 + mj;
+        }
+        for (int i = 0; i < 8; i++) H[i] += v[i];
+    }
+    for (int i = 0; i < 8; i++) { out[4 * i] = (uint8_t)(H[i] >> 24); out[4 * i + 1] = (uint8_t)(H[i] >> 16); out[4 * i + 2] = (uint8_t)(H[i] >> 8); out[4 * i + 3] = (uint8_t)H[i]; }
+}
 void serialize_compressed(const Aff& p, uint8_t out[32]) {  // arkworks layout (helpers.rs:458-460)
     memset(out, 0, 32);
     if (aff_inf(p)) { out[31] = 0x40; return; }
@@ -398,7 +443,7 @@ Fp compute_challenge(const std::vector<Fp>& evals, const Aff& commitment) {  // 
     for (size_t i = 0; i < n; i++) fp_to_be<FR>(evals[i], &buf[32 + 32 * i]);  // to_byte_array round trip (:448)
     serialize_compressed(commitment, &buf[32 + 32 * n]);
     uint8_t dg[32];
-    kzgb::sha256(buf.data(), buf.size(), dg);
+    oracle_sha256(buf.data(), buf.size(), dg);
     return fr_from_be(dg);
 }
 std::vector<Fp> roots_of_unity(size_t n) {  // helpers.rs:553-610
@@ -541,5 +586,6 @@ size_t ref_srs_decompress(const uint8_t* bytes, size_t n, int threads, uint64_t*
     return bad.load();
 }
 int ref_hw_threads() { return (int)std::thread::hardware_concurrency(); }
+void ref_sha256(const uint8_t* data, size_t len, uint8_t out[32]) { oracle_sha256(data, len, out); }
 
 }  // extern "C"

@@ -40,6 +40,20 @@ def fr_from(buf):
     return [int.from_bytes(buf[i : i + 32], "little") * ri % o.R for i in range(0, len(buf), 32)]
 
 
+def test_sha256_is_the_oracles_own_and_matches_hashlib(olib):
+    """The C++ oracle links nothing of the product: its SHA-256 is a plain FIPS 180-4 implementation of its own."""
+    import hashlib
+
+    rnd = random.Random(9)
+    for n in (0, 1, 55, 56, 63, 64, 65, 119, 120, 127, 128, 1000, 4096 + 17, 70001):
+        data = bytes(rnd.getrandbits(8) for _ in range(n))
+        out = C.create_string_buffer(32)
+        olib.ref_sha256(data, C.c_size_t(n), out)
+        assert out.raw == hashlib.sha256(data).digest(), n
+    mk = open(os.path.join(ROOT, "oracle", "Makefile")).read()
+    assert "rust-kzg-bn254_b200" not in mk.split("$(OUT):")[1]  # no product source in the oracle's build line
+
+
 def test_inverse(olib):
     rnd = random.Random(1)
     for mod, fn in ((o.R, olib.ref_fr_inv), (o.P, olib.ref_fq_inv)):
