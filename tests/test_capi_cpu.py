@@ -106,3 +106,27 @@ def test_no_cpu_fallback_without_gpu(pkg):
         pytest.skip("GPU present")
     with pytest.raises(pkg.KzgError):
         pkg.Engine(0)
+
+
+def test_bench_clock_sampler_addresses_visible_devices(monkeypatch):
+    """bench.py samples clocks through NVML / nvidia-smi, which enumerate every GPU of the box whatever CUDA_VISIBLE_DEVICES
+    says: CUDA ordinal i of the job must map to the i-th entry of the mask (index or UUID), and to i itself without a mask."""
+    import bench
+
+    monkeypatch.setenv("CUDA_VISIBLE_DEVICES", "3, 5,GPU-1234")
+    s = bench.ClockSampler(range(3))
+    assert s.targets == ["3", "5", "GPU-1234"]
+    assert bench.ClockSampler(1).targets == ["5"]
+    monkeypatch.delenv("CUDA_VISIBLE_DEVICES")
+    assert bench.ClockSampler(range(2)).targets == ["0", "1"]
+    empty = bench.ClockSampler([]).summary()
+    assert empty["samples"] == 0 and empty["reasons"] == [] and empty["sm_mhz"] is None
+
+
+def test_bench_payload_blob_distribution():
+    """D1 'payload' blobs: byte 0 of every 32-byte element is 0 (what Blob::from_raw_data yields), seeded."""
+    import bench
+
+    a, b = bench.make_blob(64, 7), bench.make_blob(64, 7)
+    assert a.shape == (64 * 32,) and (a == b).all() and (a.reshape(64, 32)[:, 0] == 0).all()
+    assert (bench.make_blob(64, 8) != a).any()
